@@ -1,0 +1,115 @@
+// Context management and shared host helpers of libcurate_b200 (C ABI in include/curate_b200.h).
+#include <cudaTypedefs.h>
+
+#include <cstring>
+
+#include "common.h"
+
+namespace cb {
+
+static std::mutex g_err_mu;
+static std::string g_last_error;
+
+void set_global_error(const char* msg) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_last_error = msg;
+}
+
+int fail(cb_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->last_error = buf;
+  set_global_error(buf);
+  return code;
+}
+
+int make_tensor_map(cb_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  if (!ctx->encode_tiled) return fail(ctx, CB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) gdim[i] = dims[i], bdim[i] = box[i], estr[i] = 1;
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = ctx->encode_tiled(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(ctx, CB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu box %u,%u stride0 %llu", (int)r, rank,
+                (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0,
+                (unsigned long long)(rank > 1 ? strides_bytes[0] : 0));
+  return CB_OK;
+}
+
+}  // namespace cb
+
+extern "C" {
+
+int cb_abi_version(void) { return CB_ABI_VERSION; }
+
+int cb_init(int device, cb_ctx** out) {
+  if (!out) return CB_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return cb::fail(nullptr, CB_ERR_CUDA, "no CUDA device (%s); libcurate_b200 has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return cb::fail(nullptr, CB_ERR_ARG, "device %d out of range (0..%d)", device, count - 1);
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return cb::fail(nullptr, CB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp p;
+  if ((e = cudaGetDeviceProperties(&p, device)) != cudaSuccess) return cb::fail(nullptr, CB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (p.major != 10)
+    return cb::fail(nullptr, CB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, p.major, p.minor);
+  cb_ctx* ctx = new cb_ctx();
+  ctx->device = device;
+  ctx->sm_count = p.multiProcessorCount;
+  ctx->cc_major = p.major, ctx->cc_minor = p.minor;
+  ctx->total_mem = p.totalGlobalMem;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+    delete ctx;
+    return cb::fail(nullptr, CB_ERR_CUDA, "cuTensorMapEncodeTiled not found in the driver");
+  }
+  ctx->encode_tiled = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  *out = ctx;
+  return CB_OK;
+}
+
+void cb_nvdec_release(cb_ctx* ctx);  // nvdec.cpp
+
+void cb_destroy(cb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cb_nvdec_release(ctx);
+  for (auto& kv : ctx->taps) {
+    cudaFree(kv.second.d_min);
+    cudaFree(kv.second.d_size);
+    cudaFree(kv.second.d_w);
+  }
+  if (ctx->d_norm_lut) cudaFree(ctx->d_norm_lut);
+  delete ctx;
+}
+
+const char* cb_last_error(cb_ctx* ctx) {
+  if (ctx) return ctx->last_error.c_str();
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(cb::g_err_mu);
+  copy = cb::g_last_error;
+  return copy.c_str();
+}
+
+int cb_device_info(cb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
+  if (!ctx) return CB_ERR_ARG;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (total_mem) *total_mem = ctx->total_mem;
+  return CB_OK;
+}
+
+unsigned long long cb_launch_count(cb_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// Shared host-side declarations for libcurate_b200: context, error plumbing, TMA descriptor encode.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/curate_b200.h"
+
+namespace cb {
+
+void set_global_error(const char* msg);
+
+struct TapTable {  // antialiased-bicubic tap table for one axis (device memory)
+  int in_size = 0, out_size = 0, crop_off = 0, crop_len = 0, max_taps = 0;
+  int src_begin = 0, src_end = 0;  // union of source indices touched by the cropped outputs
+  int* d_min = nullptr;            // [crop_len] first source index per output
+  int* d_size = nullptr;           // [crop_len] tap count per output
+  float* d_w = nullptr;            // [crop_len * max_taps] normalised weights
+  std::vector<int> h_min, h_size;
+};
+
+}  // namespace cb
+
+struct cb_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  size_t total_mem = 0;
+  std::string last_error;
+  std::mutex mu;
+  PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
+  std::map<std::tuple<int, int, int, int>, cb::TapTable> taps;  // (in, out, crop_off, crop_len)
+  float* d_norm_lut = nullptr;                                  // [3*256] fp32, normalise LUT currently loaded
+  float lut_mean[3] = {0, 0, 0}, lut_std[3] = {0, 0, 0};
+  unsigned long long launches = 0;  // kernels launched by this library (bench.py reports it)
+  void* nvdec = nullptr;            // lazily created NVDEC state (nvdec.cpp)
+};
+
+namespace cb {
+
+int fail(cb_ctx* ctx, int code, const char* fmt, ...);
+
+#define CB_CUDA(ctx, expr)                                                                                   \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess) return cb::fail(ctx, CB_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// 2-D / 3-D tiled tensor map (row pitch etc. in BYTES); returns CB_OK or an error code.
+int make_tensor_map(cb_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
+                    const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
+const TapTable* get_taps(cb_ctx* ctx, int in_size, int out_size, int crop_off, int crop_len);
+int ensure_norm_lut(cb_ctx* ctx, const float mean[3], const float std_[3], cudaStream_t stream);
+
+}  // namespace cb

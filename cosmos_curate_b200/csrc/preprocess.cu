@@ -1,0 +1,552 @@
+// Fused frame preprocess kernels (sm_100a).
+//
+//  clip_preprocess_kernel : NV12 (or RGB24) frame -> YUV->RGB u8 (OpenCV BT.601 fixed point) ->
+//      antialiased bicubic resize (ATen _upsample_bicubic2d_aa arithmetic, horizontal then vertical,
+//      fp32 FMA chains in tap order) -> centre crop -> clamp/round to u8 -> (v/255 - mean)/std LUT ->
+//      fp16/bf16/fp32, NCHW or patch-major rows for the tower's patch-embed GEMM.
+//      Replaces nvcodec_utils.py:178 + clip.py:48-62 of the reference in ONE pass over the source frame.
+//      Source strips are staged into shared memory by TMA (cp.async.bulk.tensor, mbarrier double buffer);
+//      a CTA owns one frame x one tile of output columns and walks down the source rows keeping a ring
+//      of horizontally filtered rows, so every source byte is fetched once per column tile.
+//  bilinear_u8_kernel     : NV12 -> RGB -> 4-tap bilinear (half-pixel centres) -> u8 HWC (27x48 frames).
+//  nv12_to_rgb_kernel     : full-resolution NV12 -> RGB24.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cb {
+
+// OpenCV ITUR_BT_601 fixed-point constants (shift 20)
+__device__ __forceinline__ void yuv_to_rgb(int y, int u, int v, int& r, int& g, int& b) {
+  const int yy = max(y - 16, 0) * 1220542;
+  u -= 128;
+  v -= 128;
+  r = (yy + (1 << 19) + 1673527 * v) >> 20;
+  g = (yy + (1 << 19) - 852492 * v - 409993 * u) >> 20;
+  b = (yy + (1 << 19) + 2116026 * u) >> 20;
+  r = min(max(r, 0), 255);
+  g = min(max(g, 0), 255);
+  b = min(max(b, 0), 255);
+}
+
+constexpr int kThreads = 256;
+constexpr int kSR = 32;  // source rows per strip (= lanes of a warp in the horizontal pass)
+
+struct ClipArgs {
+  const int* slots;  // device [n]
+  int n, src_w, src_h, res;
+  const int *xmin, *xsize, *ymin, *ysize;  // cropped tap tables, [res]
+  const float *wx, *wy;                    // [res][tx], [res][ty]
+  int tx, ty;
+  int y_begin, n_strips;  // first source row fetched (even), number of kSR-row strips
+  int tc;                 // output columns per CTA
+  int swa;                // strip width in pixels (multiple of 16)
+  int ring;               // ring rows (power of two >= kSR + ty)
+  const float* lut;       // [3][256]
+  int out_mode;           // 0 = u8 NCHW, 1 = typed NCHW, 2 = typed patch rows
+  int dtype, patch, k_pad;
+  void* out;
+};
+
+template <typename T>
+__device__ __forceinline__ T cvt_out(float v);
+template <>
+__device__ __forceinline__ __half cvt_out<__half>(float v) {
+  return __float2half_rn(v);
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+template <>
+__device__ __forceinline__ float cvt_out<float>(float v) {
+  return v;
+}
+
+__device__ __forceinline__ void store_typed(void* out, size_t idx, float v, int dtype) {
+  if (dtype == CB_DT_F16) ((__half*)out)[idx] = __float2half_rn(v);
+  else if (dtype == CB_DT_BF16) ((__nv_bfloat16*)out)[idx] = __float2bfloat16_rn(v);
+  else ((float*)out)[idx] = v;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreads) clip_preprocess_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                     const __grid_constant__ CUtensorMap map_b, const ClipArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = blockIdx.y;
+  const int c0 = blockIdx.x * a.tc;
+  const int ncol = min(a.tc, a.res - c0);
+  const int slot = a.slots[frame];
+
+  // ---- shared memory carve-up
+  const int raw_stage = (FMT == CB_FMT_NV12) ? (a.swa * kSR + a.swa * (kSR / 2)) : (3 * a.swa * kSR);
+  const int swp = a.swa + 1;  // odd pitch: lanes walk rows without bank conflicts
+  const int tcp = a.tc | 1;
+  uint8_t* raw = smem;                                                  // [2][raw_stage]
+  float* rgbf = (float*)(smem + 2 * raw_stage);                         // [3][kSR][swp]
+  float* ringb = rgbf + 3 * kSR * swp;                                  // [3][ring][tcp]
+  uint16_t* obuf = (uint16_t*)(ringb + 3 * a.ring * tcp);               // patch staging [tc/patch][k_pad]
+  const int npx = (a.out_mode == 2) ? a.tc / a.patch : 0;
+  uint64_t* bars = (uint64_t*)(((uintptr_t)(obuf + npx * a.k_pad) + 7) & ~(uintptr_t)7);
+
+  // source columns this tile touches
+  int x_lo = a.xmin[c0];
+  if (FMT == CB_FMT_NV12) x_lo &= ~1;
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  if (a.out_mode == 2)
+    for (int i = tid; i < npx * a.k_pad; i += kThreads) obuf[i] = 0;  // zero K padding once
+  __syncthreads();
+
+  auto issue = [&](int s) {
+    uint8_t* dst = raw + (s & 1) * raw_stage;
+    uint64_t* bar = &bars[s & 1];
+    const int y0 = a.y_begin + s * kSR;
+    mbar_expect_tx(bar, raw_stage);
+    if (FMT == CB_FMT_NV12) {
+      tma_load_3d(dst, &map_a, bar, x_lo, y0, slot);
+      tma_load_3d(dst + a.swa * kSR, &map_b, bar, x_lo, y0 >> 1, slot);
+    } else {
+      for (int k = 0; k < 3; ++k) tma_load_3d(dst + k * a.swa * kSR, &map_a, bar, x_lo * 3 + k * a.swa, y0, slot);
+    }
+  };
+  if (tid == 0) {
+    issue(0);
+    if (a.n_strips > 1) issue(1);
+  }
+
+  int next_out = 0;  // next output row to emit
+  for (int s = 0; s < a.n_strips; ++s) {
+    const int y0 = a.y_begin + s * kSR;
+    const uint8_t* rs = raw + (s & 1) * raw_stage;
+    mbar_wait(&bars[s & 1], (s >> 1) & 1);
+
+    // ---- phase 1: colour convert the strip to planar fp32 RGB (values are exact u8 integers)
+    if (FMT == CB_FMT_NV12) {
+      const int half_w = a.swa >> 1;
+      const uint8_t* ry = rs;
+      const uint8_t* ruv = rs + a.swa * kSR;
+      for (int i = tid; i < kSR * half_w; i += kThreads) {
+        const int r = i / half_w, x = (i - r * half_w) * 2;
+        const uchar2 yy = *(const uchar2*)(ry + r * a.swa + x);
+        const uchar2 uv = *(const uchar2*)(ruv + (r >> 1) * a.swa + x);
+        int R, G, B;
+        float* p = rgbf + r * swp + x;
+        yuv_to_rgb(yy.x, uv.x, uv.y, R, G, B);
+        p[0] = (float)R, p[kSR * swp] = (float)G, p[2 * kSR * swp] = (float)B;
+        yuv_to_rgb(yy.y, uv.x, uv.y, R, G, B);
+        p[1] = (float)R, p[kSR * swp + 1] = (float)G, p[2 * kSR * swp + 1] = (float)B;
+      }
+    } else {
+      for (int i = tid; i < kSR * a.swa; i += kThreads) {
+        const int r = i / a.swa, x = i - r * a.swa;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const int b = 3 * x + ch;
+          const int blk = b / a.swa, within = b - blk * a.swa;
+          rgbf[(ch * kSR + r) * swp + x] = (float)rs[(blk * kSR + r) * a.swa + within];
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && s + 2 < a.n_strips) {
+      fence_proxy_async();  // generic-proxy reads of this stage are done; hand it back to the TMA
+      issue(s + 2);
+    }
+
+    // ---- phase 2: horizontal filter; lane = source row of the strip, (column, channel) uniform per warp
+    for (int item = warp; item < ncol * 3; item += kThreads / 32) {
+      const int c = item / 3, ch = item - c * 3;
+      const int xs = a.xsize[c0 + c];
+      const float* w = a.wx + (size_t)(c0 + c) * a.tx;
+      const float* src = rgbf + (ch * kSR + lane) * swp + (a.xmin[c0 + c] - x_lo);
+      float acc = src[0] * __ldg(w);
+      for (int j = 1; j < xs; ++j) acc = fmaf(src[j], __ldg(w + j), acc);
+      ringb[(ch * a.ring + ((y0 + lane) & (a.ring - 1))) * tcp + c] = acc;
+    }
+    __syncthreads();
+
+    // ---- phase 3: emit every output row whose vertical window is now complete
+    int last = next_out;
+    const bool final_strip = (s == a.n_strips - 1);
+    while (last < a.res && (final_strip || a.ymin[last] + a.ysize[last] <= y0 + kSR)) ++last;
+    for (int yo = next_out; yo < last; ++yo) {
+      const int ym = a.ymin[yo], ys = a.ysize[yo];
+      const float* w = a.wy + (size_t)yo * a.ty;
+      for (int item = tid; item < ncol * 3; item += kThreads) {
+        const int ch = item / ncol, c = item - ch * ncol;
+        const float* rb = ringb + (size_t)ch * a.ring * tcp + c;
+        float acc = rb[(ym & (a.ring - 1)) * tcp] * __ldg(w);
+        for (int k = 1; k < ys; ++k) acc = fmaf(rb[((ym + k) & (a.ring - 1)) * tcp], __ldg(w + k), acc);
+        acc = fminf(fmaxf(acc, 0.f), 255.f);
+        const int v = __float2int_rn(acc);  // round half to even == torch.round
+        const int x = c0 + c;
+        if (a.out_mode == 0) {
+          ((uint8_t*)a.out)[(((size_t)frame * 3 + ch) * a.res + yo) * a.res + x] = (uint8_t)v;
+        } else {
+          const float f = a.lut[ch * 256 + v];
+          if (a.out_mode == 1) {
+            store_typed(a.out, (((size_t)frame * 3 + ch) * a.res + yo) * a.res + x, f, a.dtype);
+          } else {
+            const int ip = c / a.patch, px = c - ip * a.patch, py = yo % a.patch;
+            const uint16_t bits = (a.dtype == CB_DT_F16) ? __half_as_ushort(__float2half_rn(f))
+                                                         : __bfloat16_as_ushort(__float2bfloat16_rn(f));
+            obuf[ip * a.k_pad + (ch * a.patch + py) * a.patch + px] = bits;
+          }
+        }
+      }
+      if (a.out_mode == 2 && (yo % a.patch) == a.patch - 1) {  // a row of patches is complete: 128-bit stores
+        __syncthreads();
+        const int g = a.res / a.patch, prow = yo / a.patch, vec = a.k_pad >> 3;
+        const int np = ncol / a.patch;
+        for (int i = tid; i < np * vec; i += kThreads) {
+          const int ip = i / vec, q = i - ip * vec;
+          uint4* dst = (uint4*)((uint16_t*)a.out + ((size_t)frame * g * g + (size_t)prow * g + (c0 / a.patch + ip)) * a.k_pad);
+          dst[q] = ((const uint4*)(obuf + ip * a.k_pad))[q];
+        }
+        __syncthreads();
+      }
+    }
+    next_out = last;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct SimpleArgs {
+  const uint8_t* base;
+  size_t slot_stride;
+  const int* slots;
+  int n, w, h, pitch, luma_rows, out_w, out_h;
+  uint8_t* out;
+};
+
+__device__ __forceinline__ void fetch_rgb_nv12(const uint8_t* f, int pitch, int luma_rows, int x, int y, int& r, int& g, int& b) {
+  const int Y = f[(size_t)y * pitch + x];
+  const uint8_t* uv = f + (size_t)luma_rows * pitch + (size_t)(y >> 1) * pitch + (x & ~1);
+  yuv_to_rgb(Y, uv[0], uv[1], r, g, b);
+}
+
+// cvcuda.resize_into(LINEAR) semantics: half-pixel centres, clamp-to-edge taps, fp32, round-to-nearest-even.
+__global__ void bilinear_u8_kernel(const SimpleArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = a.out_w * a.out_h;
+  if (i >= a.n * per) return;
+  const int f = i / per, p = i - f * per, yo = p / a.out_w, xo = p - yo * a.out_w;
+  const uint8_t* fr = a.base + (size_t)a.slots[f] * a.slot_stride;
+  const float sx = (float)a.w / (float)a.out_w, sy = (float)a.h / (float)a.out_h;
+  const float fx = (xo + 0.5f) * sx - 0.5f, fy = (yo + 0.5f) * sy - 0.5f;
+  const int x0 = (int)floorf(fx), y0 = (int)floorf(fy);
+  const float wx = fx - (float)x0, wy = fy - (float)y0;
+  const int xa = min(max(x0, 0), a.w - 1), xb = min(max(x0 + 1, 0), a.w - 1);
+  const int ya = min(max(y0, 0), a.h - 1), yb = min(max(y0 + 1, 0), a.h - 1);
+  int p00[3], p01[3], p10[3], p11[3];
+  fetch_rgb_nv12(fr, a.pitch, a.luma_rows, xa, ya, p00[0], p00[1], p00[2]);
+  fetch_rgb_nv12(fr, a.pitch, a.luma_rows, xb, ya, p01[0], p01[1], p01[2]);
+  fetch_rgb_nv12(fr, a.pitch, a.luma_rows, xa, yb, p10[0], p10[1], p10[2]);
+  fetch_rgb_nv12(fr, a.pitch, a.luma_rows, xb, yb, p11[0], p11[1], p11[2]);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float top = __fadd_rn(__fmul_rn((float)p00[ch], 1.f - wx), __fmul_rn((float)p01[ch], wx));
+    const float bot = __fadd_rn(__fmul_rn((float)p10[ch], 1.f - wx), __fmul_rn((float)p11[ch], wx));
+    float v = __fadd_rn(__fmul_rn(top, 1.f - wy), __fmul_rn(bot, wy));
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    a.out[(size_t)i * 3 + ch] = (uint8_t)__float2int_rn(v);
+  }
+}
+
+__global__ void nv12_to_rgb_kernel(const SimpleArgs a) {
+  // one thread per horizontal pixel pair; out tightly packed [n][h][w][3]
+  const int pairs_w = (a.w + 1) >> 1;
+  const size_t per = (size_t)pairs_w * a.h;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per * a.n) return;
+  const int f = (int)(i / per);
+  const size_t p = i - (size_t)f * per;
+  const int y = (int)(p / pairs_w), x = (int)(p - (size_t)y * pairs_w) * 2;
+  const uint8_t* fr = a.base + (size_t)a.slots[f] * a.slot_stride;
+  const uint8_t* uv = fr + (size_t)a.luma_rows * a.pitch + (size_t)(y >> 1) * a.pitch + x;
+  const int U = uv[0], V = uv[1];
+  uint8_t* o = a.out + (((size_t)f * a.h + y) * a.w + x) * 3;
+  int r, g, b;
+  yuv_to_rgb(fr[(size_t)y * a.pitch + x], U, V, r, g, b);
+  o[0] = r, o[1] = g, o[2] = b;
+  if (x + 1 < a.w) {
+    yuv_to_rgb(fr[(size_t)y * a.pitch + x + 1], U, V, r, g, b);
+    o[3] = r, o[4] = g, o[5] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static float cubic_aa(float x) {  // Keys a = -0.5, float32 like ATen's bicubic_filter
+  const float a = -0.5f;
+  if (x < 0.f) x = -x;
+  if (x < 1.f) return ((a + 2.f) * x - (a + 3.f)) * x * x + 1.f;
+  if (x < 2.f) return (((x - 5.f) * x + 8.f) * x - 4.f) * a;
+  return 0.f;
+}
+
+const TapTable* get_taps(cb_ctx* ctx, int in_size, int out_size, int crop_off, int crop_len) {
+  auto key = std::make_tuple(in_size, out_size, crop_off, crop_len);
+  auto it = ctx->taps.find(key);
+  if (it != ctx->taps.end()) return &it->second;
+  TapTable t;
+  t.in_size = in_size, t.out_size = out_size, t.crop_off = crop_off, t.crop_len = crop_len;
+  // ATen upsample_antialias::_compute_weights_span / _compute_weights in float32 (see oracle/preprocess.py)
+  volatile float scale = (float)in_size / (float)out_size;
+  const float support = (scale >= 1.f) ? 2.0f * scale : 2.0f;
+  const float invscale = (scale >= 1.f) ? 1.0f / scale : 1.0f;
+  t.h_min.resize(crop_len), t.h_size.resize(crop_len);
+  std::vector<std::vector<float>> w(crop_len);
+  t.src_begin = in_size, t.src_end = 0;
+  for (int o = 0; o < crop_len; ++o) {
+    const int i = o + crop_off;
+    volatile float center = scale * ((float)i + 0.5f);
+    volatile float lo = center - support;
+    volatile float hi = center + support;
+    const int xmin = std::max((int)(lo + 0.5f), 0);
+    const int xsize = std::min((int)(hi + 0.5f), in_size) - xmin;
+    volatile float xmin_m_center = (float)xmin - center;
+    volatile float total = 0.f;
+    w[o].resize(xsize);
+    for (int j = 0; j < xsize; ++j) {
+      volatile float arg = ((float)j + xmin_m_center + 0.5f);
+      arg = arg * invscale;
+      const float wv = cubic_aa(arg);
+      w[o][j] = wv;
+      total = total + wv;
+    }
+    if (total != 0.f)
+      for (int j = 0; j < xsize; ++j) w[o][j] = w[o][j] / total;
+    t.h_min[o] = xmin, t.h_size[o] = xsize;
+    t.max_taps = std::max(t.max_taps, xsize);
+    t.src_begin = std::min(t.src_begin, xmin);
+    t.src_end = std::max(t.src_end, xmin + xsize);
+  }
+  std::vector<float> flat((size_t)crop_len * t.max_taps, 0.f);
+  for (int o = 0; o < crop_len; ++o) std::copy(w[o].begin(), w[o].end(), flat.begin() + (size_t)o * t.max_taps);
+  if (cudaMalloc(&t.d_min, crop_len * sizeof(int)) != cudaSuccess || cudaMalloc(&t.d_size, crop_len * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&t.d_w, flat.size() * sizeof(float)) != cudaSuccess)
+    return nullptr;
+  cudaMemcpy(t.d_min, t.h_min.data(), crop_len * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(t.d_size, t.h_size.data(), crop_len * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(t.d_w, flat.data(), flat.size() * sizeof(float), cudaMemcpyHostToDevice);
+  auto res = ctx->taps.emplace(key, std::move(t));
+  return &res.first->second;
+}
+
+int ensure_norm_lut(cb_ctx* ctx, const float mean[3], const float std_[3], cudaStream_t stream) {
+  bool same = ctx->d_norm_lut != nullptr;
+  for (int c = 0; c < 3 && same; ++c) same = ctx->lut_mean[c] == mean[c] && ctx->lut_std[c] == std_[c];
+  if (same) return CB_OK;
+  if (!ctx->d_norm_lut) CB_CUDA(ctx, cudaMalloc(&ctx->d_norm_lut, 3 * 256 * sizeof(float)));
+  float lut[3 * 256];
+  for (int c = 0; c < 3; ++c)
+    for (int v = 0; v < 256; ++v) {
+      volatile float x = (float)v / 255.0f;  // ConvertImageDtype: u8 -> float32 then / 255
+      volatile float d = x - mean[c];        // Normalize: sub_ then div_
+      lut[c * 256 + v] = d / std_[c];
+    }
+  // synchronous copy on the caller's stream order: the table is tiny and rarely changes
+  CB_CUDA(ctx, cudaMemcpyAsync(ctx->d_norm_lut, lut, sizeof(lut), cudaMemcpyHostToDevice, stream));
+  CB_CUDA(ctx, cudaStreamSynchronize(stream));
+  for (int c = 0; c < 3; ++c) ctx->lut_mean[c] = mean[c], ctx->lut_std[c] = std_[c];
+  return CB_OK;
+}
+
+static int python_round_half_even(double v) { return (int)std::nearbyint(v); }  // default FE_TONEAREST
+
+struct SlotBuf {  // small device staging of the slot list (grows as needed)
+  int* d = nullptr;
+  int cap = 0;
+};
+static SlotBuf g_slots;
+
+static int upload_slots(cb_ctx* ctx, const int32_t* slots, int n, cudaStream_t stream, const int** out) {
+  if (g_slots.cap < n) {
+    if (g_slots.d) cudaFree(g_slots.d);
+    g_slots.cap = std::max(1024, n);
+    CB_CUDA(ctx, cudaMalloc(&g_slots.d, g_slots.cap * sizeof(int)));
+  }
+  CB_CUDA(ctx, cudaMemcpyAsync(g_slots.d, slots, n * sizeof(int), cudaMemcpyHostToDevice, stream));
+  *out = g_slots.d;
+  return CB_OK;
+}
+
+static int check_pool(cb_ctx* ctx, const cb_surface_pool* pool, int n, const int32_t* slots) {
+  if (!ctx) return CB_ERR_ARG;
+  if (!pool || !pool->base || n < 0 || (n > 0 && !slots)) return fail(ctx, CB_ERR_ARG, "null pool/slots");
+  if (pool->format != CB_FMT_NV12 && pool->format != CB_FMT_RGB24) return fail(ctx, CB_ERR_ARG, "unknown surface format %d", pool->format);
+  if (pool->width <= 0 || pool->height <= 0) return fail(ctx, CB_ERR_ARG, "bad surface size %dx%d", pool->width, pool->height);
+  const int min_pitch = pool->format == CB_FMT_NV12 ? pool->width : 3 * pool->width;
+  if (pool->pitch < min_pitch) return fail(ctx, CB_ERR_ARG, "pitch %d < row bytes %d", pool->pitch, min_pitch);
+  if (pool->format == CB_FMT_NV12 && pool->luma_rows < pool->height) return fail(ctx, CB_ERR_ARG, "luma_rows < height");
+  for (int i = 0; i < n; ++i)
+    if (slots[i] < 0) return fail(ctx, CB_ERR_ARG, "negative slot index");
+  return CB_OK;
+}
+
+int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int res, int out_mode, int layout_patch,
+                        int k_pad, int dtype, const float mean[3], const float std_[3], void* out, cudaStream_t stream) {
+  int rc = check_pool(ctx, pool, n, slots);
+  if (rc) return rc;
+  if (n == 0) return CB_OK;
+  if (!out) return fail(ctx, CB_ERR_ARG, "null output");
+  if (res <= 0 || res > 1024) return fail(ctx, CB_ERR_ARG, "bad output resolution %d", res);
+  if (((uintptr_t)pool->base & 15) || (pool->pitch & 15) || (pool->slot_stride & 15))
+    return fail(ctx, CB_ERR_ARG, "TMA needs base/pitch/slot_stride multiples of 16 bytes");
+  if (pool->format == CB_FMT_NV12 && ((pool->width | pool->height) & 1)) return fail(ctx, CB_ERR_UNSUPPORTED, "NV12 needs even dimensions");
+  const int W = pool->width, H = pool->height;
+  // torchvision: short side -> res, long side -> int(res * long / short); centre crop res x res
+  int new_w, new_h;
+  if (W <= H) new_w = res, new_h = (int)((long long)res * H / W);
+  else new_h = res, new_w = (int)((long long)res * W / H);
+  const int top = python_round_half_even((new_h - res) / 2.0), left = python_round_half_even((new_w - res) / 2.0);
+  const TapTable* tx = get_taps(ctx, W, new_w, left, res);
+  const TapTable* ty = get_taps(ctx, H, new_h, top, res);
+  if (!tx || !ty) return fail(ctx, CB_ERR_CUDA, "tap table allocation failed");
+
+  ClipArgs a{};
+  a.n = n, a.src_w = W, a.src_h = H, a.res = res;
+  a.xmin = tx->d_min, a.xsize = tx->d_size, a.wx = tx->d_w, a.tx = tx->max_taps;
+  a.ymin = ty->d_min, a.ysize = ty->d_size, a.wy = ty->d_w, a.ty = ty->max_taps;
+  a.out_mode = out_mode, a.dtype = dtype, a.patch = layout_patch, a.k_pad = k_pad, a.out = out;
+  if (out_mode == 2) {
+    if (layout_patch <= 0 || layout_patch > 32 || res % layout_patch) return fail(ctx, CB_ERR_UNSUPPORTED, "patch %d unsupported for res %d", layout_patch, res);
+    if (k_pad < 3 * layout_patch * layout_patch || (k_pad & 7)) return fail(ctx, CB_ERR_ARG, "k_pad %d must be >= 3*p*p and a multiple of 8", k_pad);
+    if (dtype != CB_DT_F16 && dtype != CB_DT_BF16) return fail(ctx, CB_ERR_ARG, "patch layout needs a 16-bit dtype");
+    a.tc = layout_patch * (32 / layout_patch);
+  } else {
+    a.tc = 32;
+  }
+  a.y_begin = ty->src_begin & ~1;
+  a.n_strips = (ty->src_end - a.y_begin + kSR - 1) / kSR;
+  int ring = 64;
+  while (ring < kSR + ty->max_taps) ring <<= 1;
+  a.ring = ring;
+  // widest source span of any column tile
+  int span = 0;
+  const int tiles = (res + a.tc - 1) / a.tc;
+  for (int t = 0; t < tiles; ++t) {
+    const int c0 = t * a.tc, c1 = std::min(res, c0 + a.tc);
+    int lo = tx->h_min[c0], hi = 0;
+    if (pool->format == CB_FMT_NV12) lo &= ~1;
+    for (int c = c0; c < c1; ++c) hi = std::max(hi, tx->h_min[c] + tx->h_size[c]);
+    span = std::max(span, hi - lo);
+  }
+  a.swa = (span + 15) & ~15;
+  if (a.swa > 256) return fail(ctx, CB_ERR_UNSUPPORTED, "downscale too large for one TMA box (%d source columns per tile)", a.swa);
+
+  rc = ensure_norm_lut(ctx, mean, std_, stream);
+  if (rc) return rc;
+  a.lut = ctx->d_norm_lut;
+  rc = upload_slots(ctx, slots, n, stream, &a.slots);
+  if (rc) return rc;
+
+  int max_slot = 0;
+  for (int i = 0; i < n; ++i) max_slot = std::max(max_slot, (int)slots[i]);
+  CUtensorMap map_a, map_b;
+  if (pool->format == CB_FMT_NV12) {
+    uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)max_slot + 1};
+    uint64_t strides[2] = {(uint64_t)pool->pitch, (uint64_t)pool->slot_stride};
+    uint32_t box[3] = {(uint32_t)a.swa, (uint32_t)kSR, 1};
+    rc = make_tensor_map(ctx, &map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pool->base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    uint64_t dims_uv[3] = {(uint64_t)W, (uint64_t)(H / 2), (uint64_t)max_slot + 1};
+    uint32_t box_uv[3] = {(uint32_t)a.swa, (uint32_t)(kSR / 2), 1};
+    rc = make_tensor_map(ctx, &map_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (const uint8_t*)pool->base + (size_t)pool->luma_rows * pool->pitch,
+                         dims_uv, strides, box_uv, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+  } else {
+    uint64_t dims[3] = {(uint64_t)W * 3, (uint64_t)H, (uint64_t)max_slot + 1};
+    uint64_t strides[2] = {(uint64_t)pool->pitch, (uint64_t)pool->slot_stride};
+    uint32_t box[3] = {(uint32_t)a.swa, (uint32_t)kSR, 1};
+    rc = make_tensor_map(ctx, &map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pool->base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    map_b = map_a;
+  }
+
+  const int raw_stage = (pool->format == CB_FMT_NV12) ? (a.swa * kSR * 3 / 2) : (3 * a.swa * kSR);
+  const int npx = out_mode == 2 ? a.tc / a.patch : 0;
+  size_t smem = 2 * (size_t)raw_stage + (size_t)3 * kSR * (a.swa + 1) * 4 + (size_t)3 * a.ring * (a.tc | 1) * 4 + (size_t)npx * k_pad * 2 + 32;
+  if (smem > 227 * 1024) return fail(ctx, CB_ERR_UNSUPPORTED, "preprocess tile needs %zu bytes of shared memory", smem);
+  dim3 grid(tiles, n);
+  if (pool->format == CB_FMT_NV12) {
+    CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_kernel<CB_FMT_NV12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    clip_preprocess_kernel<CB_FMT_NV12><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
+  } else {
+    CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_kernel<CB_FMT_RGB24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    clip_preprocess_kernel<CB_FMT_RGB24><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
+  }
+  ctx->launches++;
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
+}
+
+static int run_simple(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int out_w, int out_h, uint8_t* out, bool bilinear,
+                      cudaStream_t stream) {
+  int rc = check_pool(ctx, pool, n, slots);
+  if (rc) return rc;
+  if (n == 0) return CB_OK;
+  if (!out) return fail(ctx, CB_ERR_ARG, "null output");
+  if (pool->format != CB_FMT_NV12) return fail(ctx, CB_ERR_UNSUPPORTED, "NV12 surfaces only");
+  SimpleArgs a{};
+  a.base = (const uint8_t*)pool->base, a.slot_stride = pool->slot_stride;
+  a.n = n, a.w = pool->width, a.h = pool->height, a.pitch = pool->pitch, a.luma_rows = pool->luma_rows;
+  a.out_w = out_w, a.out_h = out_h, a.out = out;
+  rc = upload_slots(ctx, slots, n, stream, &a.slots);
+  if (rc) return rc;
+  if (bilinear) {
+    if (out_w <= 0 || out_h <= 0) return fail(ctx, CB_ERR_ARG, "bad output size");
+    const long long total = (long long)n * out_w * out_h;
+    bilinear_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
+  } else {
+    const long long total = (long long)n * a.h * ((a.w + 1) / 2);
+    nv12_to_rgb_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
+  }
+  ctx->launches++;
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
+}
+
+}  // namespace cb
+
+extern "C" {
+
+int cb_preprocess_clip(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int res, int layout, int patch, int k_pad,
+                       int dtype, const float mean[3], const float std_[3], void* out, void* stream) {
+  if (!ctx) return CB_ERR_ARG;
+  if (!mean || !std_) return cb::fail(ctx, CB_ERR_ARG, "null mean/std");
+  if (layout != CB_LAYOUT_NCHW && layout != CB_LAYOUT_PATCH) return cb::fail(ctx, CB_ERR_ARG, "unknown layout %d", layout);
+  if (dtype < CB_DT_F16 || dtype > CB_DT_F32) return cb::fail(ctx, CB_ERR_ARG, "unknown dtype %d", dtype);
+  return cb::run_clip_preprocess(ctx, pool, slots, n, res, layout == CB_LAYOUT_PATCH ? 2 : 1, patch, k_pad, dtype, mean, std_, out,
+                                 (cudaStream_t)stream);
+}
+
+int cb_preprocess_clip_u8(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int res, uint8_t* out, void* stream) {
+  if (!ctx) return CB_ERR_ARG;
+  const float m[3] = {0, 0, 0}, s[3] = {1, 1, 1};
+  return cb::run_clip_preprocess(ctx, pool, slots, n, res, 0, 0, 0, CB_DT_F32, m, s, out, (cudaStream_t)stream);
+}
+
+int cb_preprocess_bilinear_u8(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int out_w, int out_h, uint8_t* out,
+                              void* stream) {
+  if (!ctx) return CB_ERR_ARG;
+  return cb::run_simple(ctx, pool, slots, n, out_w, out_h, out, true, (cudaStream_t)stream);
+}
+
+int cb_nv12_to_rgb(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, uint8_t* out, void* stream) {
+  if (!ctx) return CB_ERR_ARG;
+  return cb::run_simple(ctx, pool, slots, n, 0, 0, out, false, (cudaStream_t)stream);
+}
+
+}  // extern "C"

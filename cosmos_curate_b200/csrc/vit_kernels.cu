@@ -1,0 +1,397 @@
+// Non-GEMM kernels of the image tower (sm_100a): LayerNorm, token assembly, attention, pooled tail.
+//   layernorm_kernel       fp32 residual stream -> fp16 normalised activations (HBM-bound: 6 B/element)
+//   assemble_kernel        patch-embed output + [CLS] + position embedding (+ CLIP pre_layrnorm) -> residual stream
+//   attention_kernel       softmax(Q K^T / sqrt(d)) V per (image, head); K/V resident in shared memory,
+//                          mma.sync m16n8k16 with fp32 online softmax (4 % of the tower's FLOPs; the dense
+//                          Linear layers are the tcgen05 kernel in gemm.cu)
+//   clip_tail_kernel       post_layernorm(CLS) -> visual_projection -> L2 normalise -> aesthetic affine head
+#include <cuda_fp16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------- LayerNorm
+// One warp per row; D <= 32*4*kMaxChunks.  Two-pass statistics in registers (mean, then centred variance).
+constexpr int kLnMaxChunks = 12;  // D <= 1536
+
+template <bool OUT_F16>
+__device__ __forceinline__ void ln_row(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       void* __restrict__ y, int d, float eps, int lane, const float* __restrict__ add = nullptr) {
+  float4 v[kLnMaxChunks];
+  const int chunks = d >> 7;  // 128 floats per warp pass
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i)
+    if (i < chunks) {
+      v[i] = ((const float4*)x)[lane + 32 * i];
+      if (add) {
+        const float4 a = __ldg((const float4*)add + lane + 32 * i);
+        v[i].x += a.x, v[i].y += a.y, v[i].z += a.z, v[i].w += a.w;
+      }
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  const float mean = warp_sum(s) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i)
+    if (i < chunks) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + e * e);
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+#pragma unroll
+  for (int i = 0; i < kLnMaxChunks; ++i)
+    if (i < chunks) {
+      const float4 g = __ldg((const float4*)gamma + lane + 32 * i), b = __ldg((const float4*)beta + lane + 32 * i);
+      const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
+      const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
+      if (OUT_F16) {
+        const __half2 h0 = __floats2half2_rn(o0, o1), h1 = __floats2half2_rn(o2, o3);
+        uint2 o;
+        o.x = *(const uint32_t*)&h0, o.y = *(const uint32_t*)&h1;
+        ((uint2*)y)[lane + 32 * i] = o;
+      } else {
+        ((float4*)y)[lane + 32 * i] = make_float4(o0, o1, o2, o3);
+      }
+    }
+}
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __half* __restrict__ y, int rows, int d, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  ln_row<true>(x + (size_t)row * d, gamma, beta, y + (size_t)row * d, d, eps, threadIdx.x & 31);
+}
+
+// ------------------------------------------------------------------------------- token assembly
+// CLIP  : h[n][0] = LN(cls + pos[0]); h[n][1+i] = LN(patch[n][i] + pos[1+i])     (pre_layrnorm)
+// SigLIP: h[n][i] = patch[n][i] + pos[i]                                          (patch bias is in the GEMM)
+__global__ void __launch_bounds__(256) assemble_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+                                                       const float* __restrict__ pos, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float* __restrict__ h, int n, int tokens, int grid2,
+                                                       int d, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n * tokens) return;
+  const int img = row / tokens, t = row - img * tokens;
+  const bool has_cls = tokens != grid2;
+  const float* src = (has_cls && t == 0) ? cls : patch + ((size_t)img * grid2 + (t - (has_cls ? 1 : 0))) * d;
+  const float* p = pos + (size_t)t * d;
+  float* dst = h + (size_t)row * d;
+  if (gamma) {
+    ln_row<false>(src, gamma, beta, dst, d, eps, lane, p);
+  } else {
+    for (int i = lane; i < (d >> 2); i += 32) {
+      float4 a = ((const float4*)src)[i];
+      const float4 b = __ldg((const float4*)p + i);
+      a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+      ((float4*)dst)[i] = a;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ attention
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *(const uint32_t*)&h;
+}
+
+constexpr int kAttnWarps = 9;
+constexpr int kAttnThreads = kAttnWarps * 32;
+
+// HD: head dim padded to a multiple of 16 (64 -> 64, 72 -> 80).  One CTA per (image, head).
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int tokens,
+                                                                     int heads, int head_dim, float scale_log2e) {
+  constexpr int PITCH = HD + 8;  // halves; 16-byte row skew keeps ldmatrix conflict-free
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  const int t_pad = (tokens + 15) & ~15;
+  __half* sK = (__half*)smem_attn;
+  __half* sV = sK + (size_t)t_pad * PITCH;
+  const int img = blockIdx.x / heads, head = blockIdx.x - img * heads;
+  const int hidden = heads * head_dim;
+  const size_t row_stride = (size_t)3 * hidden;
+  const __half* base = qkv + (size_t)img * tokens * row_stride + (size_t)head * head_dim;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+
+  // K and V (zero padded in both directions) -> shared memory, 16-byte vectors
+  constexpr int VEC = HD / 8;
+  const int vec_valid = head_dim / 8;  // head_dim % 8 == 0 is checked on the host
+  for (int i = threadIdx.x; i < t_pad * VEC; i += kAttnThreads) {
+    const int r = i / VEC, c = i - r * VEC;
+    uint4 k4 = make_uint4(0, 0, 0, 0), v4 = make_uint4(0, 0, 0, 0);
+    if (r < tokens && c < vec_valid) {
+      const __half* p = base + (size_t)r * row_stride + c * 8;
+      k4 = *(const uint4*)(p + hidden);
+      v4 = *(const uint4*)(p + 2 * hidden);
+    }
+    *(uint4*)(sK + (size_t)r * PITCH + c * 8) = k4;
+    *(uint4*)(sV + (size_t)r * PITCH + c * 8) = v4;
+  }
+  __syncthreads();
+
+  const int q_tiles = t_pad >> 4;
+  for (int qt = warp; qt < q_tiles; qt += kAttnWarps) {
+    // Q fragments straight from global memory (rows clamped; padded columns read as zero)
+    uint32_t qa[HD / 16][4];
+    const int r0 = min(qt * 16 + g, tokens - 1), r1 = min(qt * 16 + g + 8, tokens - 1);
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks) {
+      const int c0 = ks * 16 + t4 * 2, c1 = c0 + 8;
+      qa[ks][0] = c0 < head_dim ? *(const uint32_t*)(base + (size_t)r0 * row_stride + c0) : 0u;
+      qa[ks][1] = c0 < head_dim ? *(const uint32_t*)(base + (size_t)r1 * row_stride + c0) : 0u;
+      qa[ks][2] = c1 < head_dim ? *(const uint32_t*)(base + (size_t)r0 * row_stride + c1) : 0u;
+      qa[ks][3] = c1 < head_dim ? *(const uint32_t*)(base + (size_t)r1 * row_stride + c1) : 0u;
+    }
+    float o[HD / 8][4];
+#pragma unroll
+    for (int d = 0; d < HD / 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // running max / sum for rows g and g+8
+
+    for (int kc = 0; kc < t_pad; kc += 64) {  // 64 keys per step (t_pad is a multiple of 16)
+      const int nkt = min(8, (t_pad - kc) >> 3);  // 8-key tiles in this chunk (even)
+      float s[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        if (nt < nkt) {
+#pragma unroll
+          for (int kp = 0; kp < HD / 32; ++kp) {  // two k-steps per ldmatrix.x4
+            uint32_t kb[4];
+            ldmatrix_x4(kb, smem_u32(sK + (size_t)(kc + nt * 8 + (lane & 7)) * PITCH + kp * 32 + (lane >> 3) * 8));
+            mma_16816(s[nt], qa[2 * kp], kb[0], kb[1]);
+            mma_16816(s[nt], qa[2 * kp + 1], kb[2], kb[3]);
+          }
+          if (HD % 32) {  // odd number of k-steps (HD = 80): last 16 columns
+            uint32_t kb[4];
+            ldmatrix_x4(kb, smem_u32(sK + (size_t)(kc + nt * 8 + (lane & 7)) * PITCH + (HD - 16) + ((lane >> 3) & 1) * 8));
+            mma_16816(s[nt], qa[HD / 16 - 1], kb[0], kb[1]);
+          }
+        }
+      }
+      // mask padded keys, running max
+      float mx0 = m0, mx1 = m1;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        if (nt < nkt) {
+          const int key = kc + nt * 8 + t4 * 2;
+          if (key >= tokens) s[nt][0] = s[nt][2] = -INFINITY;
+          if (key + 1 >= tokens) s[nt][1] = s[nt][3] = -INFINITY;
+          mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+          mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float corr0 = exp2f((m0 - mx0) * scale_log2e), corr1 = exp2f((m1 - mx1) * scale_log2e);
+      m0 = mx0, m1 = mx1;
+      l0 *= corr0, l1 *= corr1;
+#pragma unroll
+      for (int d = 0; d < HD / 8; ++d) o[d][0] *= corr0, o[d][1] *= corr0, o[d][2] *= corr1, o[d][3] *= corr1;
+      const float b0 = m0 * scale_log2e, b1 = m1 * scale_log2e;
+      uint32_t pa[4][4];  // P as A fragments: k-step j covers key tiles 2j, 2j+1
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        if (nt < nkt) {
+          p0 = exp2f(fmaf(s[nt][0], scale_log2e, -b0)), p1 = exp2f(fmaf(s[nt][1], scale_log2e, -b0));
+          p2 = exp2f(fmaf(s[nt][2], scale_log2e, -b1)), p3 = exp2f(fmaf(s[nt][3], scale_log2e, -b1));
+        }
+        l0 += p0 + p1, l1 += p2 + p3;
+        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_half2(p0, p1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_half2(p2, p3);
+      }
+      // O += P V
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (2 * j < nkt) {
+#pragma unroll
+          for (int dp = 0; dp < HD / 16; ++dp) {  // two 8-wide dim tiles per ldmatrix.x4.trans
+            uint32_t vb[4];
+            ldmatrix_x4_trans(vb, smem_u32(sV + (size_t)(kc + j * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + dp * 16 + (lane >> 4) * 8));
+            mma_16816(o[2 * dp], pa[j], vb[0], vb[1]);
+            mma_16816(o[2 * dp + 1], pa[j], vb[2], vb[3]);
+          }
+        }
+      }
+    }
+    // quad-reduce the row sums, normalise, store
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    const int row0 = qt * 16 + g, row1 = row0 + 8;
+    __half* ob = out + (size_t)img * tokens * hidden + (size_t)head * head_dim;
+#pragma unroll
+    for (int d = 0; d < HD / 8; ++d) {
+      const int c = d * 8 + t4 * 2;
+      if (c < head_dim) {
+        if (row0 < tokens) *(uint32_t*)(ob + (size_t)row0 * hidden + c) = pack_half2(o[d][0] * inv0, o[d][1] * inv0);
+        if (row1 < tokens) *(uint32_t*)(ob + (size_t)row1 * hidden + c) = pack_half2(o[d][2] * inv1, o[d][3] * inv1);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- CLIP tail
+// One CTA per image: post_layernorm on the CLS row, projection (fp32 weights), L2 normalise, aesthetic affine head.
+__global__ void __launch_bounds__(256) clip_tail_kernel(const float* __restrict__ h, size_t img_stride, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, const float* __restrict__ proj, int d, int proj_dim,
+                                                        float eps, const float* __restrict__ aes_w, float aes_b, float* __restrict__ emb_out,
+                                                        float* __restrict__ feat_out, float* __restrict__ score_out) {
+  extern __shared__ float sm_tail[];
+  float* pooled = sm_tail;          // [d]
+  float* feat = sm_tail + d;        // [out_dim]
+  __shared__ float red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const float* x = h + (size_t)blockIdx.x * img_stride;
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (tid < nw) ? red[tid] : 0.f;
+    if (warp == 0) {
+      t = warp_sum(t);
+      if (lane == 0) red[0] = t;
+    }
+    __syncthreads();
+    return red[0];
+  };
+  float s = 0.f;
+  for (int i = tid; i < d; i += blockDim.x) s += x[i];
+  const float mean = block_sum(s) / (float)d;
+  float q = 0.f;
+  for (int i = tid; i < d; i += blockDim.x) {
+    const float c = x[i] - mean;
+    q += c * c;
+  }
+  const float rstd = rsqrtf(block_sum(q) / (float)d + eps);
+  for (int i = tid; i < d; i += blockDim.x) pooled[i] = (x[i] - mean) * rstd * gamma[i] + beta[i];
+  __syncthreads();
+  const int out_dim = proj ? proj_dim : d;
+  if (proj) {
+    for (int o = warp; o < proj_dim; o += nw) {
+      const float* w = proj + (size_t)o * d;
+      float acc = 0.f;
+      for (int i = lane * 4; i < d; i += 128) {
+        const float4 a = __ldg((const float4*)(w + i));
+        acc += a.x * pooled[i] + a.y * pooled[i + 1] + a.z * pooled[i + 2] + a.w * pooled[i + 3];
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) feat[o] = acc;
+    }
+  } else {
+    for (int i = tid; i < d; i += blockDim.x) feat[i] = pooled[i];
+  }
+  __syncthreads();
+  float n2 = 0.f;
+  for (int i = tid; i < out_dim; i += blockDim.x) n2 += feat[i] * feat[i];
+  const float inv = 1.f / sqrtf(block_sum(n2));
+  float sc = 0.f;
+  for (int i = tid; i < out_dim; i += blockDim.x) {
+    const float e = feat[i] * inv;
+    emb_out[(size_t)blockIdx.x * out_dim + i] = e;
+    if (feat_out) feat_out[(size_t)blockIdx.x * out_dim + i] = feat[i];
+    if (aes_w) sc += e * aes_w[i];
+  }
+  if (score_out && aes_w) {
+    const float tot = block_sum(sc);
+    if (tid == 0) score_out[blockIdx.x] = tot + aes_b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+int layernorm_f16(cb_ctx* ctx, const float* x, const float* gamma, const float* beta, void* y, int rows, int d, float eps, cudaStream_t stream) {
+  if (!x || !gamma || !beta || !y) return fail(ctx, CB_ERR_ARG, "layernorm: null operand");
+  if (rows <= 0) return CB_OK;
+  if (d % 128 || d > 128 * kLnMaxChunks) return fail(ctx, CB_ERR_UNSUPPORTED, "layernorm: d=%d must be a multiple of 128 and <= %d", d, 128 * kLnMaxChunks);
+  layernorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, gamma, beta, (__half*)y, rows, d, eps);
+  ctx->launches++;
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
+}
+
+int assemble_tokens(cb_ctx* ctx, const float* patch, const float* cls, const float* pos, const float* gamma, const float* beta, float* h, int n,
+                    int tokens, int grid2, int d, float eps, cudaStream_t stream) {
+  if (d % 128 || d > 128 * kLnMaxChunks) return fail(ctx, CB_ERR_UNSUPPORTED, "assemble: d=%d unsupported", d);
+  const int rows = n * tokens;
+  assemble_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(patch, cls, pos, gamma, beta, h, n, tokens, grid2, d, eps);
+  ctx->launches++;
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
+}
+
+int attention_f16(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int heads, int head_dim, cudaStream_t stream) {
+  if (!qkv || !out) return fail(ctx, CB_ERR_ARG, "attention: null operand");
+  if (n <= 0) return CB_OK;
+  if (tokens <= 0 || heads <= 0 || head_dim % 8 || head_dim > 80 || head_dim < 16)
+    return fail(ctx, CB_ERR_UNSUPPORTED, "attention: tokens=%d heads=%d head_dim=%d unsupported", tokens, heads, head_dim);
+  const int hd = head_dim <= 64 ? 64 : 80;
+  const int t_pad = (tokens + 15) & ~15;
+  const size_t smem = (size_t)2 * t_pad * (hd + 8) * 2;
+  if (smem > 200 * 1024) return fail(ctx, CB_ERR_UNSUPPORTED, "attention: %d tokens need %zu bytes of shared memory (K/V streaming not built yet)", tokens, smem);
+  const float scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
+  if (hd == 64) {
+    CB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attention_kernel<64><<<n * heads, kAttnThreads, smem, stream>>>((const __half*)qkv, (__half*)out, tokens, heads, head_dim, scale_log2e);
+  } else {
+    CB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attention_kernel<80><<<n * heads, kAttnThreads, smem, stream>>>((const __half*)qkv, (__half*)out, tokens, heads, head_dim, scale_log2e);
+  }
+  ctx->launches++;
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
+}
+
+int clip_tail(cb_ctx* ctx, const float* h, size_t img_stride, const float* gamma, const float* beta, const float* proj, int d, int proj_dim,
+              float eps, const float* aes_w, float aes_b, float* emb_out, float* feat_out, float* score_out, int n, cudaStream_t stream) {
+  const int out_dim = proj ? proj_dim : d;
+  const size_t smem = (size_t)(d + out_dim) * sizeof(float);
+  clip_tail_kernel<<<n, 256, smem, stream>>>(h, img_stride, gamma, beta, proj, d, proj_dim, eps, aes_w, aes_b, emb_out, feat_out, score_out);
+  ctx->launches++;
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
+}
+
+}  // namespace cb
+
+extern "C" {
+int cb_layernorm_f16(cb_ctx* ctx, const float* x, const float* gamma, const float* beta, void* y, int rows, int d, float eps, void* stream) {
+  if (!ctx) return CB_ERR_ARG;
+  return cb::layernorm_f16(ctx, x, gamma, beta, y, rows, d, eps, (cudaStream_t)stream);
+}
+int cb_attention_f16(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int heads, int head_dim, void* stream) {
+  if (!ctx) return CB_ERR_ARG;
+  return cb::attention_f16(ctx, qkv, out, n, tokens, heads, head_dim, (cudaStream_t)stream);
+}
+}

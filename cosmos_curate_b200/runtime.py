@@ -1,0 +1,223 @@
+"""Thin Python layer over the C ABI: torch tensors are only zero-copy containers (data_ptr()).
+
+Nothing here computes on the data path; every operation is a call into libcurate_b200.so.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SurfacePool, VitCfg, check
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)  # reference: cosmos_curate/models/clip.py:57-60
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+_TORCH_DT = {torch.float16: _lib.DT_F16, torch.bfloat16: _lib.DT_BF16, torch.float32: _lib.DT_F32}
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def _stream_ptr(stream=None) -> int:
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return int(s.cuda_stream)
+
+
+class Context:
+    """One per process/GPU (cb_init).  Fails loudly when the library or a CUDA device is missing."""
+
+    def __init__(self, device: int | None = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.CurateB200Error(-1, "Context", "no CUDA device; this path has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        torch.cuda.set_device(self.device)
+        torch.cuda.init()
+        h = C.c_void_p()
+        check(self.lib.cb_init(self.device, C.byref(h)), "cb_init")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def launch_count(self) -> int:
+        return int(self.lib.cb_launch_count(self.h))
+
+    def device_info(self) -> dict:
+        sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        check(self.lib.cb_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)), "cb_device_info", self.h)
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
+
+    # ---- surfaces -----------------------------------------------------------------------------
+    def nv12_pool(self, buf: torch.Tensor, width: int, height: int, luma_rows: int | None = None) -> "Pool":
+        """buf: uint8 cuda [slots, rows, pitch] with rows >= luma_rows + height/2."""
+        assert buf.is_cuda and buf.dtype == torch.uint8 and buf.dim() == 3 and buf.is_contiguous()
+        luma_rows = height if luma_rows is None else luma_rows
+        assert buf.shape[1] >= luma_rows + height // 2
+        return Pool(buf, SurfacePool(buf.data_ptr(), buf.shape[1] * buf.shape[2], width, height, buf.shape[2], luma_rows, _lib.FMT_NV12))
+
+    def rgb_pool(self, frames: torch.Tensor) -> "Pool":
+        """frames: uint8 cuda [n, H, W, 3] (contiguous).  Rows are re-pitched to a 16-byte multiple if needed."""
+        assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[-1] == 3
+        n, h, w, _ = frames.shape
+        row = 3 * w
+        pitch = (row + 15) & ~15
+        if pitch != row or not frames.is_contiguous():
+            buf = torch.zeros((n, h, pitch), dtype=torch.uint8, device=frames.device)
+            buf[:, :, :row] = frames.reshape(n, h, row)
+        else:
+            buf = frames.reshape(n, h, row)
+        stride = h * pitch
+        if stride % 16:
+            pad = torch.zeros((n, (stride + 15) // 16 * 16), dtype=torch.uint8, device=frames.device)
+            pad[:, :stride] = buf.reshape(n, stride)
+            buf, stride = pad, pad.shape[1]
+        return Pool(buf, SurfacePool(buf.data_ptr(), stride, w, h, pitch, h, _lib.FMT_RGB24))
+
+    # ---- preprocess ---------------------------------------------------------------------------
+    def _slots(self, pool: "Pool", slots):
+        n_slots = pool.buf.shape[0]
+        arr = np.arange(n_slots, dtype=np.int32) if slots is None else np.ascontiguousarray(slots, dtype=np.int32)
+        return arr, arr.ctypes.data_as(C.POINTER(C.c_int32))
+
+    def preprocess_clip(self, pool: "Pool", slots=None, res: int = 224, dtype=torch.float16, layout: str = "nchw", patch: int = 0,
+                        k_pad: int = 0, mean=CLIP_MEAN, std=CLIP_STD, out: torch.Tensor | None = None) -> torch.Tensor:
+        arr, ptr = self._slots(pool, slots)
+        n = len(arr)
+        if layout == "nchw":
+            shape, lay = (n, 3, res, res), _lib.LAYOUT_NCHW
+        else:
+            g = res // patch
+            shape, lay = (n, g * g, k_pad), _lib.LAYOUT_PATCH
+        if out is None:
+            out = torch.empty(shape, dtype=dtype, device=pool.buf.device)
+        check(self.lib.cb_preprocess_clip(self.h, C.byref(pool.desc), ptr, n, res, lay, patch, k_pad, _TORCH_DT[dtype], _f3(mean), _f3(std),
+                                          out.data_ptr(), _stream_ptr()), "cb_preprocess_clip", self.h)  # fmt: skip
+        return out
+
+    def preprocess_clip_u8(self, pool: "Pool", slots=None, res: int = 224) -> torch.Tensor:
+        arr, ptr = self._slots(pool, slots)
+        out = torch.empty((len(arr), 3, res, res), dtype=torch.uint8, device=pool.buf.device)
+        check(self.lib.cb_preprocess_clip_u8(self.h, C.byref(pool.desc), ptr, len(arr), res, out.data_ptr(), _stream_ptr()),
+              "cb_preprocess_clip_u8", self.h)  # fmt: skip
+        return out
+
+    def preprocess_bilinear_u8(self, pool: "Pool", out_w: int, out_h: int, slots=None) -> torch.Tensor:
+        arr, ptr = self._slots(pool, slots)
+        out = torch.empty((len(arr), out_h, out_w, 3), dtype=torch.uint8, device=pool.buf.device)
+        check(self.lib.cb_preprocess_bilinear_u8(self.h, C.byref(pool.desc), ptr, len(arr), out_w, out_h, out.data_ptr(), _stream_ptr()),
+              "cb_preprocess_bilinear_u8", self.h)  # fmt: skip
+        return out
+
+    def nv12_to_rgb(self, pool: "Pool", slots=None) -> torch.Tensor:
+        arr, ptr = self._slots(pool, slots)
+        out = torch.empty((len(arr), pool.desc.height, pool.desc.width, 3), dtype=torch.uint8, device=pool.buf.device)
+        check(self.lib.cb_nv12_to_rgb(self.h, C.byref(pool.desc), ptr, len(arr), out.data_ptr(), _stream_ptr()), "cb_nv12_to_rgb", self.h)
+        return out
+
+    # ---- building blocks (parity tests) -----------------------------------------------------------
+    def gemm(self, a: torch.Tensor, w: torch.Tensor, bias=None, residual=None, epilogue: int = _lib.EPI_NONE, out_f32: bool = False):
+        m, k = a.shape
+        n = w.shape[0]
+        assert a.dtype == torch.float16 and w.dtype == torch.float16 and w.shape[1] == k and a.is_contiguous() and w.is_contiguous()
+        if out_f32:
+            out = residual if residual is not None else torch.empty((m, n), dtype=torch.float32, device=a.device)
+            o32, o16 = out.data_ptr(), None
+        else:
+            out = torch.empty((m, n), dtype=torch.float16, device=a.device)
+            o32, o16 = None, out.data_ptr()
+        check(self.lib.cb_gemm_f16(self.h, a.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                   residual.data_ptr() if residual is not None else None, o32, o16, m, n, k, epilogue, _stream_ptr()),
+              "cb_gemm_f16", self.h)  # fmt: skip
+        return out
+
+    def layernorm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
+        rows, d = x.shape
+        y = torch.empty((rows, d), dtype=torch.float16, device=x.device)
+        check(self.lib.cb_layernorm_f16(self.h, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), rows, d, eps, _stream_ptr()),
+              "cb_layernorm_f16", self.h)  # fmt: skip
+        return y
+
+    def attention(self, qkv: torch.Tensor, heads: int) -> torch.Tensor:
+        n, t, three_d = qkv.shape
+        d = three_d // 3
+        out = torch.empty((n, t, d), dtype=torch.float16, device=qkv.device)
+        check(self.lib.cb_attention_f16(self.h, qkv.data_ptr(), out.data_ptr(), n, t, heads, d // heads, _stream_ptr()), "cb_attention_f16", self.h)
+        return out
+
+
+class Pool:
+    def __init__(self, buf: torch.Tensor, desc: SurfacePool):
+        self.buf, self.desc = buf, desc  # keep the tensor alive while the descriptor is in use
+
+
+class VitTower:
+    """cb_vit_* wrapper: weights in (fp32 numpy, oracle/HF naming), embeddings / scores out."""
+
+    def __init__(self, ctx: Context, cfg: dict, weights: dict, max_batch: int = 256, aesthetic: tuple | None = None):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.cfg = dict(cfg)
+        c = VitCfg(cfg["image_size"], cfg["patch"], cfg["hidden"], cfg["layers"], cfg["heads"], cfg["mlp"], cfg["proj_dim"],
+                   _lib.ACT_QUICK_GELU if cfg["act"] == "quick_gelu" else _lib.ACT_GELU_TANH,
+                   _lib.ARCH_CLIP if cfg["arch"] == "clip" else _lib.ARCH_SIGLIP, cfg["ln_eps"])  # fmt: skip
+        h = C.c_void_p()
+        check(self.lib.cb_vit_create(ctx.h, C.byref(c), C.byref(h)), "cb_vit_create", ctx.h)
+        self.h = h
+        for name, arr in weights.items():
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            check(self.lib.cb_vit_set_tensor(self.h, name.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), a.size), f"cb_vit_set_tensor({name})", ctx.h)
+        self.out_dim = cfg["proj_dim"] or cfg["hidden"]
+        self.has_aesthetic = False
+        if aesthetic is not None:
+            w, b = aesthetic
+            w = np.ascontiguousarray(w, dtype=np.float32)
+            check(self.lib.cb_vit_set_aesthetic(self.h, w.ctypes.data_as(C.POINTER(C.c_float)), w.size, float(b)), "cb_vit_set_aesthetic", ctx.h)
+            self.has_aesthetic = True
+        check(self.lib.cb_vit_finalize(self.h, max_batch), "cb_vit_finalize", ctx.h)
+        self.k_pad = int(self.lib.cb_vit_k_pad(self.h))
+        self.max_batch = max_batch
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cb_vit_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def forward_patches(self, patches: torch.Tensor, want_features: bool = False):
+        n = patches.shape[0]
+        dev = patches.device
+        emb = torch.empty((n, self.out_dim), dtype=torch.float32, device=dev)
+        feat = torch.empty((n, self.out_dim), dtype=torch.float32, device=dev) if want_features else None
+        score = torch.empty((n,), dtype=torch.float32, device=dev) if self.has_aesthetic else None
+        check(self.lib.cb_vit_forward(self.h, patches.data_ptr(), n, emb.data_ptr(), feat.data_ptr() if feat is not None else None,
+                                      score.data_ptr() if score is not None else None, _stream_ptr()), "cb_vit_forward", self.ctx.h)  # fmt: skip
+        return emb, feat, score
+
+    def embed_pool(self, pool: Pool, slots=None, mean=CLIP_MEAN, std=CLIP_STD, want_features: bool = False):
+        arr, ptr = self.ctx._slots(pool, slots)
+        n, dev = len(arr), pool.buf.device
+        emb = torch.empty((n, self.out_dim), dtype=torch.float32, device=dev)
+        feat = torch.empty((n, self.out_dim), dtype=torch.float32, device=dev) if want_features else None
+        score = torch.empty((n,), dtype=torch.float32, device=dev) if self.has_aesthetic else None
+        check(self.lib.cb_vit_embed_surfaces(self.h, C.byref(pool.desc), ptr, n, _f3(mean), _f3(std), emb.data_ptr(),
+                                             feat.data_ptr() if feat is not None else None, score.data_ptr() if score is not None else None,
+                                             _stream_ptr()), "cb_vit_embed_surfaces", self.ctx.h)  # fmt: skip
+        return emb, feat, score

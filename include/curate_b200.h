@@ -1,0 +1,153 @@
+/* libcurate_b200 - C ABI of the B200-native decode -> sample -> preprocess -> embed/classify path.
+ *
+ * The reference (nvidia-cosmos/cosmos-curate) has NO FFI boundary on this path: its stages call
+ * Python libraries (PyAV, PyNvVideoCodec, CV-CUDA, torchvision, transformers).  The drop-in boundary
+ * is therefore the Python plugin surface (CuratorStage / ModelInterface, mirrored in
+ * cosmos_curate_b200/); this header is the thin C ABI those Python stages bind with ctypes.  Every entry
+ * point names the reference call it replaces (file:line relative to the reference checkout).
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every function returns CB_OK (0) or a
+ * negative error code and never throws; cb_last_error() returns the message.  Device pointers are
+ * caller-owned (torch-allocated is fine); the library owns only its context, cached tables, model
+ * weights/workspace and NVDEC sessions.  `stream` is a cudaStream_t passed as void* (NULL = default).
+ * There is no CPU fallback anywhere: without a CUDA device cb_init fails.
+ */
+#ifndef CURATE_B200_H
+#define CURATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_OK 0
+#define CB_ERR_CUDA (-1)        /* CUDA runtime / driver error */
+#define CB_ERR_ARG (-2)         /* bad argument */
+#define CB_ERR_UNSUPPORTED (-3) /* valid request this build cannot serve (size, codec, ...) */
+#define CB_ERR_NVDEC (-4)       /* libnvcuvid missing or decode failure */
+#define CB_ERR_DEMUX (-5)       /* malformed / unsupported container */
+#define CB_ERR_STATE (-6)       /* call order (e.g. forward before finalize) */
+
+#define CB_ABI_VERSION 1
+
+typedef struct cb_ctx cb_ctx;
+typedef struct cb_vit cb_vit;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int cb_abi_version(void);
+/* Creates a context on CUDA device `device` (must be sm_100).  Replaces the implicit torch/CV-CUDA
+ * device setup of nvcodec_utils.py:337 (device_id hard-coded to 0 there) and clip.py:39. */
+int cb_init(int device, cb_ctx** out);
+void cb_destroy(cb_ctx* ctx);
+/* Message of the last failing call on `ctx` (or of the last failing cb_init when ctx == NULL). */
+const char* cb_last_error(cb_ctx* ctx);
+int cb_device_info(cb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+/* Number of kernels this library has launched on `ctx` since cb_init (bench.py "gpu_launches"). */
+unsigned long long cb_launch_count(cb_ctx* ctx);
+
+/* ---- surfaces ----------------------------------------------------------------------------------- */
+#define CB_FMT_NV12 0  /* Y plane [luma_rows x pitch] then interleaved UV plane [height/2 x pitch] */
+#define CB_FMT_RGB24 1 /* interleaved RGB u8, pitch >= 3*width */
+
+/* A pool of equally shaped frames in device memory: frame i starts at base + i*slot_stride.
+ * NV12: UV plane of a frame starts `luma_rows * pitch` bytes after its Y plane (NVDEC aligns the coded
+ * height, so luma_rows >= height).  base, pitch and slot_stride must be multiples of 16 bytes. */
+typedef struct cb_surface_pool {
+  const void* base;
+  size_t slot_stride;
+  int width, height; /* display size in pixels */
+  int pitch;         /* bytes per row */
+  int luma_rows;     /* NV12 only: rows between the Y plane and the UV plane */
+  int format;        /* CB_FMT_* */
+} cb_surface_pool;
+
+/* ---- preprocess ---------------------------------------------------------------------------------- */
+#define CB_DT_F16 0
+#define CB_DT_BF16 1
+#define CB_DT_F32 2
+#define CB_LAYOUT_NCHW 0  /* out[n][3][res][res]                                   (reference tensor layout) */
+#define CB_LAYOUT_PATCH 1 /* out[n][(res/patch)^2][k_pad], k = (c, py, px), zero padded (tower input) */
+
+/* Fused colour-convert + resize + crop + normalise + pack.  Replaces, in one pass over the source
+ * frame, cvcuda.cvtcolor_into (nvcodec_utils.py:178) and the reference CLIP transform chain
+ * Resize(res, bicubic, antialias) -> CenterCrop(res) -> /255 -> Normalize (clip.py:48-62).
+ * slots[n] (host) selects the frames of `pool`; `out` is device memory of the chosen layout/dtype. */
+int cb_preprocess_clip(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int res, int layout, int patch,
+                       int k_pad, int dtype, const float mean[3], const float std_[3], void* out, void* stream);
+
+/* The same resize/crop with the u8 stage exposed: out u8 [n][3][res][res] (parity tests; this is the
+ * tensor torchvision produces before ConvertImageDtype, clip.py:50-55). */
+int cb_preprocess_clip_u8(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int res, uint8_t* out,
+                          void* stream);
+
+/* Fused NV12->RGB + bilinear resize to out_w x out_h, u8 HWC: out[n][out_h][out_w][3].  Replaces
+ * cvcuda.cvtcolor_into + cvcuda.resize_into(Interp.LINEAR) (nvcodec_utils.py:178,189-194), the
+ * 27x48 shot-detection frames of VideoFrameExtractionStage (frame_extraction_stages.py:112-116). */
+int cb_preprocess_bilinear_u8(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int out_w, int out_h,
+                              uint8_t* out, void* stream);
+
+/* Full-resolution NV12 -> RGB24 (HWC, tightly packed): what decode_video_cpu_frame_ids returns per
+ * frame (decoder_utils.py:439-451) / cvcuda.cvtcolor_into (nvcodec_utils.py:178).  Only for callers that
+ * must hand RGB frames to an unmodified downstream stage. */
+int cb_nv12_to_rgb(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, uint8_t* out, void* stream);
+
+/* ---- image tower (CLIP / SigLIP style ViT) + aesthetic head --------------------------------------- */
+#define CB_ACT_QUICK_GELU 0
+#define CB_ACT_GELU_TANH 1
+#define CB_ARCH_CLIP 0   /* CLS token, pre-LN, post-LN on CLS, bias-free projection (HF CLIPVisionModel) */
+#define CB_ARCH_SIGLIP 1 /* no CLS, patch bias, post-LN on all tokens, MAP pooling head (HF SiglipVisionModel) */
+
+typedef struct cb_vit_cfg {
+  int image_size, patch, hidden, layers, heads, mlp, proj_dim;
+  int act;  /* CB_ACT_* */
+  int arch; /* CB_ARCH_* */
+  float ln_eps;
+} cb_vit_cfg;
+
+/* Replaces CLIPModel.from_pretrained(...).to(device) (clip.py:41) for the image tower. */
+int cb_vit_create(cb_ctx* ctx, const cb_vit_cfg* cfg, cb_vit** out);
+void cb_vit_destroy(cb_vit* vit);
+/* Upload one named tensor (host fp32, row-major, `count` elements).  Names: patch_w[hidden][3*p*p],
+ * patch_b, cls, pos[tokens][hidden], pre_ln_w/b, L<i>.{ln1_w,ln1_b,qkv_w[3h][h],qkv_b,out_w,out_b,ln2_w,
+ * ln2_b,fc1_w[mlp][h],fc1_b,fc2_w[h][mlp],fc2_b}, post_ln_w/b, proj_w[proj][hidden], map_* (SigLIP). */
+int cb_vit_set_tensor(cb_vit* vit, const char* name, const float* data, size_t count);
+/* Aesthetic head folded to score = w . embedding + b (the reference MLP, aesthetics.py:44-53, has no
+ * non-linearity).  w has proj_dim (or hidden) entries.  Optional. */
+int cb_vit_set_aesthetic(cb_vit* vit, const float* w, size_t count, float b);
+/* Checks that every tensor arrived and sizes the workspace for batches up to max_batch images. */
+int cb_vit_finalize(cb_vit* vit, int max_batch);
+/* K padding (in fp16 elements) the tower expects of CB_LAYOUT_PATCH input rows. */
+int cb_vit_k_pad(const cb_vit* vit);
+/* Forward over n preprocessed images.  patches: device fp16 [n][(image/patch)^2][k_pad] (CB_LAYOUT_PATCH).
+ * emb_out: device fp32 [n][proj_dim or hidden], L2-normalised (clip.py:71-74).  feat_out (nullable):
+ * the un-normalised features.  score_out (nullable): device fp32 [n] aesthetic scores
+ * (clip_aesthetics.py:63-76). */
+int cb_vit_forward(cb_vit* vit, const void* patches, int n, float* emb_out, float* feat_out, float* score_out, void* stream);
+/* Preprocess + forward in one call: frames of `pool` -> embeddings / scores (the whole
+ * CLIPAestheticScorer.__call__, clip_aesthetics.py:63-76, from NV12 or RGB frames). */
+int cb_vit_embed_surfaces(cb_vit* vit, const cb_surface_pool* pool, const int32_t* slots, int n, const float mean[3],
+                          const float std_[3], float* emb_out, float* feat_out, float* score_out, void* stream);
+
+/* ---- building blocks exported for the parity tests ------------------------------------------------ */
+#define CB_EPI_NONE 0       /* C = A W^T (+ bias) */
+#define CB_EPI_QUICK_GELU 1 /* C = quick_gelu(A W^T + bias) */
+#define CB_EPI_GELU_TANH 2  /* C = gelu_tanh(A W^T + bias) */
+/* C[M][N] = epilogue(A[M][K] . W[N][K]^T + bias[N]) (+ residual).  A, W fp16 row-major (K contiguous,
+ * K % 8 == 0); bias fp32 or NULL.  If out_f32 != NULL: out_f32[M][N] (fp32) = result + (residual ?
+ * residual[M][N] : 0) - residual may alias out_f32.  Else out_f16[M][N] = fp16(result).
+ * The tcgen05 GEMM under every Linear of the tower (HF CLIPEncoderLayer q/k/v/out/fc1/fc2). */
+int cb_gemm_f16(cb_ctx* ctx, const void* A, const void* W, const float* bias, const float* residual, float* out_f32,
+                void* out_f16, int M, int N, int K, int epilogue, void* stream);
+/* y[rows][d] fp16 = LayerNorm(x[rows][d] fp32) * gamma + beta. */
+int cb_layernorm_f16(cb_ctx* ctx, const float* x, const float* gamma, const float* beta, void* y, int rows, int d, float eps,
+                     void* stream);
+/* Multi-head self-attention over qkv fp16 [n][tokens][3*hidden] (q | k | v, heads contiguous):
+ * out fp16 [n][tokens][hidden]; softmax in fp32, scale = head_dim^-1/2. */
+int cb_attention_f16(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int heads, int head_dim, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CURATE_B200_H */

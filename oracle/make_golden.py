@@ -131,10 +131,10 @@ def _tiny_clip_dir(tmp: Path):
     torch.manual_seed(0)
     cfg = CLIPConfig(
         text_config={"hidden_size": 32, "intermediate_size": 64, "num_hidden_layers": 1, "num_attention_heads": 2,
-                     "vocab_size": 64, "max_position_embeddings": 8, "projection_dim": 48},
-        vision_config={"hidden_size": 64, "intermediate_size": 128, "num_hidden_layers": 2, "num_attention_heads": 2,
-                       "image_size": 224, "patch_size": 32, "projection_dim": 48},
-        projection_dim=48,
+                     "vocab_size": 64, "max_position_embeddings": 8, "projection_dim": 64},
+        vision_config={"hidden_size": 128, "intermediate_size": 256, "num_hidden_layers": 2, "num_attention_heads": 2,
+                       "image_size": 224, "patch_size": 32, "projection_dim": 64},
+        projection_dim=64,
     )  # fmt: skip
     model = CLIPModel(cfg).eval()
     with torch.no_grad():  # HF init leaves LN at (1,0) and biases at 0: perturb so every term is exercised

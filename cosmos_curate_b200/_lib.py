@@ -53,7 +53,7 @@ class Mp4Info(C.Structure):
 class DecodeStats(C.Structure):
     _fields_ = [
         ("frames_decoded", C.c_int), ("frames_emitted", C.c_int), ("coded_width", C.c_int), ("coded_height", C.c_int),
-        ("pitch", C.c_int), ("luma_rows", C.c_int),
+        ("width", C.c_int), ("height", C.c_int),
     ]  # fmt: skip
 
 
@@ -80,6 +80,10 @@ SIGNATURES = {
     "cb_vit_k_pad": (_i, [_vp]),
     "cb_vit_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "cb_vit_embed_surfaces": (_i, [_vp, C.POINTER(SurfacePool), _pi32, _i, _pf, _pf, _vp, _vp, _vp, _vp]),
+    "cb_mp4_index": (_i, [_vp, _vp, C.c_size_t, C.POINTER(Mp4Info), C.POINTER(C.c_int64), C.POINTER(C.c_uint8), _i]),
+    "cb_decoder_create": (_i, [_vp, C.POINTER(_vp)]),
+    "cb_decoder_destroy": (None, [_vp]),
+    "cb_decoder_decode": (_i, [_vp, _vp, C.c_size_t, _pi32, _i, C.POINTER(SurfacePool), _pi32, C.POINTER(DecodeStats)]),
     "cb_gemm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cb_layernorm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "cb_attention_f16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

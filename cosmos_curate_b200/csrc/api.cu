@@ -1,6 +1,7 @@
 // Context management and shared host helpers of libcurate_b200 (C ABI in include/curate_b200.h).
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"

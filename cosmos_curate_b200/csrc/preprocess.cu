@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -49,6 +50,7 @@ struct ClipArgs {
   int ring;               // ring rows (power of two >= kSR + ty)
   const float* lut;       // [3][256]
   int out_mode;           // 0 = u8 NCHW, 1 = typed NCHW, 2 = typed patch rows
+  int x_align;            // source window start is aligned down to this many pixels (TMA: 16-byte aligned box start)
   int dtype, patch, k_pad;
   void* out;
 };
@@ -96,8 +98,7 @@ __global__ void __launch_bounds__(kThreads) clip_preprocess_kernel(const __grid_
   uint64_t* bars = (uint64_t*)(((uintptr_t)(obuf + npx * a.k_pad) + 7) & ~(uintptr_t)7);
 
   // source columns this tile touches
-  int x_lo = a.xmin[c0];
-  if (FMT == CB_FMT_NV12) x_lo &= ~1;
+  const int x_lo = a.xmin[c0] & ~(a.x_align - 1);
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -108,21 +109,27 @@ __global__ void __launch_bounds__(kThreads) clip_preprocess_kernel(const __grid_
     for (int i = tid; i < npx * a.k_pad; i += kThreads) obuf[i] = 0;  // zero K padding once
   __syncthreads();
 
-  auto issue = [&](int s) {
-    uint8_t* dst = raw + (s & 1) * raw_stage;
-    uint64_t* bar = &bars[s & 1];
-    const int y0 = a.y_begin + s * kSR;
-    mbar_expect_tx(bar, raw_stage);
-    if (FMT == CB_FMT_NV12) {
-      tma_load_3d(dst, &map_a, bar, x_lo, y0, slot);
-      tma_load_3d(dst + a.swa * kSR, &map_b, bar, x_lo, y0 >> 1, slot);
-    } else {
-      for (int k = 0; k < 3; ++k) tma_load_3d(dst + k * a.swa * kSR, &map_a, bar, x_lo * 3 + k * a.swa, y0, slot);
-    }
-  };
+  // NOTE: x_lo is a multiple of 16 pixels: a TMA box whose first byte is not 16-byte aligned in global memory
+  // faults with "illegal instruction" (measured on B200; u8 elements make this easy to hit).
+#define CB_ISSUE_STRIP(S_)                                                                                        \
+  do {                                                                                                            \
+    const int s_ = (S_);                                                                                          \
+    uint8_t* dst_ = raw + (s_ & 1) * raw_stage;                                                                   \
+    uint64_t* bar_ = &bars[s_ & 1];                                                                               \
+    const int ys_ = a.y_begin + s_ * kSR;                                                                         \
+    mbar_expect_tx(bar_, raw_stage);                                                                              \
+    if (FMT == CB_FMT_NV12) {                                                                                     \
+      tma_load_3d(dst_, &map_a, bar_, x_lo, ys_, slot);                                                           \
+      tma_load_3d(dst_ + a.swa * kSR, &map_b, bar_, x_lo, ys_ >> 1, slot);                                        \
+    } else {                                                                                                      \
+      tma_load_3d(dst_, &map_a, bar_, x_lo * 3, ys_, slot);                                                       \
+      tma_load_3d(dst_ + a.swa * kSR, &map_a, bar_, x_lo * 3 + a.swa, ys_, slot);                                 \
+      tma_load_3d(dst_ + 2 * a.swa * kSR, &map_a, bar_, x_lo * 3 + 2 * a.swa, ys_, slot);                         \
+    }                                                                                                             \
+  } while (0)
   if (tid == 0) {
-    issue(0);
-    if (a.n_strips > 1) issue(1);
+    CB_ISSUE_STRIP(0);
+    if (a.n_strips > 1) CB_ISSUE_STRIP(1);
   }
 
   int next_out = 0;  // next output row to emit
@@ -161,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) clip_preprocess_kernel(const __grid_
     __syncthreads();
     if (tid == 0 && s + 2 < a.n_strips) {
       fence_proxy_async();  // generic-proxy reads of this stage are done; hand it back to the TMA
-      issue(s + 2);
+      CB_ISSUE_STRIP(s + 2);
     }
 
     // ---- phase 2: horizontal filter; lane = source row of the strip, (column, channel) uniform per warp
@@ -301,7 +308,7 @@ const TapTable* get_taps(cb_ctx* ctx, int in_size, int out_size, int crop_off, i
   if (it != ctx->taps.end()) return &it->second;
   TapTable t;
   t.in_size = in_size, t.out_size = out_size, t.crop_off = crop_off, t.crop_len = crop_len;
-  // ATen upsample_antialias::_compute_weights_span / _compute_weights in float32 (see oracle/preprocess.py)
+  // ATen upsample_antialias::_compute_weights_span / _compute_weights in float32
   volatile float scale = (float)in_size / (float)out_size;
   const float support = (scale >= 1.f) ? 2.0f * scale : 2.0f;
   const float invscale = (scale >= 1.f) ? 1.0f / scale : 1.0f;
@@ -433,13 +440,13 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
   int ring = 64;
   while (ring < kSR + ty->max_taps) ring <<= 1;
   a.ring = ring;
+  a.x_align = 16;  // cp.async.bulk.tensor needs the box to start on a 16-byte boundary of the innermost dimension
   // widest source span of any column tile
   int span = 0;
   const int tiles = (res + a.tc - 1) / a.tc;
   for (int t = 0; t < tiles; ++t) {
     const int c0 = t * a.tc, c1 = std::min(res, c0 + a.tc);
-    int lo = tx->h_min[c0], hi = 0;
-    if (pool->format == CB_FMT_NV12) lo &= ~1;
+    int lo = tx->h_min[c0] & ~(a.x_align - 1), hi = 0;
     for (int c = c0; c < c1; ++c) hi = std::max(hi, tx->h_min[c] + tx->h_size[c]);
     span = std::max(span, hi - lo);
   }

@@ -165,7 +165,7 @@ class Pool:
 
 
 class VitTower:
-    """cb_vit_* wrapper: weights in (fp32 numpy, oracle/HF naming), embeddings / scores out."""
+    """cb_vit_* wrapper: weights in (fp32 numpy, names of include/curate_b200.h cb_vit_set_tensor), embeddings / scores out."""
 
     def __init__(self, ctx: Context, cfg: dict, weights: dict, max_batch: int = 256, aesthetic: tuple | None = None):
         self.ctx, self.lib = ctx, ctx.lib
@@ -221,3 +221,69 @@ class VitTower:
                                              feat.data_ptr() if feat is not None else None, score.data_ptr() if score is not None else None,
                                              _stream_ptr()), "cb_vit_embed_surfaces", self.ctx.h)  # fmt: skip
         return emb, feat, score
+
+
+# ---- demux + NVDEC ------------------------------------------------------------------------------------
+def _as_u8(data) -> np.ndarray:
+    if isinstance(data, np.ndarray):
+        return np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+    return np.frombuffer(bytes(data) if not isinstance(data, (bytes, bytearray, memoryview)) else data, dtype=np.uint8)
+
+
+def mp4_index(data, ctx: Context | None = None) -> dict:
+    """cb_mp4_index: video-track facts + per-sample PTS ticks (decode order) + sync flags (host-only parse)."""
+    buf = _as_u8(data)
+    lib = ctx.lib if ctx is not None else _lib.load()
+    h = ctx.h if ctx is not None else None
+    info = _lib.Mp4Info()
+    check(lib.cb_mp4_index(h, buf.ctypes.data, buf.size, C.byref(info), None, None, 0), "cb_mp4_index", h)
+    n = info.n_samples
+    pts = np.empty(n, dtype=np.int64)
+    sync = np.empty(n, dtype=np.uint8)
+    check(lib.cb_mp4_index(h, buf.ctypes.data, buf.size, C.byref(info), pts.ctypes.data_as(C.POINTER(C.c_int64)),
+                           sync.ctypes.data_as(C.POINTER(C.c_uint8)), n), "cb_mp4_index", h)  # fmt: skip
+    return {"codec": info.codec, "width": info.width, "height": info.height, "timescale": info.timescale, "n_samples": n,
+            "n_sync": info.n_sync, "has_ctts": bool(info.has_ctts), "duration": info.duration, "pts": pts, "sync": sync}  # fmt: skip
+
+
+class Decoder:
+    """One NVDEC session (cb_decoder_*).  Not thread-safe: use one per host thread."""
+
+    def __init__(self, ctx: Context):
+        self.ctx, self.lib = ctx, ctx.lib
+        h = C.c_void_p()
+        check(self.lib.cb_decoder_create(ctx.h, C.byref(h)), "cb_decoder_create", ctx.h)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cb_decoder_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def decode(self, data, frame_ids, pool: Pool, dst_slots) -> dict:
+        """Decode `data` (mp4 bytes) and copy display-order frames `frame_ids` (ascending, repeats allowed)
+        into `pool` slots `dst_slots`.  Raises CurateB200Error on demux / decode failure."""
+        buf = _as_u8(data)
+        ids = np.ascontiguousarray(frame_ids, dtype=np.int32)
+        slots = np.ascontiguousarray(dst_slots, dtype=np.int32)
+        assert len(ids) == len(slots)
+        st = _lib.DecodeStats()
+        check(self.lib.cb_decoder_decode(self.h, buf.ctypes.data, buf.size, ids.ctypes.data_as(C.POINTER(C.c_int32)), len(ids),
+                                         C.byref(pool.desc), slots.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st)),
+              "cb_decoder_decode", self.ctx.h)  # fmt: skip
+        return {"frames_decoded": st.frames_decoded, "frames_emitted": st.frames_emitted, "coded": (st.coded_width, st.coded_height),
+                "size": (st.width, st.height)}  # fmt: skip
+
+
+def alloc_nv12_pool(ctx: Context, slots: int, width: int, height: int) -> Pool:
+    """Device NV12 surface pool for `slots` frames of width x height (pitch aligned to 256 bytes)."""
+    w2, h2 = (width + 1) & ~1, (height + 1) & ~1
+    pitch = (w2 + 255) // 256 * 256
+    buf = torch.empty((slots, h2 + h2 // 2, pitch), dtype=torch.uint8, device=f"cuda:{ctx.device}")
+    return ctx.nv12_pool(buf, w2, h2, h2)

@@ -130,6 +130,40 @@ int cb_vit_forward(cb_vit* vit, const void* patches, int n, float* emb_out, floa
 int cb_vit_embed_surfaces(cb_vit* vit, const cb_surface_pool* pool, const int32_t* slots, int n, const float mean[3],
                           const float std_[3], float* emb_out, float* feat_out, float* score_out, void* stream);
 
+/* ---- demux + NVDEC ---------------------------------------------------------------------------- */
+typedef struct cb_decoder cb_decoder;
+
+typedef struct cb_mp4_info {
+  int codec;          /* 4 = H.264, 8 = HEVC (cudaVideoCodec numbering) */
+  int width, height;  /* sample-entry (display) size */
+  uint32_t timescale; /* mdhd timescale: PTS seconds = pts / timescale */
+  int n_samples, n_sync, has_ctts;
+  uint64_t duration;
+} cb_mp4_info;
+
+typedef struct cb_decode_stats {
+  int frames_decoded, frames_emitted;
+  int coded_width, coded_height, width, height;
+} cb_decode_stats;
+
+/* Index the first video track of an in-memory MP4: per-sample composition timestamps (decode order, in
+ * `timescale` ticks, edit list applied) and sync flags.  Replaces the container open + packet demux of
+ * get_video_timestamps (decoder_utils.py:230-278); the caller sorts and converts to float32 seconds exactly
+ * as the reference does.  pts_out / sync_out (nullable) receive min(cap, n_samples) entries.  Host-only: ctx may
+ * be NULL. */
+int cb_mp4_index(cb_ctx* ctx, const uint8_t* data, size_t size, cb_mp4_info* info, int64_t* pts_out, uint8_t* sync_out, int cap);
+
+/* One NVDEC session (parser + decoder + copy stream); use one per host thread, reuse it across clips. */
+int cb_decoder_create(cb_ctx* ctx, cb_decoder** out);
+void cb_decoder_destroy(cb_decoder* dec);
+/* Decode one clip and deliver ONLY the display-order frames frame_ids[0..n_ids) (ascending; repeats allowed,
+ * the counts of sample_closest) as NV12 into slots dst_slots[i] of `dst`.  Decoding stops after the last
+ * wanted frame.  Replaces decode_video_cpu_frame_ids (decoder_utils.py:389-461: PyAV decodes every frame,
+ * converts the wanted ones to RGB on the host) and NvVideoDecoder.generate_decoded_frames
+ * (nvcodec_utils.py:247-295).  Returns only after the copies have completed. */
+int cb_decoder_decode(cb_decoder* dec, const uint8_t* data, size_t size, const int32_t* frame_ids, int n_ids,
+                      const cb_surface_pool* dst, const int32_t* dst_slots, cb_decode_stats* stats);
+
 /* ---- building blocks exported for the parity tests ------------------------------------------------ */
 #define CB_EPI_NONE 0       /* C = A W^T (+ bias) */
 #define CB_EPI_QUICK_GELU 1 /* C = quick_gelu(A W^T + bias) */

@@ -1,0 +1,116 @@
+"""GPU: MP4 index + NVDEC decode of sampled frames vs libavcodec (cv2), through the C ABI."""
+
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from gpu_helpers import ctx  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+os.environ.setdefault("OPENCV_LOG_LEVEL", "ERROR")
+
+
+def _cv2_luma_and_bgr(path, ids):
+    import cv2
+
+    cap = cv2.VideoCapture(str(path))
+    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)  # yuv420p comes back as the Y plane only
+    capc = cv2.VideoCapture(str(path))
+    luma, bgr, want = {}, {}, set(int(i) for i in ids)
+    i = 0
+    while True:
+        ok, y = cap.read()
+        ok2, c = capc.read()
+        if not ok or not ok2:
+            break
+        if i in want:
+            luma[i], bgr[i] = y.copy(), c.copy()
+        i += 1
+    return luma, bgr, i
+
+
+def test_nvdec_sampled_frames_match_libavcodec(ctx):
+    from cosmos_curate_b200 import sampling
+    from cosmos_curate_b200.runtime import Decoder, alloc_nv12_pool, mp4_index
+
+    path = GOLDEN / "sintel_clip_10s.mp4"
+    data = np.fromfile(path, dtype=np.uint8)
+    idx = mp4_index(data, ctx)
+    ts = sampling.timestamps_from_index(idx["pts"], idx["timescale"])
+    ids, counts = sampling.frame_ids(ts, sampling.FrameExtractionPolicy.sequence, 2.0)
+    assert len(ids) == 21 and ids[-2:].tolist() == [228, 239]
+    pool = alloc_nv12_pool(ctx, len(ids), idx["width"], idx["height"])
+    dec = Decoder(ctx)
+    st = dec.decode(data, ids, pool, np.arange(len(ids)))
+    assert st["frames_emitted"] == len(ids) and st["size"] == (854, 480)
+    assert st["frames_decoded"] == 240  # the last sampled frame is the last frame of the clip
+    luma, bgr, n = _cv2_luma_and_bgr(path, ids)
+    assert n == 240
+    got = pool.buf.cpu().numpy()
+    rgb = ctx.nv12_to_rgb(pool).cpu().numpy()
+    h, w = idx["height"], idx["width"]
+    for k, i in enumerate(ids):
+        np.testing.assert_array_equal(got[k, :h, :w], luma[int(i)].reshape(h, w))  # H.264 decode is bit-exact by spec
+        d = np.abs(rgb[k].astype(int) - bgr[int(i)][..., ::-1].astype(int))
+        assert d.mean() < 1.5 and d.max() <= 12  # swscale vs OpenCV-style conversion + chroma siting
+    # early stop: only the frames up to the last wanted id are decoded
+    st = dec.decode(data, [0, 24, 48], pool, [0, 1, 2])
+    assert st["frames_emitted"] == 3 and st["frames_decoded"] <= 48 + 1 + 4
+    # repeated ids (supersampling counts) land in several slots
+    st = dec.decode(data, [5, 5, 7], pool, [0, 1, 2])
+    g2 = pool.buf.cpu().numpy()
+    np.testing.assert_array_equal(g2[0], g2[1])
+    assert (g2[0] != g2[2]).any()
+    dec.close()
+
+
+def test_nvdec_error_paths(ctx):
+    from cosmos_curate_b200._lib import CurateB200Error
+    from cosmos_curate_b200.runtime import Decoder, alloc_nv12_pool
+
+    data = np.fromfile(GOLDEN / "sintel_clip_10s.mp4", dtype=np.uint8)
+    dec = Decoder(ctx)
+    pool = alloc_nv12_pool(ctx, 2, 854, 480)
+    with pytest.raises(CurateB200Error) as e:
+        dec.decode(np.zeros(1000, np.uint8), [0], pool, [0])
+    assert e.value.code == -5
+    with pytest.raises(CurateB200Error):
+        dec.decode(data, [3, 1], pool, [0, 1])  # not ascending
+    with pytest.raises(CurateB200Error):
+        dec.decode(data, [500], pool, [0])  # beyond the clip
+    wrong = alloc_nv12_pool(ctx, 1, 1920, 1080)
+    with pytest.raises(CurateB200Error) as e:
+        dec.decode(data, [0], wrong, [0])
+    assert e.value.code == -4
+    assert dec.decode(data, [0], pool, [0])["frames_emitted"] == 1  # the session survives errors
+    assert dec.decode(data, [], pool, [])["frames_emitted"] == 0  # empty request
+    dec.close()
+
+
+def test_decode_to_embedding_end_to_end(ctx):
+    """mp4 bytes -> NVDEC -> fused preprocess -> tower, against the oracle fed with libavcodec luma-exact frames."""
+    from cosmos_curate_b200 import sampling
+    from cosmos_curate_b200.runtime import Decoder, VitTower, alloc_nv12_pool, mp4_index
+    from oracle import color, preprocess, vit
+
+    data = np.fromfile(GOLDEN / "sintel_clip_10s.mp4", dtype=np.uint8)
+    idx = mp4_index(data, ctx)
+    ts = sampling.timestamps_from_index(idx["pts"], idx["timescale"])
+    ids, _ = sampling.frame_ids(ts, sampling.FrameExtractionPolicy.sequence, 1.0)
+    pool = alloc_nv12_pool(ctx, len(ids), idx["width"], idx["height"])
+    Decoder(ctx).decode(data, ids, pool, np.arange(len(ids)))
+    cfg = vit.CLIP_TINY
+    w = vit.random_weights(cfg, seed=3)
+    tower = VitTower(ctx, cfg.to_dict(), w, max_batch=16)
+    emb, _, _ = tower.embed_pool(pool)
+    nv12 = pool.buf.cpu().numpy()
+    h, wd = idx["height"], idx["width"]
+    rgb = np.stack([color.nv12_to_rgb(np.ascontiguousarray(f[:, :wd]), h, wd) for f in nv12])
+    ref = vit.forward(cfg, w, preprocess.clip_preprocess(rgb))["embedding"]
+    rel = np.linalg.norm(emb.cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel.max() < 2e-3

@@ -1,0 +1,147 @@
+"""CPU tests of the host side: C-ABI export, product index math vs reference vectors, MP4 index."""
+
+from __future__ import annotations
+
+import json
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_json, load_golden
+
+F = np.float32
+
+
+# ---- C ABI -----------------------------------------------------------------------------------
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+
+    ge.build()
+    from cosmos_curate_b200 import _lib
+
+    declared = _lib.header_symbols()
+    assert len(declared) >= 25
+    assert set(declared) == set(_lib.SIGNATURES), set(declared) ^ set(_lib.SIGNATURES)
+    lib = _lib.load()  # binds every signature; AttributeError if the .so lacks one
+    assert lib.cb_abi_version() == 1
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in nm.splitlines() if " T " in line}
+    assert set(declared) <= exported
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cosmos_curate_b200 import _lib
+    from cosmos_curate_b200.runtime import Context
+
+    with pytest.raises(_lib.CurateB200Error):
+        Context(0)
+    import ctypes as C
+
+    h = C.c_void_p()
+    assert _lib.load().cb_init(0, C.byref(h)) == -1  # CB_ERR_CUDA, loudly
+    assert b"no CPU fallback" in _lib.load().cb_last_error(None)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = ROOT / "cosmos_curate_b200"
+    for p in pkg.rglob("*"):
+        if p.suffix in (".py", ".cu", ".cpp", ".h", ".cuh"):
+            text = p.read_text()
+            assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text, p
+
+
+# ---- index math (product module) vs the reference ----------------------------------------------
+def test_product_sampling_matches_reference_vectors():
+    from cosmos_curate_b200 import sampling
+
+    g = load_golden("sampling_ref.npz")
+    n = 0
+    for m in golden_json(g, "meta"):
+        if "raises" in m:
+            continue
+        c = m["case"]
+        ts = g[f"c{c}_ts"]
+        ids, counts, _ = sampling.sample_closest(ts, m["rate"], start=ts[0], stop=ts[-1], endpoint=m["endpoint"], dedup=True)
+        np.testing.assert_array_equal(ids, g[f"c{c}_ids"], err_msg=json.dumps(m))
+        np.testing.assert_array_equal(counts, g[f"c{c}_counts"], err_msg=json.dumps(m))
+        assert ids.dtype == np.int32 and counts.dtype == np.int32
+        n += 1
+    assert n >= 100
+    for k in range(8):
+        np.testing.assert_array_equal(sampling.find_closest_indices(g[f"f{k}_src"], g[f"f{k}_dst"]), g[f"f{k}_idx"])
+
+
+def test_product_sampling_reference_kats():
+    from cosmos_curate_b200 import sampling
+    from test_oracle_cpu import FCI_KATS, SC_KATS
+
+    for src, dst, want in FCI_KATS:
+        assert sampling.find_closest_indices(np.array(src, dtype=F), np.array(dst, dtype=F)).tolist() == want
+    for src, rate, start, stop, endpoint, ids, counts, dedup in SC_KATS:
+        gi, gc, _ = sampling.sample_closest(np.array(src, dtype=F), rate, start, stop, endpoint, dedup)
+        assert gi.tolist() == ids and gc.tolist() == counts
+    with pytest.raises(ValueError):
+        sampling.sample_closest(np.arange(3, dtype=F), -1.0)
+
+
+def test_signature_and_plan():
+    from cosmos_curate_b200 import sampling as s
+
+    sig = s.FrameExtractionSignature(s.FrameExtractionPolicy.sequence, 1.0).to_str()
+    assert sig == "FrameExtractionPolicy.sequence-1000"  # key format of clip.extracted_frames
+    ts = np.arange(300, dtype=F) / F(30)
+    plan = s.plan_extraction(ts, (s.FrameExtractionPolicy.sequence,), [1, 2])
+    assert plan["FrameExtractionPolicy.sequence-2000"].tolist() == [*range(0, 300, 15), 299]
+    np.testing.assert_array_equal(plan["FrameExtractionPolicy.sequence-1000"], plan["FrameExtractionPolicy.sequence-2000"][::2])
+    plan = s.plan_extraction(ts, (s.FrameExtractionPolicy.sequence,), [1.5])
+    assert len(plan["FrameExtractionPolicy.sequence-1500"]) == 16  # endpoint=True adds the last frame
+    ids, counts = s.frame_ids(ts, s.FrameExtractionPolicy.middle, 1.0)
+    assert ids.tolist() == [0] and counts.tolist() == [1]  # reference quirk
+    with pytest.raises(ValueError):
+        s.frame_ids(np.array([], dtype=F), s.FrameExtractionPolicy.sequence, 1.0)
+    with pytest.raises(NotImplementedError):
+        s.frame_ids(ts, s.FrameExtractionPolicy.first, 1.0)
+
+
+# ---- MP4 index (host-only C code) ---------------------------------------------------------------
+def test_mp4_index_of_reference_fixture():
+    from cosmos_curate_b200 import sampling
+    from cosmos_curate_b200.runtime import mp4_index
+
+    data = np.fromfile(GOLDEN / "sintel_clip_10s.mp4", dtype=np.uint8)
+    idx = mp4_index(data)
+    assert (idx["codec"], idx["width"], idx["height"], idx["timescale"]) == (4, 854, 480, 12288)
+    assert idx["n_samples"] == 240 and idx["n_sync"] == 1 and not idx["has_ctts"]
+    np.testing.assert_array_equal(idx["pts"], np.arange(240) * 512)
+    ts = sampling.timestamps_from_index(idx["pts"], idx["timescale"])
+    assert ts.dtype == np.float32
+    ids, _ = sampling.frame_ids(ts, sampling.FrameExtractionPolicy.sequence, 1.0)
+    assert ids.tolist() == [0, 24, 48, 72, 96, 120, 144, 168, 192, 216, 239]
+    cv2 = pytest.importorskip("cv2")
+    cap = cv2.VideoCapture(str(GOLDEN / "sintel_clip_10s.mp4"))
+    assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == idx["n_samples"]
+
+
+def test_mp4_index_rejects_garbage():
+    from cosmos_curate_b200._lib import CurateB200Error
+    from cosmos_curate_b200.runtime import mp4_index
+
+    data = np.fromfile(GOLDEN / "sintel_clip_10s.mp4", dtype=np.uint8)
+    for bad in (np.zeros(4, np.uint8), np.zeros(4096, np.uint8), data[: len(data) // 2], np.frombuffer(b"\x00\x00\x00\x18ftypisom" + b"\x00" * 64, np.uint8)):
+        with pytest.raises(CurateB200Error) as e:
+            mp4_index(bad)
+        assert e.value.code == -5  # CB_ERR_DEMUX
+    rng = np.random.default_rng(0)
+    for _ in range(200):  # bit-flip fuzz of the moov box: must never crash
+        d = data.copy()
+        pos = rng.integers(len(d) - 20000, len(d), size=8)
+        d[pos] = rng.integers(0, 256, size=8)
+        try:
+            mp4_index(d)
+        except CurateB200Error:
+            pass

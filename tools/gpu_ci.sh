@@ -1,5 +1,12 @@
 #!/bin/bash
-# Run on the B200 box: GPU parity tests (+ optional extra args), logs into gpurun_out/.
+# Run on the B200 box: GPU parity tests, one pytest process per file (a sticky CUDA error in one file must
+# not mask the others), logs into gpurun_out/.
 mkdir -p gpurun_out
-tools/cuvid_probe > gpurun_out/cuvid_probe.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -q --timeout 240 --timeout-method thread "$@" 2>&1 | tee gpurun_out/pytest_gpu.log | tail -40
+rc=0
+for f in ${GPU_TEST_FILES:-tests/test_gpu_preprocess.py tests/test_gpu_ops.py tests/test_gpu_tower.py tests/test_gpu_decode.py}; do
+  [ -f "$f" ] || continue
+  echo "=== $f"
+  timeout 900 python -m pytest "$f" -m gpu -q --timeout 240 --timeout-method thread "$@" 2>&1 | tee gpurun_out/$(basename $f .py).log | tail -25
+  [ ${PIPESTATUS[0]} -eq 0 ] || rc=1
+done
+exit $rc

@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the decode -> sample -> preprocess -> embed/classify hot path on B200.
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps K --warmup W # the reference's CPU path (oracle) on host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): synthetic 1920x1080 30 fps 10 s H.264 clips (tools/synth_h264.py: no encoder
+exists in this image), sampled at 1 fps like AestheticFilterStage (11 frames per clip), CLIP ViT-L/14 image tower
+(seeded random weights) + aesthetic affine head.  One STEP = `--clips-per-step` clips (default 24 -> 264 frames,
+the closest whole-clip count to the 256-frame batch BASELINE.json names).
+
+Printed JSON line (rank 0):
+  value   clips/s, whole job, decoded NV12 surfaces of the step already resident in HBM (preprocess + tower + head),
+          timed with CUDA events, max over ranks.
+  e2e     clips/s through the public stage API from HOST mp4 buffers: MP4 index + NVDEC decode + fused preprocess +
+          tower + D2H of embeddings/scores, wall clock between device synchronisations, max over ranks.
+  roofline      the dominant kernel (tcgen05 GEMM): algorithmic FLOPs per launch / CUDA-event time per launch vs the
+                measured sustained bf16 peak (MEASURED_PEAKS.json); roofline_other has preprocess / LayerNorm (HBM).
+  cpu_baseline  the oracle's CPU restatement of the reference path timed on the host cores (N=1, rank 0), bounded sample.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+os.environ.setdefault("OPENCV_LOG_LEVEL", "ERROR")
+
+import numpy as np  # noqa: E402
+
+FRAME_W, FRAME_H, FPS, SECONDS = 1920, 1080, 30, 10.0
+SAMPLE_FPS = 1.0
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def peaks() -> tuple[dict, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        busy = sorted(sm)[len(sm) // 2 :] if sm else []  # upper half = samples under load
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_clips(n_distinct: int, rank: int) -> list[bytes]:
+    from tools import synth_h264
+
+    return [synth_h264.make_clip(FRAME_W, FRAME_H, FPS, SECONDS, seed=1000 * rank + i, gop=FPS, pan=(2, 0)) for i in range(n_distinct)]
+
+
+# ================================================================================================ reference arm
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # under torchrun only rank 0 measures the CPU path
+    import torch
+
+    from oracle import cpu_path, vit
+
+    cores = os.cpu_count() or 1
+    cfg = vit.CLIP_VIT_L14
+    w = vit.random_weights(cfg, seed=0)
+    sd = vit.random_aesthetic_mlp(seed=0, in_dim=cfg.proj_dim)
+    path = cpu_path.CpuReferencePath(cfg, w, sd, threads=cores)
+    clips = make_clips(2, 0)
+    sample = max(1, args.ref_clips)
+    batch = [clips[i % len(clips)] for i in range(sample)]
+    for _ in range(args.warmup):
+        path.run(batch[:1], SAMPLE_FPS)
+    t, frames, phases = 0.0, 0, {"decode_s": 0.0, "preprocess_s": 0.0, "model_s": 0.0}
+    for _ in range(args.steps):
+        r = path.run(batch, SAMPLE_FPS)
+        t += r["seconds"]
+        frames += r["frames"]
+        for k in phases:
+            phases[k] += r[k]
+    value = sample * args.steps / t
+    line = {
+        "impl": "reference", "metric": "clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "frames_per_sec": frames / t,
+        "config": {"workload": "1080p30 10s H.264 clips -> 1 fps sampling -> CLIP ViT-L/14 embed + aesthetic score", "clips_per_step": sample,
+                   "frames_per_clip": frames // (sample * args.steps), "model": "clip-vit-large-patch14 (seeded random weights)", "parallelism": "host threads"},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} clip(s) per step x {args.steps} steps; cv2/libavcodec decode (PyAV stand-in) + torchvision transforms + oracle torch-fp32 tower",
+                         "phase_seconds": phases},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "torch_threads": torch.get_num_threads(),
+    }  # fmt: skip
+    print(json.dumps(line))
+
+
+# ================================================================================================ this repo's arm
+def run_b200(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from concurrent.futures import ThreadPoolExecutor
+
+    from cosmos_curate_b200 import sampling
+    from cosmos_curate_b200.models import weights as W
+    from cosmos_curate_b200.runtime import Context, Decoder, VitTower, alloc_nv12_pool, mp4_index
+
+    ctx = Context(local)
+    cfg = W.CLIP_VIT_L14
+    cps = args.clips_per_step
+    clips = make_clips(args.distinct_clips, rank)
+    plans = []
+    for c in clips:
+        idx = mp4_index(c)
+        ts = sampling.timestamps_from_index(idx["pts"], idx["timescale"])
+        ids, counts = sampling.frame_ids(ts, sampling.FrameExtractionPolicy.sequence, SAMPLE_FPS)
+        plans.append(np.repeat(ids, counts).astype(np.int32))
+    fpc = len(plans[0])
+    frames_per_step = cps * fpc
+    tower = VitTower(ctx, cfg.to_dict(), W.seeded_weights(cfg, 0), max_batch=frames_per_step, aesthetic=W.seeded_aesthetic(cfg.proj_dim, 0))
+    pools = [alloc_nv12_pool(ctx, frames_per_step, FRAME_W, FRAME_H) for _ in range(2)]
+    n_dec = args.decoders
+    decoders = [Decoder(ctx) for _ in range(n_dec)]
+    tp = ThreadPoolExecutor(max_workers=n_dec)
+    host_emb = torch.empty((frames_per_step, cfg.proj_dim), dtype=torch.float32).pin_memory()
+    host_score = torch.empty((frames_per_step,), dtype=torch.float32).pin_memory()
+    step_clips = [i % len(clips) for i in range(cps)]
+
+    def decode_step(pool):
+        def work(j):
+            k = step_clips[j]
+            # worker thread j % n_dec owns decoders[j % n_dec]: submit in waves so a decoder is never shared
+            return decoders[j % n_dec].decode(clips[k], plans[k], pool, np.arange(j * fpc, (j + 1) * fpc, dtype=np.int32))["frames_decoded"]
+
+        done = 0
+        for wave in range(0, cps, n_dec):
+            done += sum(tp.map(work, range(wave, min(cps, wave + n_dec))))
+        return done
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident-input measurement (value): decoded surfaces of one step already in HBM
+    decoded_per_step = decode_step(pools[0])
+    barrier()
+    for _ in range(max(args.warmup, 3)):
+        tower.embed_pool(pools[0])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.profile_begin()
+    ev0.record()
+    for _ in range(args.steps):
+        emb, _, score = tower.embed_pool(pools[0])
+    ev1.record()
+    prof = ctx.profile_end()
+    barrier()
+    dev_s = max_over_ranks(ev0.elapsed_time(ev1) / 1e3)
+    launches = ctx.launch_count() - l0
+    value = world * cps * args.steps / dev_s
+
+    # ---- end-to-end measurement (e2e): host mp4 bytes -> NVDEC -> preprocess -> tower -> host results
+    def e2e_step(i):
+        pool = pools[i & 1]
+        decode_step(pool)
+        emb, _, score = tower.embed_pool(pool)
+        host_emb.copy_(emb, non_blocking=True)
+        host_score.copy_(score, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e = None
+    if not args.no_e2e:
+        for i in range(max(1, min(args.warmup, 2))):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.e2e_steps):
+            e2e_step(i)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        h2d = sum(len(clips[k]) for k in step_clips)
+        e2e = {"value": world * cps * args.e2e_steps / e2e_s, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": frames_per_step * (cfg.proj_dim + 1) * 4,
+               "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "frames_per_sec": world * frames_per_step * args.e2e_steps / e2e_s,
+               "decoded_frames_per_sec": world * decoded_per_step * args.e2e_steps / e2e_s, "nvdec_sessions": n_dec,
+               "note": "every frame up to the last sampled one is decoded (reference semantics); bitstream is I_PCM-heavy synthetic H.264"}  # fmt: skip
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_src = peaks()
+    gemm_flops = cfg.gemm_flops_per_image() * frames_per_step * args.steps
+    gemm_ms, gemm_n = prof["gemm"]["ms"], max(1, prof["gemm"]["launches"])
+    ach_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    pre_bytes = (1.5 * min(FRAME_W, FRAME_H) ** 2 + 3 * 224 * 224 * 2) * frames_per_step * args.steps
+    ln_bytes = 6.0 * cfg.tokens * cfg.hidden * frames_per_step * (2 * cfg.layers) * args.steps  # fp32 in + fp16 out per LayerNorm
+    other = {}
+    for name, nbytes, key in (("preprocess", pre_bytes, "preprocess"), ("layernorm", ln_bytes, "layernorm")):
+        ms = prof[key]["ms"]
+        gbs = nbytes / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        other[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                       "ms_per_step": ms / args.steps, "launches_per_step": prof[key]["launches"] / args.steps}  # fmt: skip
+    other["attention"] = {"ms_per_step": prof["attention"]["ms"] / args.steps, "launches_per_step": prof["attention"]["launches"] / args.steps}
+    step_ms = 1e3 * dev_s / args.steps
+    line = {
+        "metric": "clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "frames_per_sec": world * frames_per_step * args.steps / dev_s,
+        "config": {"workload": "1x B200 per rank: 1080p30 10s H.264 clips, NVDEC + fused preprocess + CLIP-ViT-L/14 embed + aesthetic score (BASELINE.json configs[1])",
+                   "clips_per_step": cps, "frames_per_clip": fpc, "frames_per_step": frames_per_step, "sample_fps": SAMPLE_FPS, "distinct_clips": args.distinct_clips,
+                   "model": "clip-vit-large-patch14, seeded random weights, fp16 operands / fp32 accumulate+residual", "parallelism": f"dp{world} (clips sharded per rank, no data-path collective)",
+                   "l2": "inputs (NV12 pool 0.88 GB + activations > 1 GB) exceed the 126 MB L2", "value_inputs": "decoded NV12 surfaces resident in HBM"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
+                     "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)", "launches_per_step": gemm_n / args.steps,
+                     "ms_per_step": gemm_ms / args.steps, "share_of_step": gemm_ms / args.steps / step_ms},
+        "roofline_other": other,
+        "e2e": e2e,
+    }  # fmt: skip
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(clips[:1])
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(clips: list[bytes]) -> dict:
+    """Bounded CPU sample of the same workload: the oracle's restatement of the reference path (kind 'port')."""
+    from oracle import cpu_path, vit
+
+    cores = os.cpu_count() or 1
+    cfg = vit.CLIP_VIT_L14
+    path = cpu_path.CpuReferencePath(cfg, vit.random_weights(cfg, seed=0), vit.random_aesthetic_mlp(seed=0, in_dim=cfg.proj_dim), threads=cores)
+    path.run(clips[:1], SAMPLE_FPS)  # warm-up (thread pools, allocator)
+    n = 2
+    r = path.run([clips[i % len(clips)] for i in range(n)], SAMPLE_FPS)
+    return {"value": r["clips"] / r["seconds"], "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": f"{n} clips (1080p30 10 s, {r['frames']} sampled frames): cv2/libavcodec decode + torchvision transforms + oracle torch-fp32 ViT-L/14",
+            "frames_per_sec": r["frames"] / r["seconds"], "phase_seconds": {k: r[k] for k in ("decode_s", "preprocess_s", "model_s")}}  # fmt: skip
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clips-per-step", type=int, default=24)
+    ap.add_argument("--distinct-clips", type=int, default=4)
+    ap.add_argument("--decoders", type=int, default=12, help="concurrent NVDEC sessions per GPU (7 engines on B200)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-clips", type=int, default=2, help="clips per step of the reference arm (bounded sample)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -68,6 +68,8 @@ SIGNATURES = {
     "cb_last_error": (C.c_char_p, [_vp]),
     "cb_device_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(C.c_size_t)]),
     "cb_launch_count": (C.c_ulonglong, [_vp]),
+    "cb_profile_begin": (_i, [_vp]),
+    "cb_profile_end": (_i, [_vp, _vp, _pf, C.POINTER(_i), _i]),
     "cb_preprocess_clip": (_i, [_vp, C.POINTER(SurfacePool), _pi32, _i, _i, _i, _i, _i, _i, _pf, _pf, _vp, _vp]),
     "cb_preprocess_clip_u8": (_i, [_vp, C.POINTER(SurfacePool), _pi32, _i, _i, _vp, _vp]),
     "cb_preprocess_bilinear_u8": (_i, [_vp, C.POINTER(SurfacePool), _pi32, _i, _i, _i, _vp, _vp]),

@@ -43,9 +43,49 @@ int make_tensor_map(cb_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dtype, in
   return CB_OK;
 }
 
+void mark_launch(cb_ctx* ctx, int category, cudaStream_t stream) {
+  ctx->launches++;
+  if (!ctx->prof_on) return;
+  if (ctx->prof_n >= ctx->prof_ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    ctx->prof_ev.push_back(e);
+    ctx->prof_cat.push_back(0);
+  }
+  ctx->prof_cat[ctx->prof_n] = category;
+  cudaEventRecord(ctx->prof_ev[ctx->prof_n], stream);
+  ctx->prof_n++;
+}
+
 }  // namespace cb
 
 extern "C" {
+
+int cb_profile_begin(cb_ctx* ctx) {
+  if (!ctx) return CB_ERR_ARG;
+  ctx->prof_on = true;
+  ctx->prof_n = 0;
+  return CB_OK;
+}
+
+int cb_profile_end(cb_ctx* ctx, void* stream, float* ms_by_category, int* launches_by_category, int n_categories) {
+  if (!ctx) return CB_ERR_ARG;
+  if (!ctx->prof_on) return cb::fail(ctx, CB_ERR_STATE, "profile_end without profile_begin");
+  if (!ms_by_category || !launches_by_category || n_categories < CB_PROF_CATEGORIES) return cb::fail(ctx, CB_ERR_ARG, "profile_end: need %d categories", CB_PROF_CATEGORIES);
+  cb::mark_launch(ctx, -1, (cudaStream_t)stream);  // closing event
+  ctx->launches--;
+  ctx->prof_on = false;
+  CB_CUDA(ctx, cudaEventSynchronize(ctx->prof_ev[ctx->prof_n - 1]));
+  for (int i = 0; i < n_categories; ++i) ms_by_category[i] = 0.f, launches_by_category[i] = 0;
+  for (size_t i = 0; i + 1 < ctx->prof_n; ++i) {
+    float ms = 0.f;
+    CB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[i], ctx->prof_ev[i + 1]));
+    const int c = ctx->prof_cat[i];
+    if (c >= 0 && c < n_categories) ms_by_category[c] += ms, launches_by_category[c]++;
+  }
+  ctx->prof_n = 0;
+  return CB_OK;
+}
 
 int cb_abi_version(void) { return CB_ABI_VERSION; }
 
@@ -91,6 +131,7 @@ void cb_destroy(cb_ctx* ctx) {
     cudaFree(kv.second.d_w);
   }
   if (ctx->d_norm_lut) cudaFree(ctx->d_norm_lut);
+  for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
   delete ctx;
 }
 

@@ -42,12 +42,19 @@ struct cb_ctx {
   float* d_norm_lut = nullptr;                                  // [3*256] fp32, normalise LUT currently loaded
   float lut_mean[3] = {0, 0, 0}, lut_std[3] = {0, 0, 0};
   unsigned long long launches = 0;  // kernels launched by this library (bench.py reports it)
+  // per-category kernel timing (cb_profile_begin/end): one event before every launch, categories CB_PROF_*
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<int> prof_cat;
+  size_t prof_n = 0;
   void* nvdec = nullptr;            // lazily created NVDEC state (nvdec.cpp)
 };
 
 namespace cb {
 
 int fail(cb_ctx* ctx, int code, const char* fmt, ...);
+// Called immediately before every kernel launch of the library: counts it and, when profiling, drops an event.
+void mark_launch(cb_ctx* ctx, int category, cudaStream_t stream);
 
 #define CB_CUDA(ctx, expr)                                                                                   \
   do {                                                                                                       \

@@ -223,8 +223,8 @@ static int launch_gemm(cb_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb
   }
   const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
   const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+  mark_launch(ctx, CB_PROF_GEMM, stream);
   kern<<<grid, kGemmThreads, Cfg::kSmem, stream>>>(ma, mb, g);
-  ctx->launches++;
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }

@@ -487,6 +487,7 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
   size_t smem = 2 * (size_t)raw_stage + (size_t)3 * kSR * (a.swa + 1) * 4 + (size_t)3 * a.ring * (a.tc | 1) * 4 + (size_t)npx * k_pad * 2 + 32;
   if (smem > 227 * 1024) return fail(ctx, CB_ERR_UNSUPPORTED, "preprocess tile needs %zu bytes of shared memory", smem);
   dim3 grid(tiles, n);
+  mark_launch(ctx, CB_PROF_PREPROCESS, stream);
   if (pool->format == CB_FMT_NV12) {
     CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_kernel<CB_FMT_NV12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     clip_preprocess_kernel<CB_FMT_NV12><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
@@ -494,7 +495,6 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
     CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_kernel<CB_FMT_RGB24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     clip_preprocess_kernel<CB_FMT_RGB24><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
   }
-  ctx->launches++;
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }
@@ -512,15 +512,15 @@ static int run_simple(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* s
   a.out_w = out_w, a.out_h = out_h, a.out = out;
   rc = upload_slots(ctx, slots, n, stream, &a.slots);
   if (rc) return rc;
+  if (bilinear && (out_w <= 0 || out_h <= 0)) return fail(ctx, CB_ERR_ARG, "bad output size");
+  mark_launch(ctx, CB_PROF_PREPROCESS, stream);
   if (bilinear) {
-    if (out_w <= 0 || out_h <= 0) return fail(ctx, CB_ERR_ARG, "bad output size");
     const long long total = (long long)n * out_w * out_h;
     bilinear_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
   } else {
     const long long total = (long long)n * a.h * ((a.w + 1) / 2);
     nv12_to_rgb_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
   }
-  ctx->launches++;
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }

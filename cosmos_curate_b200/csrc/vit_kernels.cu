@@ -335,8 +335,8 @@ int layernorm_f16(cb_ctx* ctx, const float* x, const float* gamma, const float* 
   if (!x || !gamma || !beta || !y) return fail(ctx, CB_ERR_ARG, "layernorm: null operand");
   if (rows <= 0) return CB_OK;
   if (d % 128 || d > 128 * kLnMaxChunks) return fail(ctx, CB_ERR_UNSUPPORTED, "layernorm: d=%d must be a multiple of 128 and <= %d", d, 128 * kLnMaxChunks);
+  mark_launch(ctx, CB_PROF_LAYERNORM, stream);
   layernorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, gamma, beta, (__half*)y, rows, d, eps);
-  ctx->launches++;
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }
@@ -345,8 +345,8 @@ int assemble_tokens(cb_ctx* ctx, const float* patch, const float* cls, const flo
                     int tokens, int grid2, int d, float eps, cudaStream_t stream) {
   if (d % 128 || d > 128 * kLnMaxChunks) return fail(ctx, CB_ERR_UNSUPPORTED, "assemble: d=%d unsupported", d);
   const int rows = n * tokens;
+  mark_launch(ctx, CB_PROF_OTHER, stream);
   assemble_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(patch, cls, pos, gamma, beta, h, n, tokens, grid2, d, eps);
-  ctx->launches++;
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }
@@ -361,6 +361,7 @@ int attention_f16(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, in
   const size_t smem = (size_t)2 * t_pad * (hd + 8) * 2;
   if (smem > 200 * 1024) return fail(ctx, CB_ERR_UNSUPPORTED, "attention: %d tokens need %zu bytes of shared memory (K/V streaming not built yet)", tokens, smem);
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
+  mark_launch(ctx, CB_PROF_ATTENTION, stream);
   if (hd == 64) {
     CB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attention_kernel<64><<<n * heads, kAttnThreads, smem, stream>>>((const __half*)qkv, (__half*)out, tokens, heads, head_dim, scale_log2e);
@@ -368,7 +369,6 @@ int attention_f16(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, in
     CB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attention_kernel<80><<<n * heads, kAttnThreads, smem, stream>>>((const __half*)qkv, (__half*)out, tokens, heads, head_dim, scale_log2e);
   }
-  ctx->launches++;
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }
@@ -377,8 +377,8 @@ int clip_tail(cb_ctx* ctx, const float* h, size_t img_stride, const float* gamma
               float eps, const float* aes_w, float aes_b, float* emb_out, float* feat_out, float* score_out, int n, cudaStream_t stream) {
   const int out_dim = proj ? proj_dim : d;
   const size_t smem = (size_t)(d + out_dim) * sizeof(float);
+  mark_launch(ctx, CB_PROF_OTHER, stream);
   clip_tail_kernel<<<n, 256, smem, stream>>>(h, img_stride, gamma, beta, proj, d, proj_dim, eps, aes_w, aes_b, emb_out, feat_out, score_out);
-  ctx->launches++;
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }

@@ -1,0 +1,196 @@
+"""Task containers the path reads and mutates.
+
+Inside a cosmos-curate environment the reference's own classes are re-exported.  Otherwise slim stand-ins with
+the SAME field names are defined, restating only the fields this path touches:
+
+    LazyData            cosmos_curate/core/utils/data/lazy_data.py:189-405   (inline payloads only; no Ray Plasma here)
+    Clip / ClipStats    cosmos_curate/pipelines/video/utils/data_model.py:194-343, 345-390
+    Video               :413-600
+    SplitPipeTask       :690-800
+    StagePerfStats      cosmos_curate/core/utils/infra/performance_utils.py:70-140
+    StageTimer          :195-330   (reinit / time_process / log_stats call pattern; no OTel)
+"""
+
+from __future__ import annotations
+
+import contextlib
+import pathlib
+import time
+from typing import Any
+from uuid import UUID
+
+import attrs
+import numpy as np
+
+from .interfaces import PipelineTask
+
+try:  # pragma: no cover - full cosmos-curate environment
+    from cosmos_curate.core.utils.data.lazy_data import LazyData
+    from cosmos_curate.core.utils.infra.performance_utils import StagePerfStats, StageTimer
+    from cosmos_curate.pipelines.video.utils.data_model import Clip, ClipStats, SplitPipeTask, Video
+
+    USING_REFERENCE_DATA_MODEL = True
+except Exception:  # noqa: BLE001
+    USING_REFERENCE_DATA_MODEL = False
+
+    def bytes_to_numpy(data: bytes) -> np.ndarray:
+        return np.frombuffer(data, dtype=np.uint8)
+
+    @attrs.define(eq=False)
+    class LazyData:
+        value: Any = None
+        ref: Any = attrs.field(default=None, repr=False)
+        nbytes: int = 0
+
+        @classmethod
+        def coerce(cls, val):
+            if isinstance(val, LazyData):
+                return cls(ref=val.ref, value=val.value, nbytes=val.nbytes)
+            if isinstance(val, bytes):
+                arr = bytes_to_numpy(val)
+                return cls(value=arr, nbytes=arr.nbytes)
+            return cls(value=val, nbytes=getattr(val, "nbytes", 0) if val is not None else 0)
+
+        def resolve(self):
+            return self.value  # inline only (the reference's .store() calls are disabled, lazy_data.py:49-54)
+
+        def store(self) -> None:
+            return
+
+        def release(self) -> None:
+            self.value = None
+
+        def drop(self) -> None:
+            self.value, self.ref, self.nbytes = None, None, 0
+
+        def __bool__(self) -> bool:
+            return self.value is not None or self.ref is not None
+
+    @attrs.define
+    class ClipStats:
+        num_filtered_by_motion: int = 0
+        num_filtered_by_aesthetic: int = 0
+        num_filtered_by_qwen_classifier: int = 0
+        num_filtered_by_qwen_semantic: int = 0
+        num_filtered_by_artificial_text: int = 0
+        num_passed: int = 0
+        num_transcoded: int = 0
+
+    @attrs.define
+    class Clip:
+        uuid: UUID
+        source_video: str
+        span: tuple[float, float]
+        encoded_data: LazyData = attrs.field(factory=LazyData, converter=LazyData.coerce)
+        extracted_frames: LazyData = attrs.field(factory=LazyData)
+        aesthetic_score: float | None = None
+        cosmos_embed1_embedding: np.ndarray | None = None
+        intern_video_2_embedding: np.ndarray | None = None
+        openai_embedding: np.ndarray | None = None
+        errors: dict[str, str] = attrs.Factory(dict)
+
+    @attrs.define
+    class Video:
+        input_video: pathlib.Path | str
+        relative_path: str = ""
+        encoded_data: LazyData = attrs.field(factory=LazyData, converter=LazyData.coerce)
+        frame_array: LazyData = attrs.field(factory=LazyData, converter=LazyData.coerce)
+        timestamps: np.ndarray | None = attrs.field(default=None, eq=False)
+        clips: list[Clip] = attrs.Factory(list)
+        filtered_clips: list[Clip] = attrs.Factory(list)
+        num_total_clips: int = 0
+        num_clip_chunks: int = 0
+        clip_chunk_index: int = 0
+        clip_stats: ClipStats = attrs.Factory(ClipStats)
+        errors: dict[str, str] = attrs.Factory(dict)
+
+    @attrs.define
+    class StagePerfStats:
+        process_time: float = 0.0
+        actor_idle_time: float = 0.0
+        input_data_size_mb: float = 0.0
+        rss_before_mb: float = 0.0
+        rss_after_mb: float = 0.0
+        rss_delta_mb: float = 0.0
+        wall_start: float = 0.0
+        wall_end: float = 0.0
+
+    @attrs.define
+    class SplitPipeTask(PipelineTask):
+        session_id: str = ""
+        videos: list[Video] = attrs.field(factory=list)
+        stage_perf: dict[str, StagePerfStats] = attrs.Factory(dict)
+        errors: dict[str, str] = attrs.Factory(dict)
+        _init_video: Video | None = attrs.field(default=None, init=True, alias="video")
+
+        def __attrs_post_init__(self) -> None:
+            if self._init_video is not None:
+                if self.videos:
+                    msg = "Cannot specify both 'video' and 'videos' parameters"
+                    raise ValueError(msg)
+                self.videos = [self._init_video]
+                self._init_video = None
+
+        @property
+        def video(self) -> Video:
+            return self.videos[0]
+
+        def get_major_size(self) -> int:
+            total = 0
+            for v in self.videos:
+                total += v.encoded_data.nbytes + v.frame_array.nbytes
+                for c in v.clips:
+                    total += c.encoded_data.nbytes + c.extracted_frames.nbytes
+            return total
+
+    def _rss_mb() -> float:
+        try:
+            import psutil
+
+            return psutil.Process().memory_info().rss / (1024 * 1024)
+        except Exception:  # noqa: BLE001
+            return 0.0
+
+    class StageTimer:
+        """performance_utils.py:195-330: per-process_data timing recorded into task.stage_perf."""
+
+        def __init__(self, stage) -> None:
+            self._stage_name = str(stage.__class__.__name__)
+            self._last_active_time = time.time()
+            self._initialized = False
+            self._reset()
+
+        def _reset(self) -> None:
+            self._num_samples = 0
+            self._durations_s: list[float] = []
+            self._input_data_size_b = 0
+            self._start = 0.0
+            self._idle_time_s = 0.0
+            self._rss_before_mb = 0.0
+
+        def reinit(self, stage, stage_input_size: int = 1) -> None:
+            self._reset()
+            self._input_data_size_b = stage_input_size
+            self._rss_before_mb = _rss_mb()
+            self._start = time.time()
+            if self._initialized:
+                self._idle_time_s = self._start - self._last_active_time
+            self._initialized = True
+
+        @contextlib.contextmanager
+        def time_process(self, num_samples: int = 1, source_video_duration_s: float = 0):
+            t0 = time.time()
+            yield
+            dur = time.time() - t0
+            self._num_samples += num_samples
+            self._durations_s.extend([dur / max(1, num_samples)] * num_samples)
+
+        def log_stats(self, *, verbose: bool = False):
+            end = time.time()
+            self._last_active_time = end
+            rss_after = _rss_mb()
+            return self._stage_name, StagePerfStats(
+                process_time=end - self._start, actor_idle_time=self._idle_time_s, input_data_size_mb=self._input_data_size_b / 1024 / 1024,
+                rss_before_mb=self._rss_before_mb, rss_after_mb=rss_after, rss_delta_mb=rss_after - self._rss_before_mb,
+                wall_start=self._start, wall_end=end,
+            )  # fmt: skip

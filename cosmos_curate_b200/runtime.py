@@ -6,6 +6,7 @@ Nothing here computes on the data path; every operation is a call into libcurate
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -41,9 +42,12 @@ class Context:
         h = C.c_void_p()
         check(self.lib.cb_init(self.device, C.byref(h)), "cb_init")
         self.h = h
+        self._children = weakref.WeakSet()  # towers / decoders created on this context: closed before it
 
     def close(self):
         if getattr(self, "h", None):
+            for child in list(self._children):
+                child.close()
             self.lib.cb_destroy(self.h)
             self.h = None
 
@@ -55,6 +59,17 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.cb_launch_count(self.h))
+
+    PROF_CATEGORIES = ("preprocess", "gemm", "layernorm", "attention", "other")
+
+    def profile_begin(self) -> None:
+        check(self.lib.cb_profile_begin(self.h), "cb_profile_begin", self.h)
+
+    def profile_end(self) -> dict:
+        n = len(self.PROF_CATEGORIES)
+        ms, cnt = (C.c_float * n)(), (C.c_int * n)()
+        check(self.lib.cb_profile_end(self.h, _stream_ptr(), ms, cnt, n), "cb_profile_end", self.h)
+        return {k: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, k in enumerate(self.PROF_CATEGORIES)}
 
     def device_info(self) -> dict:
         sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
@@ -176,6 +191,7 @@ class VitTower:
         h = C.c_void_p()
         check(self.lib.cb_vit_create(ctx.h, C.byref(c), C.byref(h)), "cb_vit_create", ctx.h)
         self.h = h
+        ctx._children.add(self)
         for name, arr in weights.items():
             a = np.ascontiguousarray(arr, dtype=np.float32)
             check(self.lib.cb_vit_set_tensor(self.h, name.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), a.size), f"cb_vit_set_tensor({name})", ctx.h)
@@ -254,6 +270,7 @@ class Decoder:
         h = C.c_void_p()
         check(self.lib.cb_decoder_create(ctx.h, C.byref(h)), "cb_decoder_create", ctx.h)
         self.h = h
+        ctx._children.add(self)
 
     def close(self):
         if getattr(self, "h", None):

@@ -47,6 +47,17 @@ int cb_device_info(cb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, siz
 /* Number of kernels this library has launched on `ctx` since cb_init (bench.py "gpu_launches"). */
 unsigned long long cb_launch_count(cb_ctx* ctx);
 
+/* Per-kernel-category device timing: an event is recorded before every launch between begin and end; end
+ * returns the summed milliseconds and launch counts per category (bench.py's roofline figures). */
+#define CB_PROF_PREPROCESS 0
+#define CB_PROF_GEMM 1
+#define CB_PROF_LAYERNORM 2
+#define CB_PROF_ATTENTION 3
+#define CB_PROF_OTHER 4
+#define CB_PROF_CATEGORIES 5
+int cb_profile_begin(cb_ctx* ctx);
+int cb_profile_end(cb_ctx* ctx, void* stream, float* ms_by_category, int* launches_by_category, int n_categories);
+
 /* ---- surfaces ----------------------------------------------------------------------------------- */
 #define CB_FMT_NV12 0  /* Y plane [luma_rows x pitch] then interleaved UV plane [height/2 x pitch] */
 #define CB_FMT_RGB24 1 /* interleaved RGB u8, pitch >= 3*width */

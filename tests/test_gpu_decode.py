@@ -57,7 +57,7 @@ def test_nvdec_sampled_frames_match_libavcodec(ctx):
     for k, i in enumerate(ids):
         np.testing.assert_array_equal(got[k, :h, :w], luma[int(i)].reshape(h, w))  # H.264 decode is bit-exact by spec
         d = np.abs(rgb[k].astype(int) - bgr[int(i)][..., ::-1].astype(int))
-        assert d.mean() < 1.5 and d.max() <= 12  # swscale vs OpenCV-style conversion + chroma siting
+        assert d.mean() < 1.5 and d.max() <= 32  # swscale (bilinear chroma, own rounding) vs OpenCV-style nearest-chroma conversion
     # early stop: only the frames up to the last wanted id are decoded
     st = dec.decode(data, [0, 24, 48], pool, [0, 1, 2])
     assert st["frames_emitted"] == 3 and st["frames_decoded"] <= 48 + 1 + 4

@@ -82,10 +82,12 @@ SIGNATURES = {
     "cb_vit_k_pad": (_i, [_vp]),
     "cb_vit_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "cb_vit_embed_surfaces": (_i, [_vp, C.POINTER(SurfacePool), _pi32, _i, _pf, _pf, _vp, _vp, _vp, _vp]),
+    "cb_affine_score": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _vp]),
     "cb_mp4_index": (_i, [_vp, _vp, C.c_size_t, C.POINTER(Mp4Info), C.POINTER(C.c_int64), C.POINTER(C.c_uint8), _i]),
     "cb_decoder_create": (_i, [_vp, C.POINTER(_vp)]),
     "cb_decoder_destroy": (None, [_vp]),
     "cb_decoder_decode": (_i, [_vp, _vp, C.c_size_t, _pi32, _i, C.POINTER(SurfacePool), _pi32, C.POINTER(DecodeStats)]),
+    "cb_decoder_decode_thumbnails": (_i, [_vp, _vp, C.c_size_t, _i, _i, _vp, _i, C.POINTER(DecodeStats)]),
     "cb_gemm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cb_layernorm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "cb_attention_f16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -131,6 +131,7 @@ void cb_destroy(cb_ctx* ctx) {
     cudaFree(kv.second.d_w);
   }
   if (ctx->d_norm_lut) cudaFree(ctx->d_norm_lut);
+  if (ctx->d_slots) cudaFree(ctx->d_slots);
   for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
   delete ctx;
 }

@@ -48,6 +48,8 @@ struct cb_ctx {
   std::vector<int> prof_cat;
   size_t prof_n = 0;
   void* nvdec = nullptr;            // lazily created NVDEC state (nvdec.cpp)
+  int* d_slots = nullptr;           // device staging of the slot list of the current preprocess call
+  int slots_cap = 0;
 };
 
 namespace cb {
@@ -68,5 +70,7 @@ int make_tensor_map(cb_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dtype, in
 
 const TapTable* get_taps(cb_ctx* ctx, int in_size, int out_size, int crop_off, int crop_len);
 int ensure_norm_lut(cb_ctx* ctx, const float mean[3], const float std_[3], cudaStream_t stream);
+// NV12 -> RGB -> bilinear out_w x out_h for ONE surface at `base` (used on NVDEC-mapped frames), u8 HWC into `out`.
+int bilinear_from_surface(cb_ctx* ctx, const void* base, int pitch, int luma_rows, int w, int h, int out_w, int out_h, uint8_t* out, cudaStream_t stream);
 
 }  // namespace cb

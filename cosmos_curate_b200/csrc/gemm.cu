@@ -11,6 +11,9 @@
 //    patch-embed conv (im2col rows produced by the preprocess kernel) go through this kernel.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -36,13 +39,72 @@ struct GemmArgs {
   int M, N, K;
 };
 
-__device__ __forceinline__ float act_quick_gelu(float x) { return x / (1.f + __expf(-1.702f * x)); }
+// x * sigmoid(1.702 x) with one ex2.approx + one rcp.approx (both ~1 ulp; the result is rounded to fp16 anyway)
+__device__ __forceinline__ float act_quick_gelu(float x) { return __fdividef(x, 1.f + exp2f(-2.4554669595930156f * x)); }
 __device__ __forceinline__ float act_gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   const float u = k0 * (x + k1 * x * x * x);
-  const float e = __expf(2.f * u);  // tanh(u) = 1 - 2/(e^{2u}+1)
-  const float t = 1.f - 2.f / (e + 1.f);
+  const float e = exp2f(2.885390081777927f * u);  // e^{2u}; tanh(u) = 1 - 2/(e^{2u}+1)
+  const float t = 1.f - __fdividef(2.f, e + 1.f);
   return 0.5f * x * (1.f + t);
+}
+
+// One 32-column chunk of the epilogue for this thread's output row: TMEM -> registers -> bias / activation /
+// residual -> 128-bit global stores.
+template <int ACT, bool OUT_F32>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, uint32_t taddr, int row, bool row_ok, int col0) {
+  uint32_t r[32];
+  tmem_ld_32x32b_x32(taddr, r);
+  tmem_ld_wait();
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (g.bias) {
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      if (col0 + j4 * 4 < g.N) {
+        const float4 b = __ldg((const float4*)(g.bias + col0) + j4);
+        v[j4 * 4 + 0] += b.x, v[j4 * 4 + 1] += b.y, v[j4 * 4 + 2] += b.z, v[j4 * 4 + 3] += b.w;
+      }
+    }
+  }
+  if (ACT == CB_EPI_QUICK_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_quick_gelu(v[j]);
+  } else if (ACT == CB_EPI_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_gelu_tanh(v[j]);
+  }
+  if (!row_ok) return;
+  if (OUT_F32) {
+    float4* dst = (float4*)(g.out_f32 + (size_t)row * g.N + col0);
+    const float4* res = g.residual ? (const float4*)(g.residual + (size_t)row * g.N + col0) : nullptr;
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      if (col0 + j4 * 4 < g.N) {
+        float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        if (res) {
+          const float4 rr = res[j4];
+          o.x += rr.x, o.y += rr.y, o.z += rr.z, o.w += rr.w;
+        }
+        dst[j4] = o;
+      }
+    }
+  } else {
+    uint4* dst = (uint4*)(g.out_f16 + (size_t)row * g.N + col0);
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      if (col0 + j8 * 8 < g.N) {
+        __half2 h0 = __floats2half2_rn(v[j8 * 8 + 0], v[j8 * 8 + 1]);
+        __half2 h1 = __floats2half2_rn(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+        __half2 h2 = __floats2half2_rn(v[j8 * 8 + 4], v[j8 * 8 + 5]);
+        __half2 h3 = __floats2half2_rn(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+        uint4 o;
+        o.x = *(uint32_t*)&h0, o.y = *(uint32_t*)&h1, o.z = *(uint32_t*)&h2, o.w = *(uint32_t*)&h3;
+        dst[j8] = o;
+      }
+    }
+  }
 }
 
 template <int BN, int ACT, bool OUT_F32>
@@ -143,59 +205,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       for (int cc = 0; cc < BN / 32; ++cc) {
         const int col0 = n_blk * BN + cc * 32;
         if (col0 >= g.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cc * 32), r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (g.bias) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            if (col0 + j4 * 4 < g.N) {
-              const float4 b = __ldg((const float4*)(g.bias + col0) + j4);
-              v[j4 * 4 + 0] += b.x, v[j4 * 4 + 1] += b.y, v[j4 * 4 + 2] += b.z, v[j4 * 4 + 3] += b.w;
-            }
-          }
-        }
-        if (ACT == CB_EPI_QUICK_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = act_quick_gelu(v[j]);
-        } else if (ACT == CB_EPI_GELU_TANH) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = act_gelu_tanh(v[j]);
-        }
-        if (row_ok) {
-          if (OUT_F32) {
-            float4* dst = (float4*)(g.out_f32 + (size_t)row * g.N + col0);
-            const float4* res = g.residual ? (const float4*)(g.residual + (size_t)row * g.N + col0) : nullptr;
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              if (col0 + j4 * 4 < g.N) {
-                float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                if (res) {
-                  const float4 rr = res[j4];
-                  o.x += rr.x, o.y += rr.y, o.z += rr.z, o.w += rr.w;
-                }
-                dst[j4] = o;
-              }
-            }
-          } else {
-            uint4* dst = (uint4*)(g.out_f16 + (size_t)row * g.N + col0);
-#pragma unroll
-            for (int j8 = 0; j8 < 4; ++j8) {
-              if (col0 + j8 * 8 < g.N) {
-                __half2 h0 = __floats2half2_rn(v[j8 * 8 + 0], v[j8 * 8 + 1]);
-                __half2 h1 = __floats2half2_rn(v[j8 * 8 + 2], v[j8 * 8 + 3]);
-                __half2 h2 = __floats2half2_rn(v[j8 * 8 + 4], v[j8 * 8 + 5]);
-                __half2 h3 = __floats2half2_rn(v[j8 * 8 + 6], v[j8 * 8 + 7]);
-                uint4 o;
-                o.x = *(uint32_t*)&h0, o.y = *(uint32_t*)&h1, o.z = *(uint32_t*)&h2, o.w = *(uint32_t*)&h3;
-                dst[j8] = o;
-              }
-            }
-          }
-        }
+        epilogue_chunk<ACT, OUT_F32>(g, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + cc * 32), row, row_ok, col0);
       }
       tc_fence_before();
       __syncwarp();
@@ -210,6 +220,159 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+
+// ================================================================================================ 2-CTA kernel
+// A CTA pair (cluster of 2 on one TPC) owns a 256 x 256 output tile: tcgen05.mma.cta_group::2 with UMMA_M = 256.
+// Each CTA stages its own 128 rows of A and ONE HALF (128 rows) of the W tile; the MMA reads W from both CTAs'
+// shared memory, so per-CTA L2 traffic per k-block drops from 48 KB (1-CTA 128x256) to 32 KB and the flop/byte of the
+// tile rises from 85 to 131 - the 1-CTA kernel measured L2-bound at ~12 TB/s.  Roles per CTA:
+//   warp 0 TMA producer (loads credited to the LEADER's full barrier), warp 1 MMA issuer (leader CTA only),
+//   warp 2 TMEM allocator, warps 4-11 epilogue (two warps per TMEM lane quarter, each half of the columns).
+constexpr int kGemm2Threads = 384;
+constexpr int BN2 = 256;
+
+struct Gemm2Cfg {
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = BM * BK * 2, kBBytes = (BN2 / 2) * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;  // per CTA
+  static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kTmemCols = 2 * BN2;
+};
+
+template <int ACT, bool OUT_F32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
+    gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+  using Cfg = Gemm2Cfg;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_tiles = (g.M + 2 * BM - 1) / (2 * BM), n_tiles = (g.N + BN2 - 1) / BN2;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (g.K + BK - 1) / BK;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full[i], 1);   // leader: its own arrive.expect_tx for the bytes of BOTH CTAs
+      mbar_init(&empty[i], 1);  // multicast tcgen05.commit arrives in both CTAs
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 16);  // 8 epilogue warps of each CTA arrive on the leader's copy
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
+        const int row_a = m_blk * 2 * BM + (int)rank * BM, row_b = n_blk * BN2 + (int)rank * (BN2 / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+          tma_load_2d_2cta(sA + stage * Cfg::kABytes, &map_a, &full[stage], kb * BK, row_a);
+          tma_load_2d_2cta(sB + stage * Cfg::kBBytes, &map_b, &full[stage], kb * BK, row_b);
+          if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {  // ===== MMA issuer (leader CTA, one thread)
+      constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN2, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * Cfg::kABytes));
+          const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_f16_2cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma_commit_2cta(&empty[stage]);
+          if (++stage == Cfg::kStages) stage = 0, phase ^= 1;
+        }
+        umma_commit_2cta(&tfull[acc]);
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {  // ===== epilogue: lane quarter q, column half `half`
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
+      const bool row_ok = row < g.M;
+#pragma unroll 1
+      for (int cc = half * (BN2 / 64); cc < (half + 1) * (BN2 / 64); ++cc) {
+        const int col0 = n_blk * BN2 + cc * 32;
+        if (col0 >= g.N) break;  // warp-uniform
+        epilogue_chunk<ACT, OUT_F32>(g, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2 + cc * 32), row, row_ok, col0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(&tempty[acc], 0));  // the leader's MMA thread waits for both CTAs
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's MMAs / epilogue reads of our shared memory and TMEM are complete
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int ACT, bool OUT_F32>
+static int launch_gemm_2cta(cb_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t stream) {
+  auto kern = gemm_tcgen05_2cta_kernel<ACT, OUT_F32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::kSmem));
+    attr_set = true;
+  }
+  const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * ((g.N + BN2 - 1) / BN2);
+  const int pairs = std::min(tiles, ctx->sm_count / 2);
+  mark_launch(ctx, CB_PROF_GEMM, stream);
+  kern<<<2 * pairs, kGemm2Threads, Gemm2Cfg::kSmem, stream>>>(ma, mb, g);
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
 }
 
 template <int BN, int ACT, bool OUT_F32>
@@ -241,6 +404,26 @@ int gemm_f16(cb_ctx* ctx, const void* A, const void* W, const float* bias, const
   const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
   const bool wide = (N % 256 == 0 || N > 1024) && tiles256 >= ctx->sm_count;
   const int BN = wide ? 256 : 128;
+  const char* force = getenv("CB_GEMM_KERNEL");  // "1cta" / "2cta": test and A/B switch
+  const int tiles2 = ((M + 255) / 256) * ((N + 255) / 256);
+  bool use2 = tiles2 >= ctx->sm_count / 2 && N >= 256;
+  if (force && force[0] == '1') use2 = false;
+  if (force && force[0] == '2') use2 = true;
+  if (use2) {
+    CUtensorMap ma2, mb2;
+    uint64_t da2[2] = {(uint64_t)K, (uint64_t)M}, db2[2] = {(uint64_t)K, (uint64_t)N}, st2[1] = {(uint64_t)K * 2};
+    uint32_t ba2[2] = {BK, BM}, bb2[2] = {BK, BN2 / 2};
+    int rc2 = make_tensor_map(ctx, &ma2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, A, da2, st2, ba2, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc2) return rc2;
+    rc2 = make_tensor_map(ctx, &mb2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, W, db2, st2, bb2, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc2) return rc2;
+    GemmArgs g2{bias, residual, out_f32, (__half*)out_f16, M, N, K};
+    if (out_f32) return launch_gemm_2cta<CB_EPI_NONE, true>(ctx, ma2, mb2, g2, stream);
+    if (epilogue == CB_EPI_QUICK_GELU) return launch_gemm_2cta<CB_EPI_QUICK_GELU, false>(ctx, ma2, mb2, g2, stream);
+    if (epilogue == CB_EPI_GELU_TANH) return launch_gemm_2cta<CB_EPI_GELU_TANH, false>(ctx, ma2, mb2, g2, stream);
+    if (epilogue == CB_EPI_NONE) return launch_gemm_2cta<CB_EPI_NONE, false>(ctx, ma2, mb2, g2, stream);
+    return fail(ctx, CB_ERR_ARG, "gemm: unknown epilogue %d", epilogue);
+  }
   CUtensorMap ma, mb;
   uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, db[2] = {(uint64_t)K, (uint64_t)N}, st[1] = {(uint64_t)K * 2};
   uint32_t ba[2] = {BK, BM}, bb[2] = {BK, (uint32_t)BN};

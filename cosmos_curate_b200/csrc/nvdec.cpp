@@ -186,6 +186,9 @@ struct cb_decoder {
   size_t dst_slot_stride = 0;
   int dst_pitch = 0, dst_luma_rows = 0, dst_w = 0, dst_h = 0;
   bool done = false;
+  // thumbnail mode (cb_decoder_decode_thumbnails): every displayed frame -> out_w x out_h RGB, no surface copy
+  uint8_t* thumb_out = nullptr;
+  int thumb_w = 0, thumb_h = 0, thumb_cap = 0;
   std::string error;
   std::vector<uint8_t> scratch;
 };
@@ -249,6 +252,33 @@ int on_display(void* user, CUVIDPARSERDISPINFO* info) {
   cb_decoder* d = (cb_decoder*)user;
   if (!info || d->done) return 1;
   const int idx = d->display_index++;
+  if (d->thumb_out) {
+    if (idx >= d->thumb_cap) {
+      d->done = true;
+      return 1;
+    }
+    CUVIDPROCPARAMS tp;
+    memset(&tp, 0, sizeof tp);
+    tp.progressive_frame = info->progressive_frame, tp.top_field_first = info->top_field_first, tp.output_stream = d->stream;
+    unsigned long long tsrc = 0;
+    unsigned tpitch = 0;
+    int trc = d->api->MapVideoFrame64(d->dec, info->picture_index, &tsrc, &tpitch, &tp);
+    if (trc != 0) {
+      d->error = "cuvidMapVideoFrame64 failed with CUresult " + std::to_string(trc);
+      return 0;
+    }
+    const int th = (d->disp_h + 1) & ~1;
+    trc = cb::bilinear_from_surface(d->ctx, (const void*)tsrc, (int)tpitch, th, d->disp_w, d->disp_h, d->thumb_w, d->thumb_h,
+                                    d->thumb_out + (size_t)idx * d->thumb_w * d->thumb_h * 3, d->stream);
+    cudaError_t te = cudaStreamSynchronize(d->stream);
+    d->api->UnmapVideoFrame64(d->dec, tsrc);
+    if (trc != 0 || te != cudaSuccess) {
+      d->error = "thumbnail kernel failed";
+      return 0;
+    }
+    d->emitted++;
+    return 1;
+  }
   if (d->next_id >= d->n_ids || idx != d->ids[d->next_id]) return 1;
   if (((d->disp_w + 1) & ~1) != d->dst_w || ((d->disp_h + 1) & ~1) != d->dst_h) {
     d->error = "clip is " + std::to_string(d->disp_w) + "x" + std::to_string(d->disp_h) + " but the surface pool is " + std::to_string(d->dst_w) +
@@ -368,6 +398,28 @@ void cb_decoder_destroy(cb_decoder* d) {
   delete d;
 }
 
+static int run_parser(cb_decoder* d, const uint8_t* data, size_t size, const cb::Mp4Track& t, cb_decode_stats* stats, int expect);
+
+int cb_decoder_decode_thumbnails(cb_decoder* d, const uint8_t* data, size_t size, int out_w, int out_h, uint8_t* out, int max_frames,
+                                 cb_decode_stats* stats) {
+  if (!d) return CB_ERR_ARG;
+  cb_ctx* ctx = d->ctx;
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (!data || !out || out_w <= 0 || out_h <= 0 || max_frames < 0) return cb::fail(ctx, CB_ERR_ARG, "decode_thumbnails: bad argument");
+  cb::Mp4Track t;
+  const std::string err = cb::mp4_parse(data, size, &t);
+  if (!err.empty()) return cb::fail(ctx, CB_ERR_DEMUX, "mp4: %s", err.c_str());
+  cudaSetDevice(ctx->device);
+  d->ids = nullptr, d->slots = nullptr, d->n_ids = 0, d->next_id = 0, d->display_index = 0, d->decoded = 0, d->emitted = 0;
+  d->done = (max_frames == 0);
+  d->error.clear();
+  d->thumb_out = out, d->thumb_w = out_w, d->thumb_h = out_h, d->thumb_cap = max_frames;
+  const int want = std::min<int>(max_frames, (int)t.size.size());
+  const int rc = run_parser(d, data, size, t, stats, want);
+  d->thumb_out = nullptr;
+  return rc;
+}
+
 int cb_decoder_decode(cb_decoder* d, const uint8_t* data, size_t size, const int32_t* frame_ids, int n_ids, const cb_surface_pool* dst,
                       const int32_t* dst_slots, cb_decode_stats* stats) {
   if (!d) return CB_ERR_ARG;
@@ -393,6 +445,11 @@ int cb_decoder_decode(cb_decoder* d, const uint8_t* data, size_t size, const int
     d->dst_w = dst->width, d->dst_h = dst->height;
   }
 
+  return run_parser(d, data, size, t, stats, n_ids);
+}
+
+static int run_parser(cb_decoder* d, const uint8_t* data, size_t size, const cb::Mp4Track& t, cb_decode_stats* stats, int expect) {
+  cb_ctx* ctx = d->ctx;
   CUVIDPARSERPARAMS pp;
   memset(&pp, 0, sizeof pp);
   pp.CodecType = t.codec;
@@ -435,7 +492,7 @@ int cb_decoder_decode(cb_decoder* d, const uint8_t* data, size_t size, const int
     stats->coded_width = (int)d->coded_w, stats->coded_height = (int)d->coded_h, stats->width = d->disp_w, stats->height = d->disp_h;
   }
   if (failed) return cb::fail(ctx, CB_ERR_NVDEC, "decode: %s", d->error.empty() ? ("cuvidParseVideoData CUresult " + std::to_string(rc)).c_str() : d->error.c_str());
-  if (d->emitted != n_ids) return cb::fail(ctx, CB_ERR_NVDEC, "decode: stream ended after %d displayed frames, %d of %d sampled frames delivered", d->display_index, d->emitted, n_ids);
+  if (d->emitted != expect) return cb::fail(ctx, CB_ERR_NVDEC, "decode: stream ended after %d displayed frames, %d of %d sampled frames delivered", d->display_index, d->emitted, expect);
   return CB_OK;
 }
 

@@ -249,7 +249,7 @@ __global__ void bilinear_u8_kernel(const SimpleArgs a) {
   const int per = a.out_w * a.out_h;
   if (i >= a.n * per) return;
   const int f = i / per, p = i - f * per, yo = p / a.out_w, xo = p - yo * a.out_w;
-  const uint8_t* fr = a.base + (size_t)a.slots[f] * a.slot_stride;
+  const uint8_t* fr = a.base + (size_t)(a.slots ? a.slots[f] : f) * a.slot_stride;
   const float sx = (float)a.w / (float)a.out_w, sy = (float)a.h / (float)a.out_h;
   const float fx = (xo + 0.5f) * sx - 0.5f, fy = (yo + 0.5f) * sy - 0.5f;
   const int x0 = (int)floorf(fx), y0 = (int)floorf(fy);
@@ -372,20 +372,17 @@ int ensure_norm_lut(cb_ctx* ctx, const float mean[3], const float std_[3], cudaS
 
 static int python_round_half_even(double v) { return (int)std::nearbyint(v); }  // default FE_TONEAREST
 
-struct SlotBuf {  // small device staging of the slot list (grows as needed)
-  int* d = nullptr;
-  int cap = 0;
-};
-static SlotBuf g_slots;
-
 static int upload_slots(cb_ctx* ctx, const int32_t* slots, int n, cudaStream_t stream, const int** out) {
-  if (g_slots.cap < n) {
-    if (g_slots.d) cudaFree(g_slots.d);
-    g_slots.cap = std::max(1024, n);
-    CB_CUDA(ctx, cudaMalloc(&g_slots.d, g_slots.cap * sizeof(int)));
+  if (ctx->slots_cap < n) {
+    if (ctx->d_slots) {
+      CB_CUDA(ctx, cudaStreamSynchronize(stream));  // a previous launch may still read the old list
+      cudaFree(ctx->d_slots);
+    }
+    ctx->slots_cap = std::max(1024, n);
+    CB_CUDA(ctx, cudaMalloc(&ctx->d_slots, ctx->slots_cap * sizeof(int)));
   }
-  CB_CUDA(ctx, cudaMemcpyAsync(g_slots.d, slots, n * sizeof(int), cudaMemcpyHostToDevice, stream));
-  *out = g_slots.d;
+  CB_CUDA(ctx, cudaMemcpyAsync(ctx->d_slots, slots, n * sizeof(int), cudaMemcpyHostToDevice, stream));
+  *out = ctx->d_slots;
   return CB_OK;
 }
 
@@ -521,6 +518,17 @@ static int run_simple(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* s
     const long long total = (long long)n * a.h * ((a.w + 1) / 2);
     nv12_to_rgb_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
   }
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
+}
+
+int bilinear_from_surface(cb_ctx* ctx, const void* base, int pitch, int luma_rows, int w, int h, int out_w, int out_h, uint8_t* out,
+                          cudaStream_t stream) {
+  SimpleArgs a{};
+  a.base = (const uint8_t*)base, a.slot_stride = 0, a.slots = nullptr;
+  a.n = 1, a.w = w, a.h = h, a.pitch = pitch, a.luma_rows = luma_rows, a.out_w = out_w, a.out_h = out_h, a.out = out;
+  mark_launch(ctx, CB_PROF_PREPROCESS, stream);
+  bilinear_u8_kernel<<<(out_w * out_h + 255) / 256, 256, 0, stream>>>(a);
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }

@@ -330,7 +330,27 @@ __global__ void __launch_bounds__(256) clip_tail_kernel(const float* __restrict_
   }
 }
 
+// score[i] = w . emb[i] + b : the reference's aesthetic MLP (aesthetics.py:44-53) folded to its affine map
+__global__ void __launch_bounds__(256) affine_score_kernel(const float* __restrict__ emb, const float* __restrict__ w, float b,
+                                                           float* __restrict__ out, int n, int d) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float acc = 0.f;
+  for (int i = lane; i < d; i += 32) acc += emb[(size_t)row * d + i] * __ldg(w + i);
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc + b;
+}
+
 // ------------------------------------------------------------------------------------------ host
+int affine_score(cb_ctx* ctx, const float* emb, const float* w, float b, float* out, int n, int d, cudaStream_t stream) {
+  if (!emb || !w || !out) return fail(ctx, CB_ERR_ARG, "affine_score: null operand");
+  if (n <= 0) return CB_OK;
+  mark_launch(ctx, CB_PROF_OTHER, stream);
+  affine_score_kernel<<<(n + 7) / 8, 256, 0, stream>>>(emb, w, b, out, n, d);
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
+}
+
 int layernorm_f16(cb_ctx* ctx, const float* x, const float* gamma, const float* beta, void* y, int rows, int d, float eps, cudaStream_t stream) {
   if (!x || !gamma || !beta || !y) return fail(ctx, CB_ERR_ARG, "layernorm: null operand");
   if (rows <= 0) return CB_OK;
@@ -386,6 +406,10 @@ int clip_tail(cb_ctx* ctx, const float* h, size_t img_stride, const float* gamma
 }  // namespace cb
 
 extern "C" {
+int cb_affine_score(cb_ctx* ctx, const float* emb, const float* w, float b, float* out, int n, int d, void* stream) {
+  if (!ctx) return CB_ERR_ARG;
+  return cb::affine_score(ctx, emb, w, b, out, n, d, (cudaStream_t)stream);
+}
 int cb_layernorm_f16(cb_ctx* ctx, const float* x, const float* gamma, const float* beta, void* y, int rows, int d, float eps, void* stream) {
   if (!ctx) return CB_ERR_ARG;
   return cb::layernorm_f16(ctx, x, gamma, beta, y, rows, d, eps, (cudaStream_t)stream);

@@ -174,6 +174,25 @@ class Context:
         return out
 
 
+_CONTEXTS: dict[int, Context] = {}
+
+
+def get_context(device: int | None = None) -> Context:
+    """Process-wide context per device (stages and models of one actor process share it)."""
+    dev = torch.cuda.current_device() if (device is None and torch.cuda.is_available()) else int(device or 0)
+    c = _CONTEXTS.get(dev)
+    if c is None or c.h is None:
+        c = _CONTEXTS[dev] = Context(dev)
+    return c
+
+
+def affine_score(ctx: Context, emb: torch.Tensor, w: torch.Tensor, b: float) -> torch.Tensor:
+    n, d = emb.shape
+    out = torch.empty((n,), dtype=torch.float32, device=emb.device)
+    check(ctx.lib.cb_affine_score(ctx.h, emb.data_ptr(), w.data_ptr(), float(b), out.data_ptr(), n, d, _stream_ptr()), "cb_affine_score", ctx.h)
+    return out
+
+
 class Pool:
     def __init__(self, buf: torch.Tensor, desc: SurfacePool):
         self.buf, self.desc = buf, desc  # keep the tensor alive while the descriptor is in use
@@ -296,6 +315,16 @@ class Decoder:
               "cb_decoder_decode", self.ctx.h)  # fmt: skip
         return {"frames_decoded": st.frames_decoded, "frames_emitted": st.frames_emitted, "coded": (st.coded_width, st.coded_height),
                 "size": (st.width, st.height)}  # fmt: skip
+
+
+def decode_thumbnails(dec: Decoder, data, out_w: int, out_h: int, n_frames: int) -> torch.Tensor:
+    """Every frame of the clip as uint8 cuda [n, out_h, out_w, 3] (cb_decoder_decode_thumbnails)."""
+    buf = _as_u8(data)
+    out = torch.empty((n_frames, out_h, out_w, 3), dtype=torch.uint8, device=f"cuda:{dec.ctx.device}")
+    st = _lib.DecodeStats()
+    check(dec.lib.cb_decoder_decode_thumbnails(dec.h, buf.ctypes.data, buf.size, out_w, out_h, out.data_ptr(), n_frames, C.byref(st)),
+          "cb_decoder_decode_thumbnails", dec.ctx.h)  # fmt: skip
+    return out[: st.frames_emitted]
 
 
 def alloc_nv12_pool(ctx: Context, slots: int, width: int, height: int) -> Pool:

@@ -1,0 +1,15 @@
+"""CuratorStage implementations of the path.
+
+Same-name drop-ins (constructor arguments, task mutations and error convention of the reference):
+    AestheticFilterStage        cosmos_curate/pipelines/video/filtering/aesthetics/aesthetic_filter_stages.py:41-221
+    ClipFrameExtractionStage    cosmos_curate/pipelines/video/clipping/clip_frame_extraction_stages.py:43-192
+    VideoFrameExtractionStage   cosmos_curate/pipelines/video/clipping/frame_extraction_stages.py:71-204
+    ImageCLIPEmbeddingStage     cosmos_curate/pipelines/image/embedding/image_embedding_stages.py:219-283
+New fused stage (replaces ClipFrameExtractionStage -> AestheticFilterStage [-> clip embedding] in one GPU pass):
+    NvdecClipAestheticStage
+"""
+
+from .aesthetic_filter import AestheticFilterStage  # noqa: F401
+from .fused_clip import NvdecClipAestheticStage  # noqa: F401
+from .frame_extraction import ClipFrameExtractionStage, VideoFrameExtractionStage  # noqa: F401
+from .image_embedding import ImageCLIPEmbeddingStage  # noqa: F401

@@ -141,6 +141,10 @@ int cb_vit_forward(cb_vit* vit, const void* patches, int n, float* emb_out, floa
 int cb_vit_embed_surfaces(cb_vit* vit, const cb_surface_pool* pool, const int32_t* slots, int n, const float mean[3],
                           const float std_[3], float* emb_out, float* feat_out, float* score_out, void* stream);
 
+/* score[i] = w . emb[i] + b over device fp32 embeddings [n][d] (w: device fp32 [d]).  The reference's
+ * AestheticScorer.__call__ (aesthetics.py:94-106) on already-computed embeddings. */
+int cb_affine_score(cb_ctx* ctx, const float* emb, const float* w, float b, float* out, int n, int d, void* stream);
+
 /* ---- demux + NVDEC ---------------------------------------------------------------------------- */
 typedef struct cb_decoder cb_decoder;
 
@@ -174,6 +178,13 @@ void cb_decoder_destroy(cb_decoder* dec);
  * (nvcodec_utils.py:247-295).  Returns only after the copies have completed. */
 int cb_decoder_decode(cb_decoder* dec, const uint8_t* data, size_t size, const int32_t* frame_ids, int n_ids,
                       const cb_surface_pool* dst, const int32_t* dst_slots, cb_decode_stats* stats);
+
+/* Decode EVERY frame of the clip (up to max_frames) and write each as an out_w x out_h RGB u8 thumbnail into device
+ * memory out[n][out_h][out_w][3]: NV12->RGB + bilinear run directly on the mapped NVDEC surface.  Replaces
+ * PyNvcFrameExtractor.__call__ (nvcodec_utils.py:349-381: decode, per-frame reformat, full-resolution colour
+ * convert, resize, concat) as used by VideoFrameExtractionStage for the 27x48 shot-detection frames. */
+int cb_decoder_decode_thumbnails(cb_decoder* dec, const uint8_t* data, size_t size, int out_w, int out_h, uint8_t* out,
+                                 int max_frames, cb_decode_stats* stats);
 
 /* ---- building blocks exported for the parity tests ------------------------------------------------ */
 #define CB_EPI_NONE 0       /* C = A W^T (+ bias) */

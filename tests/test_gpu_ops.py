@@ -78,3 +78,25 @@ def test_attention(ctx, n, t, heads, hd):
     torch.testing.assert_close(got, want, rtol=1e-2, atol=4e-3)  # P and O rounded to fp16
 
 
+
+
+@pytest.mark.parametrize("kernel", ["1cta", "2cta"])
+@pytest.mark.parametrize(("m", "n", "k"), [(300, 256, 192), (257, 136, 72), (1000, 1024, 1024), (5000, 768, 640), (4096, 4304, 1152)])
+def test_gemm_both_kernels_with_tails(ctx, monkeypatch, kernel, m, n, k):
+    """Force the 1-CTA and the 2-CTA (cta_group::2) kernels through M/N/K tails and the activation epilogue."""
+    from cosmos_curate_b200 import _lib
+
+    monkeypatch.setenv("CB_GEMM_KERNEL", kernel)
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n)
+    a = (torch.randn(m, k, device="cuda", generator=g) * 0.5).half()
+    w = (torch.randn(n, k, device="cuda", generator=g) * 0.5).half()
+    bias = torch.randn(n, device="cuda", generator=g)
+    z = a.float() @ w.float().T + bias
+    got = ctx.gemm(a, w, bias=bias).float()
+    assert (got - z).abs().max().item() <= 2e-3 * z.abs().max().item() + 1e-2
+    got = ctx.gemm(a, w, bias=bias, epilogue=_lib.EPI_QUICK_GELU).float()
+    want = z * torch.sigmoid(1.702 * z)
+    assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-2
+    res = torch.randn(m, n, device="cuda", generator=g)
+    got = ctx.gemm(a, w, bias=bias, residual=res.clone(), out_f32=True)
+    torch.testing.assert_close(got, res + z, rtol=1e-4, atol=2e-3)

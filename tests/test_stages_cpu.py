@@ -1,0 +1,259 @@
+"""CPU tests of the host-side stage logic with fake models (the pattern of the reference's own stage tests, e.g.
+tests/cosmos_curate/pipelines/image/embedding/test_image_embedding_stages.py:55-60,126-144) and of the N>1 host
+logic on gloo (world_size 2)."""
+
+from __future__ import annotations
+
+import os
+import types
+import uuid
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cosmos_curate_b200 import sharding
+from cosmos_curate_b200.data_model import Clip, LazyData, SplitPipeTask, Video
+from cosmos_curate_b200.interfaces import CuratorStage, CuratorStageSpec, ModelInterface, SequentialRunner, run_pipeline
+from cosmos_curate_b200.stages.aesthetic_filter import AestheticFilterStage, score_frame_groups
+from cosmos_curate_b200.stages.image_embedding import ImageCLIPEmbeddingStage
+
+SIG1 = "FrameExtractionPolicy.sequence-1000"
+SIG2 = "FrameExtractionPolicy.sequence-2000"
+
+
+class _FakeScorer(ModelInterface):
+    """score(frame) = mean pixel value / 25.5 (0..10); records batch sizes."""
+
+    def __init__(self):
+        self.calls = []
+        self.was_setup = False
+
+    @property
+    def conda_env_name(self):
+        return "unified"
+
+    @property
+    def model_id_names(self):
+        return ["fake"]
+
+    def setup(self):
+        self.was_setup = True
+
+    def __call__(self, frames):
+        self.calls.append(frames.shape)
+        return torch.from_numpy(frames.reshape(len(frames), -1).mean(axis=1) / 25.5)
+
+
+def _clip(level_per_frame, shape=(8, 12), with_data=True, sigs=(SIG1,)):
+    frames = np.stack([np.full((*shape, 3), v, dtype=np.uint8) for v in level_per_frame])
+    c = Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0.0, 1.0), encoded_data=b"x" * 10 if with_data else None)
+    c.extracted_frames = LazyData(value={s: frames.copy() for s in sigs}, nbytes=frames.nbytes * len(sigs))
+    return c
+
+
+def _task(clips):
+    return SplitPipeTask(session_id="s", video=Video(input_video="v.mp4", clips=list(clips)))
+
+
+def test_aesthetic_filter_contract_and_error_convention():
+    model = _FakeScorer()
+    stage = AestheticFilterStage(score_threshold=3.0, reduction="min", log_stats=True, model=model)
+    good = _clip([255, 128, 200])  # min score = 128/25.5 = 5.02
+    low = _clip([255, 25])  # min = 0.98 -> filtered
+    no_data = _clip([100], with_data=False)
+    missing = _clip([100], sigs=(SIG2,))
+    task = _task([good, low, no_data, missing])
+    out = run_pipeline([task], [stage], runner=SequentialRunner())
+    assert out is not None and out[0] is task and model.was_setup
+    v = task.video
+    assert v.clips == [good] and v.filtered_clips == [low, no_data, missing]
+    assert v.clip_stats.num_filtered_by_aesthetic == 3
+    assert good.aesthetic_score == pytest.approx(128 / 25.5) and low.aesthetic_score == pytest.approx(25 / 25.5)
+    assert no_data.errors == {"encoded_data": "empty"} and no_data.aesthetic_score == -1.0
+    assert missing.errors == {f"frames-{SIG1}": "missing"} and missing.aesthetic_score == -1.0
+    assert not good.extracted_frames  # last consumer dropped the LazyData
+    assert SIG2 in missing.extracted_frames.resolve()  # untouched key of another consumer
+    assert "AestheticFilterStage" in task.stage_perf
+    assert len(model.calls) == 1 and model.calls[0][0] == 5  # ONE batched model call for both clips
+
+
+def test_aesthetic_filter_pop_keeps_other_signatures_and_mean():
+    model = _FakeScorer()
+    stage = AestheticFilterStage(score_threshold=0.0, reduction="mean", model=model)
+    c = _clip([51, 102], sigs=(SIG1, SIG2))
+    task = _task([c])
+    stage.stage_setup()
+    stage.process_data([task])
+    assert c.aesthetic_score == pytest.approx((2 + 4) / 2)
+    ef = c.extracted_frames.resolve()
+    assert ef is not None and list(ef) == [SIG2]  # popped own key only; dict not dropped
+    with pytest.raises(NotImplementedError):
+        AestheticFilterStage(0.0, reduction="max", model=_FakeScorer()).stage_setup()  # type: ignore[arg-type]
+
+
+def test_batching_is_invisible_in_results():
+    rng = np.random.default_rng(0)
+    groups = [rng.integers(0, 256, size=(n, 6, 8, 3), dtype=np.uint8) for n in (3, 11, 7, 1)]
+    groups.append(rng.integers(0, 256, size=(4, 5, 5, 3), dtype=np.uint8))  # another resolution: its own batch
+    m = _FakeScorer()
+    per = score_frame_groups(m, groups, max_batch=12)
+    for g, s in zip(groups, per):
+        np.testing.assert_allclose(s, g.reshape(len(g), -1).mean(axis=1) / 25.5)
+    assert sorted(c[0] for c in m.calls) == [3, 4, 8, 11]  # greedy fill <= 12 frames per call, per frame size
+
+
+def test_threshold_behaviour_like_reference_test():
+    for thr, filtered in ((9.0, True), (1.0, False)):  # test_aesthetic_filter.py:133-181
+        task = _task([_clip([128] * 11)])
+        run_pipeline([task], [AestheticFilterStage(score_threshold=thr, reduction="mean", model=_FakeScorer())])
+        assert (len(task.video.filtered_clips), len(task.video.clips)) == ((1, 0) if filtered else (0, 1))
+
+
+def test_sequential_runner_order_and_none():
+    log = []
+
+    class S(CuratorStage):
+        def __init__(self, name, ret=True):
+            self.n, self.ret = name, ret
+
+        def stage_setup(self):
+            log.append(("setup", self.n))
+
+        def process_data(self, t):
+            log.append(("run", self.n))
+            return t if self.ret else None
+
+        def destroy(self):
+            log.append(("destroy", self.n))
+
+    assert run_pipeline([1], [S("a"), CuratorStageSpec(S("b"))]) == [1]
+    assert log == [("setup", "a"), ("setup", "b"), ("run", "a"), ("destroy", "a"), ("run", "b"), ("destroy", "b")]
+    assert run_pipeline([1], [S("c", ret=False), S("d")]) is None
+    assert S("x").stage_batch_size == 1 and S("x").resources.gpus == 0.0 and S("x").conda_env_name is None
+
+
+def test_image_clip_embedding_stage_contract():
+    class _FakeCLIPModel(ModelInterface):
+        conda_env_name = "unified"
+        model_id_names = ["fake"]
+
+        def setup(self):
+            pass
+
+        def __call__(self, batch):
+            return torch.from_numpy(batch.reshape(len(batch), -1)[:, :4].astype(np.float32))
+
+    def task(frame):
+        img = types.SimpleNamespace(image_data=None if frame is None else types.SimpleNamespace(frames=[frame]), embeddings={}, errors={})
+        return types.SimpleNamespace(image=img, stage_perf={}, get_major_size=lambda: 0)
+
+    a, b, c = task(np.full((4, 4, 3), 7, np.uint8)), task(None), task(np.full((4, 4, 3), 9, np.uint8))
+    stage = ImageCLIPEmbeddingStage(model=_FakeCLIPModel(), log_stats=True)
+    stage.stage_setup()
+    out = stage.process_data([a, b, c])
+    assert out == [a, b, c]
+    assert a.image.embeddings["clip"].tolist() == [7, 7, 7, 7] and c.image.embeddings["clip"].tolist() == [9, 9, 9, 9]
+    assert b.image.errors == {"clip_embedding": "no image_data"} and "clip" not in b.image.embeddings
+    assert "ImageCLIPEmbeddingStage" in a.stage_perf
+
+
+def test_models_fail_loudly_without_weights(monkeypatch):
+    from cosmos_curate_b200.models.aesthetics import AestheticScorer
+    from cosmos_curate_b200.models.clip import CLIPImageEmbeddings
+
+    monkeypatch.delenv("CURATE_B200_SYNTHETIC_WEIGHTS", raising=False)
+    monkeypatch.delenv("CURATE_B200_WEIGHTS_DIR", raising=False)
+    assert CLIPImageEmbeddings().model_id_names == ["openai/clip-vit-large-patch14"]
+    assert AestheticScorer().model_id_names == ["ttj/sac-logos-ava1-l14-linearMSE"]
+    with pytest.raises(FileNotFoundError):
+        AestheticScorer().load()
+
+
+def test_aesthetic_fold_matches_reference_mlp():
+    from conftest import load_golden
+    from cosmos_curate_b200.models import weights as W
+
+    g = load_golden("aesthetic_ref.npz")
+    w, b = W.fold_aesthetic_mlp({k[3:]: g[k] for k in g.files if k.startswith("sd_")})
+    np.testing.assert_allclose(g["emb"] @ w + b, g["score"], rtol=1e-4, atol=2e-5)  # reference MLP outputs
+
+
+def test_hf_checkpoint_loader_roundtrip(tmp_path):
+    """load_hf_clip_dir reads what CLIPModel.save_pretrained writes (the reference loads with from_pretrained, clip.py:41)."""
+    from conftest import golden_json, load_golden
+    from cosmos_curate_b200.models import weights as W
+
+    transformers = pytest.importorskip("transformers")
+    torch.manual_seed(0)
+    cfg = transformers.CLIPConfig(
+        text_config={"hidden_size": 32, "intermediate_size": 64, "num_hidden_layers": 1, "num_attention_heads": 2, "vocab_size": 64,
+                     "max_position_embeddings": 8, "projection_dim": 64},
+        vision_config={"hidden_size": 128, "intermediate_size": 256, "num_hidden_layers": 2, "num_attention_heads": 2, "image_size": 224,
+                       "patch_size": 32, "projection_dim": 64},
+        projection_dim=64,
+    )  # fmt: skip
+    model = transformers.CLIPModel(cfg).eval()
+    model.save_pretrained(tmp_path)
+    c, w = W.load_hf_clip_dir(tmp_path)
+    assert (c.hidden, c.layers, c.heads, c.mlp, c.patch, c.proj_dim, c.act) == (128, 2, 2, 256, 32, 64, "quick_gelu")
+    sd = model.state_dict()
+    np.testing.assert_array_equal(w["L1.qkv_w"][128:256], sd["vision_model.encoder.layers.1.self_attn.k_proj.weight"].numpy())
+    np.testing.assert_array_equal(w["patch_w"], sd["vision_model.embeddings.patch_embedding.weight"].numpy().reshape(128, -1))
+    assert w["proj_w"].shape == (64, 128) and w["pos"].shape == (50, 128)
+
+
+# ---- multi-GPU host logic -------------------------------------------------------------------------
+def test_shard_by_weight_is_balanced_and_complete():
+    rng = np.random.default_rng(1)
+    w = np.concatenate([np.full(40, 1.0), np.full(40, 2.25), np.full(20, 9.0)])  # 720p / 1080p / 4K mix
+    rng.shuffle(w)
+    parts = sharding.shard_by_weight(w, 8)
+    assert sorted(i for p in parts for i in p) == list(range(100))
+    loads = [w[p].sum() for p in parts]
+    assert max(loads) - min(loads) <= 9.0  # within one heaviest item
+    assert sharding.shard_by_weight(w, 8) == parts  # deterministic
+    assert sharding.shard_by_weight([], 2) == [[], []]
+    assert sharding.rank_slice(10, 1, 4).tolist() == [1, 5, 9]
+    with pytest.raises(ValueError):
+        sharding.shard_by_weight([1.0], 0)
+
+
+def _gloo_worker(rank: int, world: int, port: int, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        clips = list(range(11))
+        mine = sharding.shard_by_weight([1.0 + (i % 3) for i in clips], world)[rank]
+        local = torch.tensor([[float(i), float(i) * 2, rank] for i in mine], dtype=torch.float32).reshape(len(mine), 3)
+        ids = torch.tensor(mine, dtype=torch.int64)
+        emb, gid = sharding.all_gather_embeddings(local, ids)
+        q.put((rank, emb.numpy(), gid.numpy()))
+        e2, _ = sharding.all_gather_embeddings(torch.zeros((0, 3)) if rank == 0 else torch.ones((2, 3)))  # ragged incl. an empty rank
+        q.put((rank, e2.numpy(), None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_all_gather_embeddings_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(4)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = [g for g in got if g[2] is not None]
+    assert len(full) == 2
+    np.testing.assert_array_equal(full[0][1], full[1][1])  # identical on both ranks
+    ids = full[0][2]
+    assert sorted(ids.tolist()) == list(range(11))
+    np.testing.assert_array_equal(full[0][1][:, 0], ids.astype(np.float32))  # rows stay attached to their clip ids
+    ragged = [g for g in got if g[2] is None]
+    for _, e, _ in ragged:
+        assert e.shape == (2, 3) and (e == 1).all()

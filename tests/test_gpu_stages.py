@@ -1,0 +1,178 @@
+"""GPU: the CuratorStage / ModelInterface drop-ins end to end (SequentialRunner, like the reference's stage tests),
+scores and embeddings checked against the oracle."""
+
+from __future__ import annotations
+
+import os
+import uuid
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from gpu_helpers import ctx  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+os.environ.setdefault("OPENCV_LOG_LEVEL", "ERROR")
+
+SIG1 = "FrameExtractionPolicy.sequence-1000"
+
+
+def _oracle_scores(cfg, w, sd, rgb_frames):
+    from oracle import preprocess, vit
+
+    ref = vit.forward(cfg, w, preprocess.clip_preprocess(rgb_frames))
+    return ref["embedding"], vit.aesthetic_mlp_forward(sd, ref["embedding"])
+
+
+def _model(cfg_name="CLIP_TINY", seed=7):
+    """CLIPAestheticScorer with oracle-seeded weights so the oracle can reproduce the numbers."""
+    from cosmos_curate_b200.models.clip_aesthetics import CLIPAestheticScorer
+    from cosmos_curate_b200.runtime import VitTower, get_context
+    from oracle import vit
+
+    cfg = getattr(vit, cfg_name)
+    w = vit.random_weights(cfg, seed=seed)
+    sd = vit.random_aesthetic_mlp(seed=seed, in_dim=cfg.proj_dim)
+    aw, ab = vit.collapse_aesthetic_mlp(sd)
+
+    class _Seeded(CLIPAestheticScorer):
+        def setup(self_inner):
+            from cosmos_curate_b200.models.clip import CLIPImageEmbeddings
+
+            m = CLIPImageEmbeddings()
+            m._tower = VitTower(get_context(), cfg.to_dict(), w, max_batch=64, aesthetic=(aw, ab))
+            self_inner._clip_model = m
+
+    return _Seeded(), cfg, w, sd
+
+
+def _clip_task(data: bytes, n_clips=1):
+    from cosmos_curate_b200.data_model import Clip, SplitPipeTask, Video
+
+    clips = [Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0.0, 10.0), encoded_data=data) for _ in range(n_clips)]
+    return SplitPipeTask(session_id="s", video=Video(input_video="v.mp4", clips=clips))
+
+
+def test_extraction_then_aesthetic_filter_matches_oracle(ctx):
+    """ClipFrameExtractionStage (NVDEC) -> AestheticFilterStage, the reference's stage pair, on the reference fixture."""
+    from cosmos_curate_b200.interfaces import run_pipeline
+    from cosmos_curate_b200.stages import AestheticFilterStage, ClipFrameExtractionStage
+
+    data = (GOLDEN / "sintel_clip_10s.mp4").read_bytes()
+    model, cfg, w, sd = _model()
+    task = _clip_task(data)
+    extract = ClipFrameExtractionStage(target_fps=[1, 2], log_stats=True)
+    extract.stage_setup()
+    extract.process_data([task])
+    clip = task.video.clips[0]
+    ef = clip.extracted_frames.resolve()
+    assert set(ef) == {SIG1, "FrameExtractionPolicy.sequence-2000"}
+    assert ef[SIG1].shape == (11, 480, 854, 3) and ef["FrameExtractionPolicy.sequence-2000"].shape == (21, 480, 854, 3)
+    np.testing.assert_array_equal(ef[SIG1], ef["FrameExtractionPolicy.sequence-2000"][::2])  # LCM + stride rule
+    frames = ef[SIG1].copy()
+    stage = AestheticFilterStage(score_threshold=0.0, reduction="mean", log_stats=True, model=model)
+    out = run_pipeline([task], [stage])
+    assert out is not None and "AestheticFilterStage" in task.stage_perf and "ClipFrameExtractionStage" in task.stage_perf
+    _, want = _oracle_scores(cfg, w, sd, frames)
+    assert clip.aesthetic_score == pytest.approx(float(want.mean()), abs=2e-3)  # reference test tolerance (TOLERANCE = 0.002)
+    assert SIG1 not in clip.extracted_frames.resolve()  # popped; the 2 fps key stays for the embedding consumer
+    stage2 = AestheticFilterStage(score_threshold=float(want.min()) + 0.5, reduction="min", model=model)
+    stage2._model = model
+    t2 = _clip_task(data)
+    t2.video.clips[0].extracted_frames = type(clip.extracted_frames)(value={SIG1: frames}, nbytes=frames.nbytes)
+    stage2.stage_setup()
+    stage2.process_data([t2])
+    assert len(t2.video.filtered_clips) == 1 and t2.video.clip_stats.num_filtered_by_aesthetic == 1
+
+
+def test_fused_nvdec_stage_matches_oracle_and_error_convention(ctx):
+    from cosmos_curate_b200.interfaces import run_pipeline
+    from cosmos_curate_b200.runtime import Decoder, alloc_nv12_pool
+    from cosmos_curate_b200.stages import NvdecClipAestheticStage
+    from oracle import color
+    from tools import synth_h264
+
+    sintel = (GOLDEN / "sintel_clip_10s.mp4").read_bytes()
+    synth = synth_h264.make_clip(640, 360, 30, 3.0, seed=5, gop=30, pan=(2, 1))
+    model, cfg, w, sd = _model()
+    task = _clip_task(sintel, n_clips=2)
+    from cosmos_curate_b200.data_model import Clip
+
+    task.video.clips.append(Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0, 3), encoded_data=synth))
+    task.video.clips.append(Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0, 1), encoded_data=b"\x00" * 4096))  # garbage
+    task.video.clips.append(Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0, 1)))  # no data
+    stage = NvdecClipAestheticStage(score_threshold=-0.5, reduction="min", write_embedding=True, max_batch=16, num_decoders=3, log_stats=True, model=model)
+    out = run_pipeline([task], [stage])
+    assert out is not None
+    v = task.video
+    assert len(v.clips) == 3 and len(v.filtered_clips) == 2 and v.clip_stats.num_filtered_by_aesthetic == 2
+    bad, empty = v.filtered_clips
+    assert bad.errors["frame_extraction"] == "video_decode_failed" and bad.aesthetic_score == -1.0 and not bad.encoded_data
+    assert empty.errors == {"encoded_data": "empty"} and empty.aesthetic_score == -1.0
+    assert "NvdecClipAestheticStage" in task.stage_perf
+    # oracle: decode the same frames with the (already validated) NVDEC wrapper, then the CPU oracle chain
+    dec = Decoder(ctx)
+    for clip, data, (wd, h), ids in ((v.clips[0], sintel, (854, 480), [0, 24, 48, 72, 96, 120, 144, 168, 192, 216, 239]), (v.clips[2], synth, (640, 360), [0, 30, 60, 89])):
+        pool = alloc_nv12_pool(ctx, len(ids), wd, h)
+        dec.decode(data, ids, pool, np.arange(len(ids)))
+        nv12 = pool.buf.cpu().numpy()
+        rgb = np.stack([color.nv12_to_rgb(np.ascontiguousarray(f[:, :wd]), h, wd) for f in nv12])
+        emb, scores = _oracle_scores(cfg, w, sd, rgb)
+        assert clip.aesthetic_score == pytest.approx(float(scores.min()), abs=3e-3)
+        m = emb.mean(axis=0)
+        m /= np.linalg.norm(m)
+        assert np.linalg.norm(clip.openai_embedding - m) / np.linalg.norm(m) < 2e-3
+    assert v.clips[0].aesthetic_score == v.clips[1].aesthetic_score  # identical clips, batch-invariant results
+
+
+def test_video_frame_extraction_thumbnails(ctx):
+    from cosmos_curate_b200.data_model import SplitPipeTask, Video
+    from cosmos_curate_b200.runtime import Decoder, alloc_nv12_pool
+    from cosmos_curate_b200.stages import VideoFrameExtractionStage
+    from oracle import color, preprocess
+
+    data = (GOLDEN / "sintel_clip_10s.mp4").read_bytes()
+    task = SplitPipeTask(session_id="s", video=Video(input_video="v.mp4", encoded_data=data))
+    stage = VideoFrameExtractionStage(output_hw=(27, 48), log_stats=True)
+    stage.stage_setup()
+    stage.process_data([task])
+    fa = task.video.frame_array.resolve()
+    assert fa.shape == (240, 27, 48, 3) and fa.dtype == np.uint8  # TransNetV2 input of the reference (a8/a9)
+    ids = [0, 100, 239]
+    pool = alloc_nv12_pool(ctx, 3, 854, 480)
+    Decoder(ctx).decode(data, ids, pool, [0, 1, 2])
+    nv12 = pool.buf.cpu().numpy()
+    for k, i in enumerate(ids):
+        want = preprocess.resize_bilinear_u8(color.nv12_to_rgb(np.ascontiguousarray(nv12[k][:, :854]), 480, 854), 27, 48)
+        d = np.abs(fa[i].astype(int) - want.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 5e-3
+    bad = SplitPipeTask(session_id="b", video=Video(input_video="b.mp4", encoded_data=b"\x01" * 999))
+    stage.process_data([bad])
+    assert bad.video.errors["frame_extraction"] == "null" and not bad.video.frame_array
+    with pytest.raises(ValueError):
+        stage.process_data([SplitPipeTask(session_id="n", video=Video(input_video="n.mp4"))])  # "Please load video bytes!"
+
+
+def test_model_interfaces_direct_calls(ctx):
+    from oracle import preprocess, vit
+
+    model, cfg, w, sd = _model()
+    model.setup()
+    rng = np.random.default_rng(2)
+    frames = rng.integers(0, 256, size=(5, 270, 480, 3), dtype=np.uint8)
+    scores = model(frames)
+    assert isinstance(scores, torch.Tensor) and scores.is_cuda and scores.shape == (5,)
+    emb, want = _oracle_scores(cfg, w, sd, frames)
+    np.testing.assert_allclose(scores.cpu().numpy(), want, atol=3e-3)
+    e2 = model._clip_model(torch.from_numpy(frames).permute(0, 3, 1, 2))  # NCHW tensor input like clip.py:64-70 accepts
+    assert np.linalg.norm(e2.cpu().numpy() - emb, axis=1).max() < 2e-3
+    assert model._clip_model(frames[:0]).shape == (0, cfg.proj_dim)
+    with pytest.raises(ValueError):
+        model(frames.astype(np.float32))
+    from cosmos_curate_b200.models.aesthetics import AestheticScorer
+
+    a = AestheticScorer(seed=3, dim=cfg.proj_dim)
+    a.setup()
+    np.testing.assert_allclose(a(emb).cpu().numpy(), emb @ a.w + a.b, rtol=1e-5, atol=1e-5)

@@ -51,6 +51,7 @@ struct ClipArgs {
   const float* lut;       // [3][256]
   int out_mode;           // 0 = u8 NCHW, 1 = typed NCHW, 2 = typed patch rows
   int x_align;            // source window start is aligned down to this many pixels (TMA: 16-byte aligned box start)
+  int gu;                 // v2: rows of the per-group dense weight table (>= widest 4-column union window)
   int dtype, patch, k_pad;
   void* out;
 };
@@ -223,6 +224,206 @@ __global__ void __launch_bounds__(kThreads) clip_preprocess_kernel(const __grid_
         }
         __syncthreads();
       }
+    }
+    next_out = last;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ v2
+// Same data flow as clip_preprocess_kernel, re-tiled so the horizontal pass stops being shared-memory bound:
+//   * output columns are processed in groups of 4 adjacent columns; their tap windows overlap by ~75 %, so one
+//     lane (= one source row) walks the UNION window once, loading each pixel once (3 x LDS.32) and applying it to
+//     the 4 columns with a dense, zero-padded weight row fetched as one broadcast LDS.128: 12 FMAs per 4 loads
+//     instead of 1 FMA per 2 loads.  fma(x, 0, acc) == acc, so the result is bit-identical to the tap-order chain.
+//   * colour conversion uses add-min-relu (DPX) instead of separate add / shift / clamp chains;
+//   * all output rows that became ready in a strip are emitted in one parallel sweep.
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, 2) clip_preprocess_v2_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                          const __grid_constant__ CUtensorMap map_b, const ClipArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int frame = blockIdx.y;
+  const int c0 = blockIdx.x * a.tc;
+  const int ncol = min(a.tc, a.res - c0);
+  const int slot = a.slots[frame];
+  const int ngroups = (ncol + 3) >> 2;
+
+  const int raw_stage = (FMT == CB_FMT_NV12) ? (a.swa * kSR + a.swa * (kSR / 2)) : (3 * a.swa * kSR);
+  const int swp = a.swa + 1;
+  const int tcp = a.tc | 1;
+  uint8_t* raw = smem;
+  float* rgbf = (float*)(smem + 2 * raw_stage);
+  float* ringb = rgbf + 3 * kSR * swp;
+  float4* wg = (float4*)(((uintptr_t)(ringb + 3 * a.ring * tcp) + 15) & ~(uintptr_t)15);  // [groups][gu] x 4 columns
+  int* gbase = (int*)(wg + ((a.tc + 3) >> 2) * a.gu);                                      // [groups] first source column, [groups] length
+  uint16_t* obuf = (uint16_t*)(gbase + 2 * ((a.tc + 3) >> 2));
+  const int npx = (a.out_mode == 2) ? a.tc / a.patch : 0;
+  uint64_t* bars = (uint64_t*)(((uintptr_t)(obuf + npx * a.k_pad) + 7) & ~(uintptr_t)7);
+
+  const int x_lo = a.xmin[c0] & ~(a.x_align - 1);
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  // dense weight table of this column tile
+  for (int i = tid; i < ngroups * a.gu; i += kThreads) wg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.out_mode == 2)
+    for (int i = tid; i < npx * a.k_pad; i += kThreads) obuf[i] = 0;
+  __syncthreads();
+  if (tid < ngroups) {
+    const int cfirst = c0 + 4 * tid, base = a.xmin[cfirst];
+    int len = 0;
+    for (int k = 0; k < 4 && 4 * tid + k < ncol; ++k) len = max(len, a.xmin[cfirst + k] + a.xsize[cfirst + k] - base);
+    gbase[tid] = base, gbase[ngroups + tid] = len;
+  }
+  for (int i = tid; i < ncol * a.tx; i += kThreads) {
+    const int c = i / a.tx, j = i - c * a.tx;
+    if (j < a.xsize[c0 + c]) {
+      const int g = c >> 2, k = c & 3;
+      const int d = a.xmin[c0 + c] - a.xmin[c0 + 4 * g];
+      ((float*)&wg[g * a.gu + d + j])[k] = a.wx[(size_t)(c0 + c) * a.tx + j];
+    }
+  }
+  __syncthreads();
+
+#define CB_ISSUE_STRIP2(S_)                                                                                       \
+  do {                                                                                                            \
+    const int s_ = (S_);                                                                                          \
+    uint8_t* dst_ = raw + (s_ & 1) * raw_stage;                                                                   \
+    uint64_t* bar_ = &bars[s_ & 1];                                                                               \
+    const int ys_ = a.y_begin + s_ * kSR;                                                                         \
+    mbar_expect_tx(bar_, raw_stage);                                                                              \
+    if (FMT == CB_FMT_NV12) {                                                                                     \
+      tma_load_3d(dst_, &map_a, bar_, x_lo, ys_, slot);                                                           \
+      tma_load_3d(dst_ + a.swa * kSR, &map_b, bar_, x_lo, ys_ >> 1, slot);                                        \
+    } else {                                                                                                      \
+      tma_load_3d(dst_, &map_a, bar_, x_lo * 3, ys_, slot);                                                       \
+      tma_load_3d(dst_ + a.swa * kSR, &map_a, bar_, x_lo * 3 + a.swa, ys_, slot);                                 \
+      tma_load_3d(dst_ + 2 * a.swa * kSR, &map_a, bar_, x_lo * 3 + 2 * a.swa, ys_, slot);                         \
+    }                                                                                                             \
+  } while (0)
+  if (tid == 0) {
+    CB_ISSUE_STRIP2(0);
+    if (a.n_strips > 1) CB_ISSUE_STRIP2(1);
+  }
+
+  int next_out = 0;
+  for (int s = 0; s < a.n_strips; ++s) {
+    const int y0 = a.y_begin + s * kSR;
+    const uint8_t* rs = raw + (s & 1) * raw_stage;
+    mbar_wait(&bars[s & 1], (s >> 1) & 1);
+
+    // ---- phase 1: colour conversion (one thread per horizontal pixel pair sharing a chroma sample)
+    if (FMT == CB_FMT_NV12) {
+      const int half_w = a.swa >> 1;
+      const uint8_t* ry = rs;
+      const uint8_t* ruv = rs + a.swa * kSR;
+      constexpr int kMax = (256 << 20) - 1;
+      for (int i = tid; i < kSR * half_w; i += kThreads) {
+        const int r = i / half_w, x = (i - r * half_w) * 2;
+        const uchar2 yy = *(const uchar2*)(ry + r * a.swa + x);
+        const uchar2 uv = *(const uchar2*)(ruv + (r >> 1) * a.swa + x);
+        const int u = (int)uv.x - 128, v = (int)uv.y - 128;
+        const int ruv_ = 1673527 * v, guv_ = -852492 * v - 409993 * u, buv_ = 2116026 * u;
+        const int y0v = max((int)yy.x - 16, 0) * 1220542 + (1 << 19), y1v = max((int)yy.y - 16, 0) * 1220542 + (1 << 19);
+        float* p = rgbf + r * swp + x;
+        p[0] = (float)(__viaddmin_s32_relu(y0v, ruv_, kMax) >> 20);
+        p[1] = (float)(__viaddmin_s32_relu(y1v, ruv_, kMax) >> 20);
+        p[kSR * swp] = (float)(__viaddmin_s32_relu(y0v, guv_, kMax) >> 20);
+        p[kSR * swp + 1] = (float)(__viaddmin_s32_relu(y1v, guv_, kMax) >> 20);
+        p[2 * kSR * swp] = (float)(__viaddmin_s32_relu(y0v, buv_, kMax) >> 20);
+        p[2 * kSR * swp + 1] = (float)(__viaddmin_s32_relu(y1v, buv_, kMax) >> 20);
+      }
+    } else {
+      for (int i = tid; i < kSR * a.swa; i += kThreads) {
+        const int r = i / a.swa, x = i - r * a.swa;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const int b = 3 * x + ch;
+          const int blk = b / a.swa, within = b - blk * a.swa;
+          rgbf[(ch * kSR + r) * swp + x] = (float)rs[(blk * kSR + r) * a.swa + within];
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && s + 2 < a.n_strips) {
+      fence_proxy_async();
+      CB_ISSUE_STRIP2(s + 2);
+    }
+
+    // ---- phase 2: horizontal filter, 4 columns x 3 channels per lane (lane = source row)
+    for (int g = warp; g < ngroups; g += kThreads / 32) {
+      const int len = gbase[ngroups + g];
+      const float* px = rgbf + lane * swp + (gbase[g] - x_lo);
+      const float4* w = wg + g * a.gu;
+      float acc[3][4];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) acc[ch][0] = acc[ch][1] = acc[ch][2] = acc[ch][3] = 0.f;
+#pragma unroll 4
+      for (int p = 0; p < len; ++p) {
+        const float4 wv = w[p];
+        const float r = px[p], gg = px[kSR * swp + p], b = px[2 * kSR * swp + p];
+        acc[0][0] = fmaf(r, wv.x, acc[0][0]), acc[0][1] = fmaf(r, wv.y, acc[0][1]), acc[0][2] = fmaf(r, wv.z, acc[0][2]), acc[0][3] = fmaf(r, wv.w, acc[0][3]);
+        acc[1][0] = fmaf(gg, wv.x, acc[1][0]), acc[1][1] = fmaf(gg, wv.y, acc[1][1]), acc[1][2] = fmaf(gg, wv.z, acc[1][2]), acc[1][3] = fmaf(gg, wv.w, acc[1][3]);
+        acc[2][0] = fmaf(b, wv.x, acc[2][0]), acc[2][1] = fmaf(b, wv.y, acc[2][1]), acc[2][2] = fmaf(b, wv.z, acc[2][2]), acc[2][3] = fmaf(b, wv.w, acc[2][3]);
+      }
+      const int slot_row = (y0 + lane) & (a.ring - 1);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (4 * g + k < ncol) ringb[(ch * a.ring + slot_row) * tcp + 4 * g + k] = acc[ch][k];
+    }
+    __syncthreads();
+
+    // ---- phase 3: emit all output rows whose vertical window is complete, one patch row at a time
+    int last = next_out;
+    const bool final_strip = (s == a.n_strips - 1);
+    while (last < a.res && (final_strip || a.ymin[last] + a.ysize[last] <= y0 + kSR)) ++last;
+    int seg = next_out;
+    while (seg < last) {
+      const int seg_end = (a.out_mode == 2) ? min(last, (seg / a.patch + 1) * a.patch) : last;
+      const int per_row = ncol * 3;
+      for (int item = tid; item < (seg_end - seg) * per_row; item += kThreads) {
+        const int yo = seg + item / per_row, rem = item % per_row;
+        const int ch = rem / ncol, c = rem - ch * ncol;
+        const int ym = a.ymin[yo], ys = a.ysize[yo];
+        const float* w = a.wy + (size_t)yo * a.ty;
+        const float* rb = ringb + (size_t)ch * a.ring * tcp + c;
+        float acc = rb[(ym & (a.ring - 1)) * tcp] * __ldg(w);
+        for (int k = 1; k < ys; ++k) acc = fmaf(rb[((ym + k) & (a.ring - 1)) * tcp], __ldg(w + k), acc);
+        acc = fminf(fmaxf(acc, 0.f), 255.f);
+        const int v = __float2int_rn(acc);
+        const int x = c0 + c;
+        if (a.out_mode == 0) {
+          ((uint8_t*)a.out)[(((size_t)frame * 3 + ch) * a.res + yo) * a.res + x] = (uint8_t)v;
+        } else {
+          const float f = a.lut[ch * 256 + v];
+          if (a.out_mode == 1) {
+            store_typed(a.out, (((size_t)frame * 3 + ch) * a.res + yo) * a.res + x, f, a.dtype);
+          } else {
+            const int ip = c / a.patch, px_ = c - ip * a.patch, py = yo % a.patch;
+            const uint16_t bits = (a.dtype == CB_DT_F16) ? __half_as_ushort(__float2half_rn(f))
+                                                         : __bfloat16_as_ushort(__float2bfloat16_rn(f));
+            obuf[ip * a.k_pad + (ch * a.patch + py) * a.patch + px_] = bits;
+          }
+        }
+      }
+      if (a.out_mode == 2 && (seg_end % a.patch) == 0) {  // a row of patches is complete: 128-bit stores
+        __syncthreads();
+        const int gsz = a.res / a.patch, prow = (seg_end - 1) / a.patch, vec = a.k_pad >> 3;
+        const int np = ncol / a.patch;
+        for (int i = tid; i < np * vec; i += kThreads) {
+          const int ip = i / vec, q = i - ip * vec;
+          uint4* dst = (uint4*)((uint16_t*)a.out + ((size_t)frame * gsz * gsz + (size_t)prow * gsz + (c0 / a.patch + ip)) * a.k_pad);
+          dst[q] = ((const uint4*)(obuf + ip * a.k_pad))[q];
+        }
+        __syncthreads();
+      }
+      seg = seg_end;
     }
     next_out = last;
   }
@@ -448,6 +649,18 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
     span = std::max(span, hi - lo);
   }
   a.swa = (span + 15) & ~15;
+  // v2: widest union window of any group of 4 adjacent output columns
+  int gu = 1;
+  for (int c = 0; c < res; c += 4) {
+    if ((c % a.tc) + 4 > a.tc && (c % a.tc) % 4) continue;
+    const int cl = std::min(res, std::min(c + 4, (c / a.tc + 1) * a.tc));
+    int hi = 0;
+    for (int k = c; k < cl; ++k) hi = std::max(hi, tx->h_min[k] + tx->h_size[k] - tx->h_min[c]);
+    gu = std::max(gu, hi);
+  }
+  a.gu = gu;
+  const char* kver = getenv("CB_PRE_KERNEL");
+  const bool use_v2 = !(kver && kver[0] == '1');
   if (a.swa > 256) return fail(ctx, CB_ERR_UNSUPPORTED, "downscale too large for one TMA box (%d source columns per tile)", a.swa);
 
   rc = ensure_norm_lut(ctx, mean, std_, stream);
@@ -482,10 +695,19 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
   const int raw_stage = (pool->format == CB_FMT_NV12) ? (a.swa * kSR * 3 / 2) : (3 * a.swa * kSR);
   const int npx = out_mode == 2 ? a.tc / a.patch : 0;
   size_t smem = 2 * (size_t)raw_stage + (size_t)3 * kSR * (a.swa + 1) * 4 + (size_t)3 * a.ring * (a.tc | 1) * 4 + (size_t)npx * k_pad * 2 + 32;
+  if (use_v2) smem += 16 + (size_t)((a.tc + 3) / 4) * a.gu * 16 + (size_t)2 * ((a.tc + 3) / 4) * 4;
   if (smem > 227 * 1024) return fail(ctx, CB_ERR_UNSUPPORTED, "preprocess tile needs %zu bytes of shared memory", smem);
   dim3 grid(tiles, n);
   mark_launch(ctx, CB_PROF_PREPROCESS, stream);
-  if (pool->format == CB_FMT_NV12) {
+  if (use_v2) {
+    if (pool->format == CB_FMT_NV12) {
+      CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_v2_kernel<CB_FMT_NV12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      clip_preprocess_v2_kernel<CB_FMT_NV12><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
+    } else {
+      CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_v2_kernel<CB_FMT_RGB24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      clip_preprocess_v2_kernel<CB_FMT_RGB24><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
+    }
+  } else if (pool->format == CB_FMT_NV12) {
     CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_kernel<CB_FMT_NV12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     clip_preprocess_kernel<CB_FMT_NV12><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
   } else {

@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 2) clip_preprocess_v2_kernel(const _
   float* ringb = rgbf + 3 * kSR * swp;
   float4* wg = (float4*)(((uintptr_t)(ringb + 3 * a.ring * tcp) + 15) & ~(uintptr_t)15);  // [groups][gu] x 4 columns
   int* gbase = (int*)(wg + ((a.tc + 3) >> 2) * a.gu);                                      // [groups] first source column, [groups] length
-  uint16_t* obuf = (uint16_t*)(gbase + 2 * ((a.tc + 3) >> 2));
+  uint16_t* obuf = (uint16_t*)(((uintptr_t)(gbase + 2 * ((a.tc + 3) >> 2)) + 15) & ~(uintptr_t)15);
   const int npx = (a.out_mode == 2) ? a.tc / a.patch : 0;
   uint64_t* bars = (uint64_t*)(((uintptr_t)(obuf + npx * a.k_pad) + 7) & ~(uintptr_t)7);
 
@@ -695,7 +695,7 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
   const int raw_stage = (pool->format == CB_FMT_NV12) ? (a.swa * kSR * 3 / 2) : (3 * a.swa * kSR);
   const int npx = out_mode == 2 ? a.tc / a.patch : 0;
   size_t smem = 2 * (size_t)raw_stage + (size_t)3 * kSR * (a.swa + 1) * 4 + (size_t)3 * a.ring * (a.tc | 1) * 4 + (size_t)npx * k_pad * 2 + 32;
-  if (use_v2) smem += 16 + (size_t)((a.tc + 3) / 4) * a.gu * 16 + (size_t)2 * ((a.tc + 3) / 4) * 4;
+  if (use_v2) smem += 48 + (size_t)((a.tc + 3) / 4) * a.gu * 16 + (size_t)2 * ((a.tc + 3) / 4) * 4;
   if (smem > 227 * 1024) return fail(ctx, CB_ERR_UNSUPPORTED, "preprocess tile needs %zu bytes of shared memory", smem);
   dim3 grid(tiles, n);
   mark_launch(ctx, CB_PROF_PREPROCESS, stream);

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(const float* __restrict__
 
 // ------------------------------------------------------------------------------------ attention
 __device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -117,6 +117,11 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, uint32_t addr) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
 }
+__device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2, inputs <= 0 here; flush-to-zero is what softmax wants
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *(const uint32_t*)&h;
@@ -125,11 +130,22 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 constexpr int kAttnWarps = 9;
 constexpr int kAttnThreads = kAttnWarps * 32;
 
-// HD: head dim padded to a multiple of 16 (64 -> 64, 72 -> 80).  One CTA per (image, head).
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// HD: head dim padded to a multiple of 16 (64 -> 64, 72 -> 80).  One CTA per (image, head): K and V of the head stay in
+// shared memory (cp.async fill), each warp owns 16-query tiles.  T is short (257 / 50 / ...), so instead of an online
+// softmax the kernel makes two passes over the keys: pass A takes the exact row maxima from S = Q K^T, pass B recomputes S
+// in 32-key chunks, forms P = exp2((S - m) * scale * log2e) in fp32, accumulates the row sums and O += P V.  MMAs are issued
+// over independent accumulators back to back (legacy tensor pipe latency), fragment loads are batched ahead of them.
 template <int HD>
 __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int tokens,
                                                                      int heads, int head_dim, float scale_log2e) {
   constexpr int PITCH = HD + 8;  // halves; 16-byte row skew keeps ldmatrix conflict-free
+  constexpr int KS = HD / 16;    // k-steps over the head dimension
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int t_pad = (tokens + 15) & ~15;
   __half* sK = (__half*)smem_attn;
@@ -140,105 +156,137 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
   const __half* base = qkv + (size_t)img * tokens * row_stride + (size_t)head * head_dim;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
 
-  // K and V (zero padded in both directions) -> shared memory, 16-byte vectors
+  // K and V (zero padded in both directions) -> shared memory, all copies in flight at once
   constexpr int VEC = HD / 8;
   const int vec_valid = head_dim / 8;  // head_dim % 8 == 0 is checked on the host
   for (int i = threadIdx.x; i < t_pad * VEC; i += kAttnThreads) {
     const int r = i / VEC, c = i - r * VEC;
-    uint4 k4 = make_uint4(0, 0, 0, 0), v4 = make_uint4(0, 0, 0, 0);
+    __half* dk = sK + (size_t)r * PITCH + c * 8;
+    __half* dv = sV + (size_t)r * PITCH + c * 8;
     if (r < tokens && c < vec_valid) {
       const __half* p = base + (size_t)r * row_stride + c * 8;
-      k4 = *(const uint4*)(p + hidden);
-      v4 = *(const uint4*)(p + 2 * hidden);
+      cp_async_16(dk, p + hidden);
+      cp_async_16(dv, p + 2 * hidden);
+    } else {
+      *(uint4*)dk = make_uint4(0, 0, 0, 0);
+      *(uint4*)dv = make_uint4(0, 0, 0, 0);
     }
-    *(uint4*)(sK + (size_t)r * PITCH + c * 8) = k4;
-    *(uint4*)(sV + (size_t)r * PITCH + c * 8) = v4;
   }
-  __syncthreads();
 
   const int q_tiles = t_pad >> 4;
+  bool first = true;
   for (int qt = warp; qt < q_tiles; qt += kAttnWarps) {
     // Q fragments straight from global memory (rows clamped; padded columns read as zero)
-    uint32_t qa[HD / 16][4];
+    uint32_t qa[KS][4];
     const int r0 = min(qt * 16 + g, tokens - 1), r1 = min(qt * 16 + g + 8, tokens - 1);
 #pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks) {
+    for (int ks = 0; ks < KS; ++ks) {
       const int c0 = ks * 16 + t4 * 2, c1 = c0 + 8;
-      qa[ks][0] = c0 < head_dim ? *(const uint32_t*)(base + (size_t)r0 * row_stride + c0) : 0u;
-      qa[ks][1] = c0 < head_dim ? *(const uint32_t*)(base + (size_t)r1 * row_stride + c0) : 0u;
-      qa[ks][2] = c1 < head_dim ? *(const uint32_t*)(base + (size_t)r0 * row_stride + c1) : 0u;
-      qa[ks][3] = c1 < head_dim ? *(const uint32_t*)(base + (size_t)r1 * row_stride + c1) : 0u;
+      qa[ks][0] = c0 < head_dim ? __ldg((const uint32_t*)(base + (size_t)r0 * row_stride + c0)) : 0u;
+      qa[ks][1] = c0 < head_dim ? __ldg((const uint32_t*)(base + (size_t)r1 * row_stride + c0)) : 0u;
+      qa[ks][2] = c1 < head_dim ? __ldg((const uint32_t*)(base + (size_t)r0 * row_stride + c1)) : 0u;
+      qa[ks][3] = c1 < head_dim ? __ldg((const uint32_t*)(base + (size_t)r1 * row_stride + c1)) : 0u;
     }
+    if (qt + kAttnWarps < q_tiles) {  // pull the next tile's Q rows towards L2 while this tile computes
+      const int rn = min((qt + kAttnWarps) * 16 + (lane & 15), tokens - 1);
+      prefetch_l2(base + (size_t)rn * row_stride);
+    }
+    if (first) {  // the Q loads above overlap the K/V fill
+      cp_async_wait_all();
+      __syncthreads();
+      first = false;
+    }
+
+    // S = Q K^T for `nkt` 8-key tiles starting at key kc (nkt is 4, or 2 in the tail of a 16-multiple length)
+    auto qk_chunk = [&](int kc, int nkt, float (&sc)[4][4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
+#pragma unroll
+      for (int kp = 0; kp < HD / 32; ++kp) {  // two k-steps per ldmatrix.x4
+        uint32_t kb[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nkt) ldmatrix_x4(kb[i], smem_u32(sK + (size_t)(kc + i * 8 + (lane & 7)) * PITCH + kp * 32 + (lane >> 3) * 8));
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nkt) mma_16816(sc[i], qa[2 * kp], kb[i][0], kb[i][1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nkt) mma_16816(sc[i], qa[2 * kp + 1], kb[i][2], kb[i][3]);
+      }
+      if (HD % 32) {  // odd number of k-steps (HD = 80): last 16 columns
+        uint32_t kb[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nkt) ldmatrix_x4(kb[i], smem_u32(sK + (size_t)(kc + i * 8 + (lane & 7)) * PITCH + (HD - 16) + ((lane >> 3) & 1) * 8));
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nkt) mma_16816(sc[i], qa[KS - 1], kb[i][0], kb[i][1]);
+      }
+    };
+
+    // ---- pass A: exact row maxima
+    float m0 = -INFINITY, m1 = -INFINITY;  // rows g and g+8
+    for (int kc = 0; kc < t_pad; kc += 32) {
+      const int nkt = min(4, (t_pad - kc) >> 3);
+      float sc[4][4];
+      qk_chunk(kc, nkt, sc);
+      if (kc + 32 > tokens) {  // only the last chunk(s) hold padded keys
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int key = kc + i * 8 + t4 * 2;
+          if (key >= tokens) sc[i][0] = sc[i][2] = -INFINITY;
+          if (key + 1 >= tokens) sc[i][1] = sc[i][3] = -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        m0 = fmaxf(m0, fmaxf(sc[i][0], sc[i][1]));
+        m1 = fmaxf(m1, fmaxf(sc[i][2], sc[i][3]));
+      }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    const float b0 = m0 * scale_log2e, b1 = m1 * scale_log2e;
+
+    // ---- pass B: P = exp2(S*c - m*c), row sums, O += P V
     float o[HD / 8][4];
 #pragma unroll
     for (int d = 0; d < HD / 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // running max / sum for rows g and g+8
-
-    for (int kc = 0; kc < t_pad; kc += 64) {  // 64 keys per step (t_pad is a multiple of 16)
-      const int nkt = min(8, (t_pad - kc) >> 3);  // 8-key tiles in this chunk (even)
-      float s[8][4];
+    float l0 = 0.f, l1 = 0.f;
+    for (int kc = 0; kc < t_pad; kc += 32) {
+      const int nkt = min(4, (t_pad - kc) >> 3);
+      float sc[4][4];
+      qk_chunk(kc, nkt, sc);
+      const bool tail = kc + 32 > tokens;
+      uint32_t pa[2][4];  // P as A fragments: k-step j covers key tiles 2j, 2j+1
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        if (nt < nkt) {
-#pragma unroll
-          for (int kp = 0; kp < HD / 32; ++kp) {  // two k-steps per ldmatrix.x4
-            uint32_t kb[4];
-            ldmatrix_x4(kb, smem_u32(sK + (size_t)(kc + nt * 8 + (lane & 7)) * PITCH + kp * 32 + (lane >> 3) * 8));
-            mma_16816(s[nt], qa[2 * kp], kb[0], kb[1]);
-            mma_16816(s[nt], qa[2 * kp + 1], kb[2], kb[3]);
-          }
-          if (HD % 32) {  // odd number of k-steps (HD = 80): last 16 columns
-            uint32_t kb[4];
-            ldmatrix_x4(kb, smem_u32(sK + (size_t)(kc + nt * 8 + (lane & 7)) * PITCH + (HD - 16) + ((lane >> 3) & 1) * 8));
-            mma_16816(s[nt], qa[HD / 16 - 1], kb[0], kb[1]);
-          }
-        }
-      }
-      // mask padded keys, running max
-      float mx0 = m0, mx1 = m1;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        if (nt < nkt) {
-          const int key = kc + nt * 8 + t4 * 2;
-          if (key >= tokens) s[nt][0] = s[nt][2] = -INFINITY;
-          if (key + 1 >= tokens) s[nt][1] = s[nt][3] = -INFINITY;
-          mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-          mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-        }
-      }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float corr0 = exp2f((m0 - mx0) * scale_log2e), corr1 = exp2f((m1 - mx1) * scale_log2e);
-      m0 = mx0, m1 = mx1;
-      l0 *= corr0, l1 *= corr1;
-#pragma unroll
-      for (int d = 0; d < HD / 8; ++d) o[d][0] *= corr0, o[d][1] *= corr0, o[d][2] *= corr1, o[d][3] *= corr1;
-      const float b0 = m0 * scale_log2e, b1 = m1 * scale_log2e;
-      uint32_t pa[4][4];  // P as A fragments: k-step j covers key tiles 2j, 2j+1
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-        if (nt < nkt) {
-          p0 = exp2f(fmaf(s[nt][0], scale_log2e, -b0)), p1 = exp2f(fmaf(s[nt][1], scale_log2e, -b0));
-          p2 = exp2f(fmaf(s[nt][2], scale_log2e, -b1)), p3 = exp2f(fmaf(s[nt][3], scale_log2e, -b1));
+      for (int i = 0; i < 4; ++i) {
+        float p0 = fast_exp2(fmaf(sc[i][0], scale_log2e, -b0)), p1 = fast_exp2(fmaf(sc[i][1], scale_log2e, -b0));
+        float p2 = fast_exp2(fmaf(sc[i][2], scale_log2e, -b1)), p3 = fast_exp2(fmaf(sc[i][3], scale_log2e, -b1));
+        if (tail) {  // padded keys contribute nothing (their V rows are zero as well)
+          const int key = kc + i * 8 + t4 * 2;
+          if (key >= tokens) p0 = p2 = 0.f;
+          if (key + 1 >= tokens) p1 = p3 = 0.f;
         }
         l0 += p0 + p1, l1 += p2 + p3;
-        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_half2(p0, p1);
-        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_half2(p2, p3);
+        pa[i >> 1][(i & 1) * 2 + 0] = pack_half2(p0, p1);
+        pa[i >> 1][(i & 1) * 2 + 1] = pack_half2(p2, p3);
       }
-      // O += P V
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
         if (2 * j < nkt) {
+          constexpr int DP = HD / 16;  // pairs of 8-wide dim tiles
+          uint32_t vb[DP][4];
 #pragma unroll
-          for (int dp = 0; dp < HD / 16; ++dp) {  // two 8-wide dim tiles per ldmatrix.x4.trans
-            uint32_t vb[4];
-            ldmatrix_x4_trans(vb, smem_u32(sV + (size_t)(kc + j * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + dp * 16 + (lane >> 4) * 8));
-            mma_16816(o[2 * dp], pa[j], vb[0], vb[1]);
-            mma_16816(o[2 * dp + 1], pa[j], vb[2], vb[3]);
+          for (int dp = 0; dp < DP; ++dp)
+            ldmatrix_x4_trans(vb[dp], smem_u32(sV + (size_t)(kc + j * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + dp * 16 + (lane >> 4) * 8));
+#pragma unroll
+          for (int dp = 0; dp < DP; ++dp) {
+            mma_16816(o[2 * dp], pa[j], vb[dp][0], vb[dp][1]);
+            mma_16816(o[2 * dp + 1], pa[j], vb[dp][2], vb[dp][3]);
           }
         }
       }
@@ -259,6 +307,10 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
         if (row1 < tokens) *(uint32_t*)(ob + (size_t)row1 * hidden + c) = pack_half2(o[d][2] * inv1, o[d][3] * inv1);
       }
     }
+  }
+  if (first) {  // a warp without a tile (q_tiles < warps) still has to meet the fill barrier
+    cp_async_wait_all();
+    __syncthreads();
   }
 }
 

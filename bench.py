@@ -98,27 +98,24 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # under torchrun only rank 0 measures the CPU path
-    import torch
-
     from oracle import cpu_path, vit
 
     cores = os.cpu_count() or 1
-    cfg = vit.CLIP_VIT_L14
-    w = vit.random_weights(cfg, seed=0)
-    sd = vit.random_aesthetic_mlp(seed=0, in_dim=cfg.proj_dim)
-    path = cpu_path.CpuReferencePath(cfg, w, sd, threads=cores)
+    procs, threads = cpu_layout(cores)
+    pool = cpu_path.CpuReferencePool(vit.CLIP_VIT_L14, seed=0, procs=procs, threads=threads)
     clips = make_clips(2, 0)
-    sample = max(1, args.ref_clips)
+    sample = max(procs, args.ref_clips)  # at least one clip per worker so every host core is busy
     batch = [clips[i % len(clips)] for i in range(sample)]
-    for _ in range(args.warmup):
-        path.run(batch[:1], SAMPLE_FPS)
+    for _ in range(max(1, args.warmup)):
+        pool.run(batch[:procs], SAMPLE_FPS)
     t, frames, phases = 0.0, 0, {"decode_s": 0.0, "preprocess_s": 0.0, "model_s": 0.0}
     for _ in range(args.steps):
-        r = path.run(batch, SAMPLE_FPS)
+        r = pool.run(batch, SAMPLE_FPS)
         t += r["seconds"]
         frames += r["frames"]
         for k in phases:
             phases[k] += r[k]
+    pool.close()
     value = sample * args.steps / t
     line = {
         "impl": "reference", "metric": "clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -126,11 +123,12 @@ def run_reference(args) -> None:
         "frames_per_sec": frames / t,
         "config": {"workload": "1080p30 10s H.264 clips -> 1 fps sampling -> CLIP ViT-L/14 embed + aesthetic score", "clips_per_step": sample,
                    "frames_per_clip": frames // (sample * args.steps), "model": "clip-vit-large-patch14 (seeded random weights)", "parallelism": "host threads"},
-        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} clip(s) per step x {args.steps} steps; cv2/libavcodec decode (PyAV stand-in) + torchvision transforms + oracle torch-fp32 tower",
-                         "phase_seconds": phases},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": procs * threads, "kind": "port",
+                         "sample": f"{sample} clip(s) per step x {args.steps} steps over {procs} worker processes x {threads} threads; cv2/libavcodec decode "
+                                   "(PyAV stand-in) + torchvision transforms + oracle torch-fp32 tower, one model call per clip",
+                         "worker_seconds": phases},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "torch_threads": torch.get_num_threads(),
+        "host_cores": cores,
     }  # fmt: skip
     print(json.dumps(line))
 
@@ -166,22 +164,36 @@ def run_b200(args) -> None:
     tower = VitTower(ctx, cfg.to_dict(), W.seeded_weights(cfg, 0), max_batch=frames_per_step, aesthetic=W.seeded_aesthetic(cfg.proj_dim, 0))
     pools = [alloc_nv12_pool(ctx, frames_per_step, FRAME_W, FRAME_H) for _ in range(2)]
     n_dec = args.decoders
-    decoders = [Decoder(ctx) for _ in range(n_dec)]
-    tp = ThreadPoolExecutor(max_workers=n_dec)
+    tp = ThreadPoolExecutor(max_workers=n_dec)       # one NVDEC session per worker thread (thread-local, reused across clips)
+    coord = ThreadPoolExecutor(max_workers=1)         # runs "decode step i+1" while the tower works on step i
+    tls = threading.local()
+    all_decoders = []
     host_emb = torch.empty((frames_per_step, cfg.proj_dim), dtype=torch.float32).pin_memory()
     host_score = torch.empty((frames_per_step,), dtype=torch.float32).pin_memory()
     step_clips = [i % len(clips) for i in range(cps)]
 
-    def decode_step(pool):
+    def my_decoder():
+        d = getattr(tls, "dec", None)
+        if d is None:
+            d = tls.dec = Decoder(ctx)
+            all_decoders.append(d)
+        return d
+
+    def decode_step(pool, seek=False):
         def work(j):
             k = step_clips[j]
-            # worker thread j % n_dec owns decoders[j % n_dec]: submit in waves so a decoder is never shared
-            return decoders[j % n_dec].decode(clips[k], plans[k], pool, np.arange(j * fpc, (j + 1) * fpc, dtype=np.int32))["frames_decoded"]
+            return my_decoder().decode(clips[k], plans[k], pool, np.arange(j * fpc, (j + 1) * fpc, dtype=np.int32), seek_keyframes=seek)["frames_decoded"]
 
-        done = 0
-        for wave in range(0, cps, n_dec):
-            done += sum(tp.map(work, range(wave, min(cps, wave + n_dec))))
-        return done
+        return sum(tp.map(work, range(cps)))
+
+    def decode_ceiling(reps: int) -> float:
+        """All NVDEC sessions decoding whole clips, surfaces discarded: frames/s."""
+        from cosmos_curate_b200.runtime import decode_discard
+
+        list(tp.map(lambda j: decode_discard(my_decoder(), clips[step_clips[j]]), range(n_dec)))  # warm-up: sessions created
+        t0 = time.perf_counter()
+        n = sum(tp.map(lambda j: decode_discard(my_decoder(), clips[step_clips[j % cps]]), range(reps)))
+        return n / (time.perf_counter() - t0)
 
     def barrier():
         torch.cuda.synchronize()
@@ -196,7 +208,7 @@ def run_b200(args) -> None:
         return float(t.item())
 
     # ---- resident-input measurement (value): decoded surfaces of one step already in HBM
-    decoded_per_step = decode_step(pools[0])
+    decode_step(pools[0])
     barrier()
     for _ in range(max(args.warmup, 3)):
         tower.embed_pool(pools[0])
@@ -217,30 +229,43 @@ def run_b200(args) -> None:
     launches = ctx.launch_count() - l0
     value = world * cps * args.steps / dev_s
 
-    # ---- end-to-end measurement (e2e): host mp4 bytes -> NVDEC -> preprocess -> tower -> host results
-    def e2e_step(i):
-        pool = pools[i & 1]
-        decode_step(pool)
-        emb, _, score = tower.embed_pool(pool)
-        host_emb.copy_(emb, non_blocking=True)
-        host_score.copy_(score, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    # ---- end-to-end measurement (e2e): host mp4 bytes -> NVDEC -> preprocess -> tower -> host results.
+    # Decode of step i+1 (NVDEC engines + host parsing threads) overlaps the tower of step i (SMs); two surface pools.
+    def e2e_run(n_steps: int, seek: bool):
+        fut = coord.submit(decode_step, pools[0], seek)
+        decoded = 0
+        for i in range(n_steps):
+            decoded += fut.result()
+            if i + 1 < n_steps:
+                fut = coord.submit(decode_step, pools[(i + 1) & 1], seek)
+            emb, _, score = tower.embed_pool(pools[i & 1])
+            host_emb.copy_(emb, non_blocking=True)
+            host_score.copy_(score, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return decoded
 
-    e2e = None
-    if not args.no_e2e:
-        for i in range(max(1, min(args.warmup, 2))):
-            e2e_step(i)
+    def e2e_measure(seek: bool):
+        e2e_run(max(1, min(args.warmup, 2)), seek)
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.e2e_steps):
-            e2e_step(i)
+        decoded = e2e_run(args.e2e_steps, seek)
         barrier()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        sec = max_over_ranks(time.perf_counter() - t0)
         h2d = sum(len(clips[k]) for k in step_clips)
-        e2e = {"value": world * cps * args.e2e_steps / e2e_s, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": frames_per_step * (cfg.proj_dim + 1) * 4,
-               "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_s / args.e2e_steps, "frames_per_sec": world * frames_per_step * args.e2e_steps / e2e_s,
-               "decoded_frames_per_sec": world * decoded_per_step * args.e2e_steps / e2e_s, "nvdec_sessions": n_dec,
-               "note": "every frame up to the last sampled one is decoded (reference semantics); bitstream is I_PCM-heavy synthetic H.264"}  # fmt: skip
+        return {"value": world * cps * args.e2e_steps / sec, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": frames_per_step * (cfg.proj_dim + 1) * 4,
+                "steps": args.e2e_steps, "ms_per_step": 1e3 * sec / args.e2e_steps, "frames_per_sec": world * frames_per_step * args.e2e_steps / sec,
+                "decoded_frames_per_sec": world * decoded / sec, "decoded_frames_per_step": decoded // args.e2e_steps, "nvdec_sessions": n_dec}  # fmt: skip
+
+    e2e = e2e_sparse = ceiling = None
+    if not args.no_e2e:
+        e2e = e2e_measure(seek=False)
+        e2e["note"] = ("every frame up to the last sampled one is decoded (reference semantics, decoder_utils.py:439-455); synthetic I_PCM + "
+                       "motion-only P pictures; decode of step i+1 overlaps the tower of step i")
+        e2e_sparse = e2e_measure(seek=True)
+        e2e_sparse["note"] = "CB_DECODE_SEEK_SYNC: only GOPs holding sampled frames are decoded (identical frames); closed GOP = 30, 1 fps sampling"
+        ceil_fps = decode_ceiling(2 * n_dec)
+        ceiling = {"decode_only_frames_per_sec_per_gpu": ceil_fps, "sessions": n_dec,
+                   "e2e_fraction_of_decode_ceiling": (e2e["decoded_frames_per_sec"] / world) / ceil_fps if ceil_fps > 0 else None}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -276,7 +301,7 @@ def run_b200(args) -> None:
                      "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)", "launches_per_step": gemm_n / args.steps,
                      "ms_per_step": gemm_ms / args.steps, "share_of_step": gemm_ms / args.steps / step_ms},
         "roofline_other": other,
-        "e2e": e2e,
+        "e2e": e2e, "e2e_keyframe_seek": e2e_sparse, "decode_roofline": ceiling,
     }  # fmt: skip
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(clips[:1])
@@ -285,19 +310,29 @@ def run_b200(args) -> None:
         dist.destroy_process_group()
 
 
+def cpu_layout(cores: int) -> tuple[int, int]:
+    """(worker processes, torch threads each): the reference scales this path by replicating actors, not by threading one model."""
+    threads = 16 if cores >= 32 else max(1, cores // 2)
+    return max(1, cores // threads), threads
+
+
 def cpu_baseline(clips: list[bytes]) -> dict:
     """Bounded CPU sample of the same workload: the oracle's restatement of the reference path (kind 'port')."""
     from oracle import cpu_path, vit
 
     cores = os.cpu_count() or 1
-    cfg = vit.CLIP_VIT_L14
-    path = cpu_path.CpuReferencePath(cfg, vit.random_weights(cfg, seed=0), vit.random_aesthetic_mlp(seed=0, in_dim=cfg.proj_dim), threads=cores)
-    path.run(clips[:1], SAMPLE_FPS)  # warm-up (thread pools, allocator)
-    n = 2
-    r = path.run([clips[i % len(clips)] for i in range(n)], SAMPLE_FPS)
-    return {"value": r["clips"] / r["seconds"], "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": f"{n} clips (1080p30 10 s, {r['frames']} sampled frames): cv2/libavcodec decode + torchvision transforms + oracle torch-fp32 ViT-L/14",
-            "frames_per_sec": r["frames"] / r["seconds"], "phase_seconds": {k: r[k] for k in ("decode_s", "preprocess_s", "model_s")}}  # fmt: skip
+    procs, threads = cpu_layout(cores)
+    pool = cpu_path.CpuReferencePool(vit.CLIP_VIT_L14, seed=0, procs=procs, threads=threads)
+    try:
+        pool.run([clips[i % len(clips)] for i in range(procs)], SAMPLE_FPS)  # warm-up: one clip per worker
+        n = 2 * procs
+        r = pool.run([clips[i % len(clips)] for i in range(n)], SAMPLE_FPS)
+    finally:
+        pool.close()
+    return {"value": r["clips"] / r["seconds"], "unit": "clips/s", "cores": procs * threads, "kind": "port",
+            "sample": f"{n} clips (1080p30 10 s, {r['frames']} sampled frames) over {procs} worker processes x {threads} threads: cv2/libavcodec decode + "
+                      "torchvision transforms + oracle torch-fp32 ViT-L/14, one model call per clip",
+            "frames_per_sec": r["frames"] / r["seconds"], "worker_seconds": {k: r[k] for k in ("decode_s", "preprocess_s", "model_s")}}  # fmt: skip
 
 
 def main() -> None:

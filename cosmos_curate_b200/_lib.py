@@ -21,6 +21,7 @@ LAYOUT_NCHW, LAYOUT_PATCH = 0, 1
 ACT_QUICK_GELU, ACT_GELU_TANH = 0, 1
 ARCH_CLIP, ARCH_SIGLIP = 0, 1
 EPI_NONE, EPI_QUICK_GELU, EPI_GELU_TANH = 0, 1, 2
+DECODE_SEEK_SYNC, DECODE_DISCARD_ALL = 1, 2
 
 
 class CurateB200Error(RuntimeError):
@@ -87,6 +88,7 @@ SIGNATURES = {
     "cb_decoder_create": (_i, [_vp, C.POINTER(_vp)]),
     "cb_decoder_destroy": (None, [_vp]),
     "cb_decoder_decode": (_i, [_vp, _vp, C.c_size_t, _pi32, _i, C.POINTER(SurfacePool), _pi32, C.POINTER(DecodeStats)]),
+    "cb_decoder_decode_ex": (_i, [_vp, _vp, C.c_size_t, _pi32, _i, C.POINTER(SurfacePool), _pi32, _i, C.POINTER(DecodeStats)]),
     "cb_decoder_decode_thumbnails": (_i, [_vp, _vp, C.c_size_t, _i, _i, _vp, _i, C.POINTER(DecodeStats)]),
     "cb_gemm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cb_layernorm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),

@@ -186,6 +186,8 @@ struct cb_decoder {
   size_t dst_slot_stride = 0;
   int dst_pitch = 0, dst_luma_rows = 0, dst_w = 0, dst_h = 0;
   bool done = false;
+  bool discard = false;            // decode everything, deliver nothing (decode-rate ceiling measurement)
+  std::vector<int32_t> rank;       // sample index (decode order) -> display-order frame index
   // thumbnail mode (cb_decoder_decode_thumbnails): every displayed frame -> out_w x out_h RGB, no surface copy
   uint8_t* thumb_out = nullptr;
   int thumb_w = 0, thumb_h = 0, thumb_cap = 0;
@@ -251,7 +253,14 @@ int on_decode(void* user, void* pic) {
 int on_display(void* user, CUVIDPARSERDISPINFO* info) {
   cb_decoder* d = (cb_decoder*)user;
   if (!info || d->done) return 1;
-  const int idx = d->display_index++;
+  d->display_index++;
+  if (d->discard) return 1;
+  const long long smp = info->timestamp;
+  if (smp < 0 || smp >= (long long)d->rank.size()) {
+    d->error = "decoder returned an unknown picture timestamp";
+    return 0;
+  }
+  const int idx = d->rank[(size_t)smp];  // display-order index of this picture within the clip
   if (d->thumb_out) {
     if (idx >= d->thumb_cap) {
       d->done = true;
@@ -398,7 +407,7 @@ void cb_decoder_destroy(cb_decoder* d) {
   delete d;
 }
 
-static int run_parser(cb_decoder* d, const uint8_t* data, size_t size, const cb::Mp4Track& t, cb_decode_stats* stats, int expect);
+static int run_parser(cb_decoder* d, const uint8_t* data, size_t size, const cb::Mp4Track& t, cb_decode_stats* stats, int expect, int flags);
 
 int cb_decoder_decode_thumbnails(cb_decoder* d, const uint8_t* data, size_t size, int out_w, int out_h, uint8_t* out, int max_frames,
                                  cb_decode_stats* stats) {
@@ -415,13 +424,19 @@ int cb_decoder_decode_thumbnails(cb_decoder* d, const uint8_t* data, size_t size
   d->error.clear();
   d->thumb_out = out, d->thumb_w = out_w, d->thumb_h = out_h, d->thumb_cap = max_frames;
   const int want = std::min<int>(max_frames, (int)t.size.size());
-  const int rc = run_parser(d, data, size, t, stats, want);
+  d->discard = false;
+  const int rc = run_parser(d, data, size, t, stats, want, 0);
   d->thumb_out = nullptr;
   return rc;
 }
 
 int cb_decoder_decode(cb_decoder* d, const uint8_t* data, size_t size, const int32_t* frame_ids, int n_ids, const cb_surface_pool* dst,
                       const int32_t* dst_slots, cb_decode_stats* stats) {
+  return cb_decoder_decode_ex(d, data, size, frame_ids, n_ids, dst, dst_slots, 0, stats);
+}
+
+int cb_decoder_decode_ex(cb_decoder* d, const uint8_t* data, size_t size, const int32_t* frame_ids, int n_ids, const cb_surface_pool* dst,
+                         const int32_t* dst_slots, int flags, cb_decode_stats* stats) {
   if (!d) return CB_ERR_ARG;
   cb_ctx* ctx = d->ctx;
   if (stats) memset(stats, 0, sizeof *stats);
@@ -438,17 +453,18 @@ int cb_decoder_decode(cb_decoder* d, const uint8_t* data, size_t size, const int
   cudaSetDevice(ctx->device);
 
   d->ids = frame_ids, d->slots = dst_slots, d->n_ids = n_ids, d->next_id = 0, d->display_index = 0, d->decoded = 0, d->emitted = 0;
-  d->done = (n_ids == 0);
+  d->discard = (flags & CB_DECODE_DISCARD_ALL) != 0;
+  d->done = (n_ids == 0) && !d->discard;
   d->error.clear();
   if (dst) {
     d->dst_base = (uint8_t*)dst->base, d->dst_slot_stride = dst->slot_stride, d->dst_pitch = dst->pitch, d->dst_luma_rows = dst->luma_rows;
     d->dst_w = dst->width, d->dst_h = dst->height;
   }
 
-  return run_parser(d, data, size, t, stats, n_ids);
+  return run_parser(d, data, size, t, stats, d->discard ? 0 : n_ids, flags);
 }
 
-static int run_parser(cb_decoder* d, const uint8_t* data, size_t size, const cb::Mp4Track& t, cb_decode_stats* stats, int expect) {
+static int run_parser(cb_decoder* d, const uint8_t* data, size_t size, const cb::Mp4Track& t, cb_decode_stats* stats, int expect, int flags) {
   cb_ctx* ctx = d->ctx;
   CUVIDPARSERPARAMS pp;
   memset(&pp, 0, sizeof pp);
@@ -464,28 +480,55 @@ static int run_parser(cb_decoder* d, const uint8_t* data, size_t size, const cb:
 
   bool failed = false;
   const size_t n = t.size.size();
-  for (size_t i = 0; i < n && !d->done && !failed; ++i) {
+  // display-order index of every sample: rank of its composition time (stable for equal times)
+  {
+    std::vector<int32_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (int32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return t.pts[a] < t.pts[b]; });
+    d->rank.assign(n, 0);
+    for (size_t r = 0; r < n; ++r) d->rank[order[r]] = (int32_t)r;
+  }
+  auto feed = [&](size_t i) {
     d->scratch.clear();
     if (i == 0 || t.sync[i]) d->scratch.insert(d->scratch.end(), t.param_sets_annexb.begin(), t.param_sets_annexb.end());
     if (!cb::mp4_sample_annexb(data, size, t, i, &d->scratch)) {
       d->error = "malformed sample " + std::to_string(i);
       failed = true;
-      break;
+      return;
     }
     CUVIDSOURCEDATAPACKET pkt;
     memset(&pkt, 0, sizeof pkt);
     pkt.flags = CUVID_PKT_TIMESTAMP | CUVID_PKT_ENDOFPICTURE;
-    pkt.payload = d->scratch.data(), pkt.payload_size = d->scratch.size(), pkt.timestamp = t.pts[i];
+    pkt.payload = d->scratch.data(), pkt.payload_size = d->scratch.size(), pkt.timestamp = (CUvideotimestamp)i;  // sample index
     rc = d->api->ParseVideoData(parser, &pkt);
     if (rc != 0 || !d->error.empty()) failed = true;
-  }
-  if (!failed && !d->done) {  // flush: frames still queued for display
+  };
+  auto flush = [&]() {  // end-of-stream: every decoded picture is displayed, the parser restarts at the next IDR
     CUVIDSOURCEDATAPACKET pkt;
     memset(&pkt, 0, sizeof pkt);
     pkt.flags = CUVID_PKT_ENDOFSTREAM;
     rc = d->api->ParseVideoData(parser, &pkt);
     if (rc != 0 || !d->error.empty()) failed = true;
+  };
+  size_t pos = 0;
+  const bool seek = (flags & CB_DECODE_SEEK_SYNC) != 0 && !t.has_ctts && !d->thumb_out && !d->discard && d->n_ids > 0;
+  if (seek) {
+    // Without reordering (no ctts) display index == sample index.  Jump to the sync sample in front of every wanted frame that
+    // lies beyond the current position: the GOPs in between hold no wanted frame and are never decoded.
+    for (int k = 0; k < d->n_ids && !failed && !d->done; ++k) {
+      const size_t j = (size_t)d->ids[k];
+      if (j < pos) continue;  // repeated id, already delivered
+      size_t gsync = j;
+      while (gsync > pos && !t.sync[gsync]) --gsync;
+      if (gsync > pos && t.sync[gsync]) {
+        if (pos > 0) flush();
+        pos = gsync;
+      }
+      for (; pos <= j && !failed && !d->done; ++pos) feed(pos);
+    }
   }
+  for (; pos < n && !d->done && !failed; ++pos) feed(pos);
+  if (!failed && !d->done) flush();  // frames still queued for display
   d->api->DestroyVideoParser(parser);
   if (stats) {
     stats->frames_decoded = d->decoded, stats->frames_emitted = d->emitted;

@@ -302,19 +302,30 @@ class Decoder:
         except Exception:  # noqa: BLE001
             pass
 
-    def decode(self, data, frame_ids, pool: Pool, dst_slots) -> dict:
+    def decode(self, data, frame_ids, pool: Pool, dst_slots, seek_keyframes: bool = False) -> dict:
         """Decode `data` (mp4 bytes) and copy display-order frames `frame_ids` (ascending, repeats allowed)
-        into `pool` slots `dst_slots`.  Raises CurateB200Error on demux / decode failure."""
+        into `pool` slots `dst_slots`.  `seek_keyframes` skips GOPs that hold no wanted frame (identical output).
+        Raises CurateB200Error on demux / decode failure."""
         buf = _as_u8(data)
         ids = np.ascontiguousarray(frame_ids, dtype=np.int32)
         slots = np.ascontiguousarray(dst_slots, dtype=np.int32)
         assert len(ids) == len(slots)
         st = _lib.DecodeStats()
-        check(self.lib.cb_decoder_decode(self.h, buf.ctypes.data, buf.size, ids.ctypes.data_as(C.POINTER(C.c_int32)), len(ids),
-                                         C.byref(pool.desc), slots.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st)),
+        flags = _lib.DECODE_SEEK_SYNC if seek_keyframes else 0
+        check(self.lib.cb_decoder_decode_ex(self.h, buf.ctypes.data, buf.size, ids.ctypes.data_as(C.POINTER(C.c_int32)), len(ids),
+                                            C.byref(pool.desc), slots.ctypes.data_as(C.POINTER(C.c_int32)), flags, C.byref(st)),
               "cb_decoder_decode", self.ctx.h)  # fmt: skip
         return {"frames_decoded": st.frames_decoded, "frames_emitted": st.frames_emitted, "coded": (st.coded_width, st.coded_height),
                 "size": (st.width, st.height)}  # fmt: skip
+
+
+def decode_discard(dec: Decoder, data) -> int:
+    """Decode every picture of the clip and deliver none; returns the number decoded (NVDEC ceiling measurement)."""
+    buf = _as_u8(data)
+    st = _lib.DecodeStats()
+    check(dec.lib.cb_decoder_decode_ex(dec.h, buf.ctypes.data, buf.size, None, 0, None, None, _lib.DECODE_DISCARD_ALL, C.byref(st)),
+          "cb_decoder_decode_ex", dec.ctx.h)
+    return st.frames_decoded
 
 
 def decode_thumbnails(dec: Decoder, data, out_w: int, out_h: int, n_frames: int) -> torch.Tensor:

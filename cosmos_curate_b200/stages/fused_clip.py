@@ -46,6 +46,7 @@ class NvdecClipAestheticStage(CuratorStage):
         max_batch: int = 256,
         num_decoders: int = 8,
         stage_batch_size: int = 8,
+        seek_keyframes: bool = True,
         verbose: bool = False,
         log_stats: bool = False,
         model: CLIPAestheticScorer | None = None,
@@ -55,6 +56,7 @@ class NvdecClipAestheticStage(CuratorStage):
         self._num_gpus_per_worker = num_gpus_per_worker
         self._write_embedding, self._max_batch, self._num_decoders = write_embedding, max_batch, num_decoders
         self._stage_batch_size, self._verbose, self._log_stats = stage_batch_size, verbose, log_stats
+        self._seek = seek_keyframes  # decode only the GOPs that contain sampled frames (identical frames, fewer decoded)
         self._model = model if model is not None else CLIPAestheticScorer(max_batch=max_batch)
         self._reduce_fn = np.min
         self._pools: dict[tuple[int, int], object] = {}
@@ -125,7 +127,7 @@ class NvdecClipAestheticStage(CuratorStage):
         def work(arg):
             j, (clip, data, ids, first) = arg
             try:
-                self._decoders[j % self._num_decoders].decode(data, ids, pool, np.arange(first, first + len(ids), dtype=np.int32))
+                self._decoders[j % self._num_decoders].decode(data, ids, pool, np.arange(first, first + len(ids), dtype=np.int32), seek_keyframes=self._seek)
                 return None
             except CurateB200Error as e:
                 return e

@@ -179,6 +179,15 @@ void cb_decoder_destroy(cb_decoder* dec);
 int cb_decoder_decode(cb_decoder* dec, const uint8_t* data, size_t size, const int32_t* frame_ids, int n_ids,
                       const cb_surface_pool* dst, const int32_t* dst_slots, cb_decode_stats* stats);
 
+#define CB_DECODE_SEEK_SYNC 1   /* skip GOPs without a wanted frame: restart at the sync sample (stss) in front of each one */
+#define CB_DECODE_DISCARD_ALL 2 /* decode every picture, deliver none (NVDEC ceiling measurement; frame_ids ignored) */
+/* cb_decoder_decode with flags.  CB_DECODE_SEEK_SYNC delivers bit-identical frames while decoding only the closed GOPs
+ * that contain sampled frames (streams with composition offsets fall back to sequential decode).  The reference decodes
+ * every frame up to the last sampled one (decoder_utils.py:439-455); its sensor library plans sparse seeks the same way
+ * (core/sensors/utils/video.py) but the clip path never got them. */
+int cb_decoder_decode_ex(cb_decoder* dec, const uint8_t* data, size_t size, const int32_t* frame_ids, int n_ids,
+                         const cb_surface_pool* dst, const int32_t* dst_slots, int flags, cb_decode_stats* stats);
+
 /* Decode EVERY frame of the clip (up to max_frames) and write each as an out_w x out_h RGB u8 thumbnail into device
  * memory out[n][out_h][out_w][3]: NV12->RGB + bilinear run directly on the mapped NVDEC surface.  Replaces
  * PyNvcFrameExtractor.__call__ (nvcodec_utils.py:349-381: decode, per-frame reformat, full-resolution colour

@@ -107,3 +107,49 @@ class CpuReferencePath:
         t2 = time.perf_counter()
         return {"seconds": t2 - t0, "decode_s": t1 - t0, "preprocess_s": t_pre, "model_s": t_model, "clips": len(clips), "frames": n_frames,
                 "embeddings": embs, "scores": scores}  # fmt: skip
+
+
+# ---- several reference actors side by side (one process each, like the reference's per-stage Ray actors) ------------
+_W = {}
+
+
+def _worker_init(cfg_dict: dict, seed: int, threads: int) -> None:
+    torch.set_num_threads(threads)
+    cfg = vit.VitConfig(**cfg_dict)
+    _W["path"] = CpuReferencePath(cfg, vit.random_weights(cfg, seed=seed), vit.random_aesthetic_mlp(seed=seed, in_dim=cfg.proj_dim or cfg.hidden),
+                                  threads=threads)  # fmt: skip
+
+
+def _worker_run(args):
+    clip, fps = args
+    r = _W["path"].run([clip], fps, decode_workers=1)
+    return {k: r[k] for k in ("seconds", "decode_s", "preprocess_s", "model_s", "clips", "frames")}
+
+
+class CpuReferencePool:
+    """`procs` worker processes x `threads` torch threads; each worker runs whole clips through CpuReferencePath."""
+
+    def __init__(self, cfg: vit.VitConfig, seed: int, procs: int, threads: int):
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+
+        self.procs, self.threads = procs, threads
+        self.ex = ProcessPoolExecutor(max_workers=procs, mp_context=mp.get_context("spawn"), initializer=_worker_init, initargs=(cfg.to_dict(), seed, threads))
+        list(self.ex.map(_noop, range(procs * 2)))  # start the workers (imports + weights) before anything is timed
+
+    def run(self, clips: list[bytes], fps: float = 1.0) -> dict:
+        t0 = time.perf_counter()
+        parts = list(self.ex.map(_worker_run, [(c, fps) for c in clips]))
+        sec = time.perf_counter() - t0
+        out = {"seconds": sec, "clips": len(clips), "frames": sum(p["frames"] for p in parts)}
+        for k in ("decode_s", "preprocess_s", "model_s"):
+            out[k] = sum(p[k] for p in parts)  # summed over workers (CPU-seconds of wall inside workers)
+        return out
+
+    def close(self):
+        self.ex.shutdown(wait=True, cancel_futures=True)
+
+
+def _noop(i):
+    time.sleep(0.05)
+    return i

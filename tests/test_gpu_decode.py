@@ -114,3 +114,37 @@ def test_decode_to_embedding_end_to_end(ctx):
     ref = vit.forward(cfg, w, preprocess.clip_preprocess(rgb))["embedding"]
     rel = np.linalg.norm(emb.cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1)
     assert rel.max() < 2e-3
+
+
+def test_keyframe_seek_is_bit_identical_and_lossless_vs_source(ctx):
+    """Multi-GOP synthetic clip: CB_DECODE_SEEK_SYNC decodes fewer pictures but delivers the same surfaces; the IDR
+    pictures are I_PCM, so NVDEC output must equal the encoder's source samples exactly."""
+    from cosmos_curate_b200.runtime import Decoder, alloc_nv12_pool, decode_discard, mp4_index
+    from tools import synth_h264
+
+    w, h, fps = 640, 368, 30
+    mp4, src = synth_h264.make_clip(w, h, fps, 4.0, seed=11, gop=30, pan=(2, 1), return_sources=True)
+    data = np.frombuffer(mp4, dtype=np.uint8)
+    idx = mp4_index(data, ctx)
+    assert idx["n_samples"] == 120 and idx["n_sync"] == 4 and (idx["width"], idx["height"]) == (w, h)
+    ids = np.array([0, 30, 60, 75, 75, 90, 119], dtype=np.int32)  # IDRs, a mid-GOP frame twice, the last frame
+    dec = Decoder(ctx)
+    full, sparse = alloc_nv12_pool(ctx, len(ids), w, h), alloc_nv12_pool(ctx, len(ids), w, h)
+    sparse.buf.fill_(7)
+    st_full = dec.decode(data, ids, full, np.arange(len(ids)))
+    st_seek = dec.decode(data, ids, sparse, np.arange(len(ids)), seek_keyframes=True)
+    assert st_full["frames_decoded"] == 120
+    assert st_seek["frames_decoded"] == 1 + 1 + 16 + 30  # GOP0: 1, GOP1: 1, GOP2: frames 60..75, GOP3: 90..119
+    a, b = full.buf.cpu().numpy(), sparse.buf.cpu().numpy()
+    np.testing.assert_array_equal(a[:, : h + h // 2, :w], b[:, : h + h // 2, :w])
+    for k, i in enumerate(ids):
+        if int(i) in src:  # IDR pictures: lossless
+            y, u, v = src[int(i)]
+            np.testing.assert_array_equal(a[k, :h, :w], y)
+            np.testing.assert_array_equal(a[k, h : h + h // 2, 0:w:2], u)
+            np.testing.assert_array_equal(a[k, h : h + h // 2, 1:w:2], v)
+    # frame 75 = frame 60 panned by 15 * (2, 1) pixels (interior)
+    k60, k75 = 2, 3
+    np.testing.assert_array_equal(a[k75, 40 : h - 40, 40 : w - 80], a[k60, 40 + 15 : h - 40 + 15, 40 + 30 : w - 80 + 30])
+    assert decode_discard(dec, data) == 120
+    dec.close()

@@ -47,7 +47,7 @@ class VitCfg(C.Structure):
 class Mp4Info(C.Structure):
     _fields_ = [
         ("codec", C.c_int), ("width", C.c_int), ("height", C.c_int), ("timescale", C.c_uint32),
-        ("n_samples", C.c_int), ("n_sync", C.c_int), ("has_ctts", C.c_int), ("duration", C.c_uint64),
+        ("n_samples", C.c_int), ("n_sync", C.c_int), ("has_ctts", C.c_int), ("duration", C.c_uint64), ("sample_bytes", C.c_uint64),
     ]  # fmt: skip
 
 

@@ -372,6 +372,8 @@ int cb_mp4_index(cb_ctx* ctx, const uint8_t* data, size_t size, cb_mp4_info* inf
   info->n_samples = (int)t.size.size(), info->has_ctts = t.has_ctts ? 1 : 0, info->duration = t.duration;
   int nsync = 0;
   for (uint8_t s : t.sync) nsync += s;
+  info->sample_bytes = 0;
+  for (uint32_t b : t.size) info->sample_bytes += b;
   info->n_sync = nsync;
   const int n = std::min<int>(cap, info->n_samples);
   for (int i = 0; i < n; ++i) {

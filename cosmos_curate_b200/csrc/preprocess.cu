@@ -316,26 +316,34 @@ __global__ void __launch_bounds__(kThreads, 2) clip_preprocess_v2_kernel(const _
     const uint8_t* rs = raw + (s & 1) * raw_stage;
     mbar_wait(&bars[s & 1], (s >> 1) & 1);
 
-    // ---- phase 1: colour conversion (one thread per horizontal pixel pair sharing a chroma sample)
+    // ---- phase 1: colour conversion; one thread owns a 2-row x 4-pixel block (two chroma samples, three 32-bit loads)
     if (FMT == CB_FMT_NV12) {
-      const int half_w = a.swa >> 1;
+      const int q4 = a.swa >> 2;
       const uint8_t* ry = rs;
       const uint8_t* ruv = rs + a.swa * kSR;
       constexpr int kMax = (256 << 20) - 1;
-      for (int i = tid; i < kSR * half_w; i += kThreads) {
-        const int r = i / half_w, x = (i - r * half_w) * 2;
-        const uchar2 yy = *(const uchar2*)(ry + r * a.swa + x);
-        const uchar2 uv = *(const uchar2*)(ruv + (r >> 1) * a.swa + x);
-        const int u = (int)uv.x - 128, v = (int)uv.y - 128;
-        const int ruv_ = 1673527 * v, guv_ = -852492 * v - 409993 * u, buv_ = 2116026 * u;
-        const int y0v = max((int)yy.x - 16, 0) * 1220542 + (1 << 19), y1v = max((int)yy.y - 16, 0) * 1220542 + (1 << 19);
+      for (int i = tid; i < (kSR / 2) * q4; i += kThreads) {
+        const int rp = i / q4, x = (i - rp * q4) * 4, r = rp * 2;
+        const uint32_t ya = *(const uint32_t*)(ry + r * a.swa + x), yb = *(const uint32_t*)(ry + (r + 1) * a.swa + x);
+        const uint32_t uv4 = *(const uint32_t*)(ruv + rp * a.swa + x);
         float* p = rgbf + r * swp + x;
-        p[0] = (float)(__viaddmin_s32_relu(y0v, ruv_, kMax) >> 20);
-        p[1] = (float)(__viaddmin_s32_relu(y1v, ruv_, kMax) >> 20);
-        p[kSR * swp] = (float)(__viaddmin_s32_relu(y0v, guv_, kMax) >> 20);
-        p[kSR * swp + 1] = (float)(__viaddmin_s32_relu(y1v, guv_, kMax) >> 20);
-        p[2 * kSR * swp] = (float)(__viaddmin_s32_relu(y0v, buv_, kMax) >> 20);
-        p[2 * kSR * swp + 1] = (float)(__viaddmin_s32_relu(y1v, buv_, kMax) >> 20);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // the two chroma samples of the block
+          const int u = (int)((uv4 >> (16 * h)) & 0xff) - 128, v = (int)((uv4 >> (16 * h + 8)) & 0xff) - 128;
+          const int ruv_ = 1673527 * v, guv_ = -852492 * v - 409993 * u, buv_ = 2116026 * u;
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const uint32_t yw = rr ? yb : ya;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int yv = max((int)((yw >> (16 * h + 8 * k)) & 0xff) - 16, 0) * 1220542 + (1 << 19);
+              float* q = p + rr * swp + 2 * h + k;
+              q[0] = (float)(__viaddmin_s32_relu(yv, ruv_, kMax) >> 20);
+              q[kSR * swp] = (float)(__viaddmin_s32_relu(yv, guv_, kMax) >> 20);
+              q[2 * kSR * swp] = (float)(__viaddmin_s32_relu(yv, buv_, kMax) >> 20);
+            }
+          }
+        }
       }
     } else {
       for (int i = tid; i < kSR * a.swa; i += kThreads) {
@@ -386,29 +394,39 @@ __global__ void __launch_bounds__(kThreads, 2) clip_preprocess_v2_kernel(const _
     int seg = next_out;
     while (seg < last) {
       const int seg_end = (a.out_mode == 2) ? min(last, (seg / a.patch + 1) * a.patch) : last;
-      const int per_row = ncol * 3;
-      for (int item = tid; item < (seg_end - seg) * per_row; item += kThreads) {
-        const int yo = seg + item / per_row, rem = item % per_row;
-        const int ch = rem / ncol, c = rem - ch * ncol;
+      for (int yo = seg + warp; yo < seg_end; yo += kThreads / 32) {  // one warp per output row, lane = column
         const int ym = a.ymin[yo], ys = a.ysize[yo];
-        const float* w = a.wy + (size_t)yo * a.ty;
-        const float* rb = ringb + (size_t)ch * a.ring * tcp + c;
-        float acc = rb[(ym & (a.ring - 1)) * tcp] * __ldg(w);
-        for (int k = 1; k < ys; ++k) acc = fmaf(rb[((ym + k) & (a.ring - 1)) * tcp], __ldg(w + k), acc);
-        acc = fminf(fmaxf(acc, 0.f), 255.f);
-        const int v = __float2int_rn(acc);
-        const int x = c0 + c;
-        if (a.out_mode == 0) {
-          ((uint8_t*)a.out)[(((size_t)frame * 3 + ch) * a.res + yo) * a.res + x] = (uint8_t)v;
-        } else {
-          const float f = a.lut[ch * 256 + v];
-          if (a.out_mode == 1) {
-            store_typed(a.out, (((size_t)frame * 3 + ch) * a.res + yo) * a.res + x, f, a.dtype);
-          } else {
-            const int ip = c / a.patch, px_ = c - ip * a.patch, py = yo % a.patch;
-            const uint16_t bits = (a.dtype == CB_DT_F16) ? __half_as_ushort(__float2half_rn(f))
-                                                         : __bfloat16_as_ushort(__float2bfloat16_rn(f));
-            obuf[ip * a.k_pad + (ch * a.patch + py) * a.patch + px_] = bits;
+        const float* wrow = a.wy + (size_t)yo * a.ty;
+        const float w_lo = lane < ys ? __ldg(wrow + lane) : 0.f, w_hi = lane + 32 < ys ? __ldg(wrow + lane + 32) : 0.f;
+        const int c = min(lane, ncol - 1);
+        const float* rb = ringb + c;
+        const int chs = a.ring * tcp;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+        for (int k = 0; k < ys; ++k) {
+          const float w = __shfl_sync(0xffffffffu, k < 32 ? w_lo : w_hi, k & 31);
+          const float* rr = rb + ((ym + k) & (a.ring - 1)) * tcp;
+          acc0 = fmaf(rr[0], w, acc0), acc1 = fmaf(rr[chs], w, acc1), acc2 = fmaf(rr[2 * chs], w, acc2);
+        }
+        if (lane < ncol) {
+          const int x = c0 + c;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            float acc = ch == 0 ? acc0 : (ch == 1 ? acc1 : acc2);
+            acc = fminf(fmaxf(acc, 0.f), 255.f);
+            const int v = __float2int_rn(acc);
+            if (a.out_mode == 0) {
+              ((uint8_t*)a.out)[(((size_t)frame * 3 + ch) * a.res + yo) * a.res + x] = (uint8_t)v;
+            } else {
+              const float f = a.lut[ch * 256 + v];
+              if (a.out_mode == 1) {
+                store_typed(a.out, (((size_t)frame * 3 + ch) * a.res + yo) * a.res + x, f, a.dtype);
+              } else {
+                const int ip = c / a.patch, px_ = c - ip * a.patch, py = yo % a.patch;
+                const uint16_t bits = (a.dtype == CB_DT_F16) ? __half_as_ushort(__float2half_rn(f))
+                                                             : __bfloat16_as_ushort(__float2bfloat16_rn(f));
+                obuf[ip * a.k_pad + (ch * a.patch + py) * a.patch + px_] = bits;
+              }
+            }
           }
         }
       }
@@ -659,6 +677,7 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
     gu = std::max(gu, hi);
   }
   a.gu = gu;
+  if (ty->max_taps > 64 || tx->max_taps > 64) return fail(ctx, CB_ERR_UNSUPPORTED, "downscale factor too large (%d vertical taps)", ty->max_taps);
   const char* kver = getenv("CB_PRE_KERNEL");
   const bool use_v2 = !(kver && kver[0] == '1');
   if (a.swa > 256) return fail(ctx, CB_ERR_UNSUPPORTED, "downscale too large for one TMA box (%d source columns per tile)", a.swa);

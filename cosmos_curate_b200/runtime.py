@@ -278,7 +278,8 @@ def mp4_index(data, ctx: Context | None = None) -> dict:
     check(lib.cb_mp4_index(h, buf.ctypes.data, buf.size, C.byref(info), pts.ctypes.data_as(C.POINTER(C.c_int64)),
                            sync.ctypes.data_as(C.POINTER(C.c_uint8)), n), "cb_mp4_index", h)  # fmt: skip
     return {"codec": info.codec, "width": info.width, "height": info.height, "timescale": info.timescale, "n_samples": n,
-            "n_sync": info.n_sync, "has_ctts": bool(info.has_ctts), "duration": info.duration, "pts": pts, "sync": sync}  # fmt: skip
+            "n_sync": info.n_sync, "has_ctts": bool(info.has_ctts), "duration": info.duration, "sample_bytes": info.sample_bytes,
+            "pts": pts, "sync": sync}  # fmt: skip
 
 
 class Decoder:

@@ -120,3 +120,43 @@ def plan_extraction(all_ts: np.ndarray, policies, target_fps: list):
                 ids, counts = frame_ids(all_ts, policy, f)
                 plan[FrameExtractionSignature(policy, f).to_str()] = np.repeat(ids, counts)
     return plan
+
+
+@attrs.define
+class VideoMetadata:
+    """Same fields as the reference's VideoMetadata (decoder_utils.py:57-84)."""
+
+    height: int
+    width: int
+    fps: float
+    num_frames: int
+    video_codec: str
+    pixel_format: str
+    video_duration: float
+    bit_rate_k: int
+    format_name: str = "unknown"
+    audio_codec: str | None = None
+
+    @property
+    def length_s(self) -> float:
+        return self.video_duration
+
+
+def video_metadata_from_index(idx: dict) -> VideoMetadata:
+    """extract_video_metadata (decoder_utils.py:120-197) without the ffprobe subprocess + temp file: the same
+    quantities ffprobe prints for an MP4 video stream, derived from the moov index (cb_mp4_index).
+        avg_frame_rate = nb_frames / stream duration, fps = num / den; num_frames = int(duration * fps);
+        bit_rate_k = int(bit_rate / 1024) with bit_rate = 8 * sample bytes / duration."""
+    ts, dur, n = int(idx["timescale"]), int(idx["duration"]), int(idx["n_samples"])
+    if dur <= 0 or ts <= 0:
+        msg = "Could not find `duration` in video metadata."
+        raise KeyError(msg)
+    rate = Fraction(n * ts, dur).limit_denominator(60000)
+    fps = rate.numerator / rate.denominator
+    duration_s = float(f"{dur / ts:.6f}")  # ffprobe prints seconds with 6 decimals
+    bit_rate = int(8 * int(idx["sample_bytes"]) / (dur / ts))
+    return VideoMetadata(
+        height=int(idx["height"]), width=int(idx["width"]), fps=fps, num_frames=int(duration_s * fps),
+        video_codec={4: "h264", 8: "hevc"}.get(int(idx["codec"]), "unknown"), pixel_format="yuv420p", video_duration=duration_s,
+        bit_rate_k=int(bit_rate / 1024), format_name="mov,mp4,m4a,3gp,3g2,mj2",
+    )  # fmt: skip

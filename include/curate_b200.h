@@ -153,7 +153,8 @@ typedef struct cb_mp4_info {
   int width, height;  /* sample-entry (display) size */
   uint32_t timescale; /* mdhd timescale: PTS seconds = pts / timescale */
   int n_samples, n_sync, has_ctts;
-  uint64_t duration;
+  uint64_t duration;     /* mdhd duration in `timescale` ticks */
+  uint64_t sample_bytes; /* sum of the video sample sizes (stream bit rate = 8 * sample_bytes / seconds) */
 } cb_mp4_info;
 
 typedef struct cb_decode_stats {

@@ -127,6 +127,22 @@ def test_mp4_index_of_reference_fixture():
     assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == idx["n_samples"]
 
 
+def test_video_metadata_from_index_matches_container_facts():
+    from cosmos_curate_b200 import sampling
+    from cosmos_curate_b200.runtime import mp4_index
+    from tools import synth_h264
+
+    m = sampling.video_metadata_from_index(mp4_index(np.fromfile(GOLDEN / "sintel_clip_10s.mp4", dtype=np.uint8)))
+    assert (m.width, m.height, m.fps, m.num_frames, m.video_codec, m.pixel_format, m.video_duration) == (854, 480, 24.0, 240, "h264", "yuv420p", 10.0)
+    assert 1300 < m.bit_rate_k < 1500  # 1.76 MB over 10 s
+    clip = synth_h264.make_clip(320, 192, 30, 1.0, seed=1)
+    m = sampling.video_metadata_from_index(mp4_index(np.frombuffer(clip, dtype=np.uint8)))
+    assert (m.width, m.height, m.fps, m.num_frames) == (320, 192, 30.0, 30)  # reference KATs: avg rate 30.0 (test_decoder_utils.py:358-385)
+    cv2 = pytest.importorskip("cv2")
+    cap = cv2.VideoCapture(str(GOLDEN / "sintel_clip_10s.mp4"))
+    assert cap.get(cv2.CAP_PROP_FPS) == 24.0 and int(cap.get(cv2.CAP_PROP_FRAME_WIDTH)) == 854
+
+
 def test_mp4_index_rejects_garbage():
     from cosmos_curate_b200._lib import CurateB200Error
     from cosmos_curate_b200.runtime import mp4_index

@@ -234,23 +234,30 @@ constexpr int kGemm2Threads = 384;
 constexpr int BN2 = 256;
 
 struct Gemm2Cfg {
-  static constexpr int kStages = 6;
+  static constexpr int kStages = 5;
   static constexpr int kABytes = BM * BK * 2, kBBytes = (BN2 / 2) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;  // per CTA
-  static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kEpiBytes = 8 * 4096;             // one 32x32 fp32 staging tile per epilogue warp (TMA store / reduce-add)
+  static constexpr int kSmem = kStages * kStageBytes + kEpiBytes + 1024 + 256;
   static constexpr int kTmemCols = 2 * BN2;
 };
 
-template <int ACT, bool OUT_F32>
+// EPI_TMA (fp32 output only): the epilogue stages each 32x32 chunk in shared memory (128-byte swizzle) and hands it to the
+// TMA: plain store, or - for the residual stream, out == residual - cp.reduce.async.bulk.tensor .add, i.e. h += tile is
+// performed at L2.  The SMs never read the residual and every global access is a full 128-byte line; the row-per-thread
+// ld/st path it replaces touched 32 lines per instruction and held the K=1024 out-projection at 26 % tensor-pipe activity.
+template <int ACT, bool OUT_F32, bool EPI_TMA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
-    gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+    gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                             const __grid_constant__ CUtensorMap map_c, const GemmArgs g) {
   using Cfg = Gemm2Cfg;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* sEpi = smem + Cfg::kStages * Cfg::kStageBytes;  // 1024-byte aligned: stage sizes are multiples of 1024
+  uint64_t* bars = (uint64_t*)(sEpi + Cfg::kEpiBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
   uint64_t* tfull = bars + 2 * Cfg::kStages;
@@ -330,19 +337,70 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
     }
   } else if (warp >= 4) {  // ===== epilogue: lane quarter q, column half `half`
     const int q = warp & 3, half = (warp - 4) >> 2;
+    uint8_t* stage_buf = sEpi + (warp - 4) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int m_blk = t / n_tiles, n_blk = t - m_blk * n_tiles;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
+      const int row_base = m_blk * 2 * BM + (int)rank * BM + q * 32;
+      const int row = row_base + lane;
       const bool row_ok = row < g.M;
 #pragma unroll 1
       for (int cc = half * (BN2 / 64); cc < (half + 1) * (BN2 / 64); ++cc) {
         const int col0 = n_blk * BN2 + cc * 32;
         if (col0 >= g.N) break;  // warp-uniform
-        epilogue_chunk<ACT, OUT_F32>(g, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2 + cc * 32), row, row_ok, col0);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2 + cc * 32);
+        if (EPI_TMA) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (g.bias) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              if (col0 + j4 * 4 < g.N) {
+                const float4 b = __ldg((const float4*)(g.bias + col0) + j4);
+                v[j4 * 4 + 0] += b.x, v[j4 * 4 + 1] += b.y, v[j4 * 4 + 2] += b.z, v[j4 * 4 + 3] += b.w;
+              }
+            }
+          }
+          if (ACT == CB_EPI_QUICK_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_quick_gelu(v[j]);
+          } else if (ACT == CB_EPI_GELU_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_gelu_tanh(v[j]);
+          }
+          if (lane == 0) bulk_wait_read0();  // the previous chunk's TMA has finished reading the staging tile
+          __syncwarp();
+          if (OUT_F32) {  // 32 rows x 128 B, 128-byte swizzle: conflict-free STS.128
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              *(float4*)(stage_buf + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          } else {  // 32 rows x 64 B fp16, 64-byte swizzle
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const __half2 h0 = __floats2half2_rn(v[j8 * 8 + 0], v[j8 * 8 + 1]), h1 = __floats2half2_rn(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+              const __half2 h2 = __floats2half2_rn(v[j8 * 8 + 4], v[j8 * 8 + 5]), h3 = __floats2half2_rn(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+              uint4 o;
+              o.x = *(const uint32_t*)&h0, o.y = *(const uint32_t*)&h1, o.z = *(const uint32_t*)&h2, o.w = *(const uint32_t*)&h3;
+              *(uint4*)(stage_buf + lane * 64 + ((j8 ^ ((lane >> 1) & 3)) << 4)) = o;
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (OUT_F32 && g.residual) tma_reduce_add_2d(&map_c, stage_buf, col0, row_base);
+            else tma_store_2d(&map_c, stage_buf, col0, row_base);
+            bulk_commit();
+          }
+        } else {
+          epilogue_chunk<ACT, OUT_F32>(g, taddr, row, row_ok, col0);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -351,6 +409,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
     }
   }
 
+  if (EPI_TMA && warp >= 4 && lane == 0) bulk_wait0();  // outstanding TMA stores / reductions of this warp are complete
   tc_fence_before();
   cluster_sync_all();  // the peer's MMAs / epilogue reads of our shared memory and TMEM are complete
   if (warp == 2) {
@@ -359,9 +418,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
   }
 }
 
-template <int ACT, bool OUT_F32>
-static int launch_gemm_2cta(cb_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t stream) {
-  auto kern = gemm_tcgen05_2cta_kernel<ACT, OUT_F32>;
+template <int ACT, bool OUT_F32, bool EPI_TMA>
+static int launch_gemm_2cta(cb_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmArgs& g,
+                            cudaStream_t stream) {
+  auto kern = gemm_tcgen05_2cta_kernel<ACT, OUT_F32, EPI_TMA>;
   static bool attr_set = false;
   if (!attr_set) {
     CB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::kSmem));
@@ -370,7 +430,7 @@ static int launch_gemm_2cta(cb_ctx* ctx, const CUtensorMap& ma, const CUtensorMa
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * ((g.N + BN2 - 1) / BN2);
   const int pairs = std::min(tiles, ctx->sm_count / 2);
   mark_launch(ctx, CB_PROF_GEMM, stream);
-  kern<<<2 * pairs, kGemm2Threads, Gemm2Cfg::kSmem, stream>>>(ma, mb, g);
+  kern<<<2 * pairs, kGemm2Threads, Gemm2Cfg::kSmem, stream>>>(ma, mb, mc, g);
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }
@@ -418,10 +478,31 @@ int gemm_f16(cb_ctx* ctx, const void* A, const void* W, const float* bias, const
     rc2 = make_tensor_map(ctx, &mb2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, W, db2, st2, bb2, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc2) return rc2;
     GemmArgs g2{bias, residual, out_f32, (__half*)out_f16, M, N, K};
-    if (out_f32) return launch_gemm_2cta<CB_EPI_NONE, true>(ctx, ma2, mb2, g2, stream);
-    if (epilogue == CB_EPI_QUICK_GELU) return launch_gemm_2cta<CB_EPI_QUICK_GELU, false>(ctx, ma2, mb2, g2, stream);
-    if (epilogue == CB_EPI_GELU_TANH) return launch_gemm_2cta<CB_EPI_GELU_TANH, false>(ctx, ma2, mb2, g2, stream);
-    if (epilogue == CB_EPI_NONE) return launch_gemm_2cta<CB_EPI_NONE, false>(ctx, ma2, mb2, g2, stream);
+    const char* epi = getenv("CB_GEMM_EPILOGUE");  // "direct": A/B switch for the TMA epilogue
+    const bool tma_ok = !(epi && epi[0] == 'd');
+    if (tma_ok && out_f32 && (residual == nullptr || residual == out_f32) && !((uintptr_t)out_f32 & 15)) {
+      CUtensorMap mc2;
+      uint64_t dc2[2] = {(uint64_t)N, (uint64_t)M}, sc2[1] = {(uint64_t)N * 4};
+      uint32_t bc2[2] = {32, 32};
+      rc2 = make_tensor_map(ctx, &mc2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out_f32, dc2, sc2, bc2, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc2) return rc2;
+      return launch_gemm_2cta<CB_EPI_NONE, true, true>(ctx, ma2, mb2, mc2, g2, stream);
+    }
+    if (tma_ok && !out_f32 && !((uintptr_t)out_f16 & 15)) {
+      CUtensorMap mc2;
+      uint64_t dc2[2] = {(uint64_t)N, (uint64_t)M}, sc2[1] = {(uint64_t)N * 2};
+      uint32_t bc2[2] = {32, 32};
+      rc2 = make_tensor_map(ctx, &mc2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out_f16, dc2, sc2, bc2, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc2) return rc2;
+      if (epilogue == CB_EPI_QUICK_GELU) return launch_gemm_2cta<CB_EPI_QUICK_GELU, false, true>(ctx, ma2, mb2, mc2, g2, stream);
+      if (epilogue == CB_EPI_GELU_TANH) return launch_gemm_2cta<CB_EPI_GELU_TANH, false, true>(ctx, ma2, mb2, mc2, g2, stream);
+      if (epilogue == CB_EPI_NONE) return launch_gemm_2cta<CB_EPI_NONE, false, true>(ctx, ma2, mb2, mc2, g2, stream);
+      return fail(ctx, CB_ERR_ARG, "gemm: unknown epilogue %d", epilogue);
+    }
+    if (out_f32) return launch_gemm_2cta<CB_EPI_NONE, true, false>(ctx, ma2, mb2, ma2, g2, stream);
+    if (epilogue == CB_EPI_QUICK_GELU) return launch_gemm_2cta<CB_EPI_QUICK_GELU, false, false>(ctx, ma2, mb2, ma2, g2, stream);
+    if (epilogue == CB_EPI_GELU_TANH) return launch_gemm_2cta<CB_EPI_GELU_TANH, false, false>(ctx, ma2, mb2, ma2, g2, stream);
+    if (epilogue == CB_EPI_NONE) return launch_gemm_2cta<CB_EPI_NONE, false, false>(ctx, ma2, mb2, ma2, g2, stream);
     return fail(ctx, CB_ERR_ARG, "gemm: unknown epilogue %d", epilogue);
   }
   CUtensorMap ma, mb;

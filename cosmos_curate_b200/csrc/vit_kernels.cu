@@ -7,6 +7,8 @@
 //   clip_tail_kernel       post_layernorm(CLS) -> visual_projection -> L2 normalise -> aesthetic affine head
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -197,54 +199,62 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
       first = false;
     }
 
-    // S = Q K^T for `nkt` 8-key tiles starting at key kc (nkt is 4, or 2 in the tail of a 16-multiple length)
-    auto qk_chunk = [&](int kc, int nkt, float (&sc)[4][4]) {
+    // per-lane shared-memory offsets of the ldmatrix rows (bytes)
+    const uint32_t k_lane = smem_u32(sK) + (uint32_t)(((lane & 7) * PITCH + (lane >> 3) * 8) * 2);
+    const uint32_t k_lane_tail = smem_u32(sK) + (uint32_t)(((lane & 7) * PITCH + (HD - 16) + ((lane >> 3) & 1) * 8) * 2);
+    const uint32_t v_lane = smem_u32(sV) + (uint32_t)(((((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + (lane >> 4) * 8) * 2);
+
+    // S = Q K^T for NKT 8-key tiles starting at key kc.  NKT is a compile-time constant (4, or 2 for the 16-key tail of a
+    // 16-multiple length) so every ldmatrix / mma is unconditional: no convergence barriers around the .sync instructions.
+    auto qk_chunk = [&](int kc, auto nkt_c, float (&sc)[4][4]) {
+      constexpr int NKT = decltype(nkt_c)::value;
 #pragma unroll
       for (int i = 0; i < 4; ++i) sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
+      const uint32_t kbase = k_lane + (uint32_t)(kc * PITCH * 2);
 #pragma unroll
       for (int kp = 0; kp < HD / 32; ++kp) {  // two k-steps per ldmatrix.x4
-        uint32_t kb[4][4];
+        uint32_t kb[NKT][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < nkt) ldmatrix_x4(kb[i], smem_u32(sK + (size_t)(kc + i * 8 + (lane & 7)) * PITCH + kp * 32 + (lane >> 3) * 8));
+        for (int i = 0; i < NKT; ++i) ldmatrix_x4(kb[i], kbase + (uint32_t)((i * 8 * PITCH + kp * 32) * 2));
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < nkt) mma_16816(sc[i], qa[2 * kp], kb[i][0], kb[i][1]);
+        for (int i = 0; i < NKT; ++i) mma_16816(sc[i], qa[2 * kp], kb[i][0], kb[i][1]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < nkt) mma_16816(sc[i], qa[2 * kp + 1], kb[i][2], kb[i][3]);
+        for (int i = 0; i < NKT; ++i) mma_16816(sc[i], qa[2 * kp + 1], kb[i][2], kb[i][3]);
       }
       if (HD % 32) {  // odd number of k-steps (HD = 80): last 16 columns
-        uint32_t kb[4][4];
+        uint32_t kb[NKT][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < nkt) ldmatrix_x4(kb[i], smem_u32(sK + (size_t)(kc + i * 8 + (lane & 7)) * PITCH + (HD - 16) + ((lane >> 3) & 1) * 8));
+        for (int i = 0; i < NKT; ++i) ldmatrix_x4(kb[i], k_lane_tail + (uint32_t)((kc + i * 8) * PITCH * 2));
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i < nkt) mma_16816(sc[i], qa[KS - 1], kb[i][0], kb[i][1]);
+        for (int i = 0; i < NKT; ++i) mma_16816(sc[i], qa[KS - 1], kb[i][0], kb[i][1]);
       }
     };
+    using Full = std::integral_constant<int, 4>;
+    using Tail = std::integral_constant<int, 2>;
+    const int full_end = t_pad & ~31;  // keys [0, full_end) in 32-key chunks, then an optional 16-key tail
 
     // ---- pass A: exact row maxima
     float m0 = -INFINITY, m1 = -INFINITY;  // rows g and g+8
-    for (int kc = 0; kc < t_pad; kc += 32) {
-      const int nkt = min(4, (t_pad - kc) >> 3);
+    auto max_chunk = [&](int kc, auto nkt_c) {
+      constexpr int NKT = decltype(nkt_c)::value;
       float sc[4][4];
-      qk_chunk(kc, nkt, sc);
-      if (kc + 32 > tokens) {  // only the last chunk(s) hold padded keys
+      qk_chunk(kc, nkt_c, sc);
+      if (kc + NKT * 8 > tokens) {  // padded keys only live in the last chunk(s)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NKT; ++i) {
           const int key = kc + i * 8 + t4 * 2;
           if (key >= tokens) sc[i][0] = sc[i][2] = -INFINITY;
           if (key + 1 >= tokens) sc[i][1] = sc[i][3] = -INFINITY;
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NKT; ++i) {
         m0 = fmaxf(m0, fmaxf(sc[i][0], sc[i][1]));
         m1 = fmaxf(m1, fmaxf(sc[i][2], sc[i][3]));
       }
-    }
+    };
+    for (int kc = 0; kc < full_end; kc += 32) max_chunk(kc, Full{});
+    if (full_end < t_pad) max_chunk(full_end, Tail{});
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
     m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
     m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
@@ -256,14 +266,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
 #pragma unroll
     for (int d = 0; d < HD / 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
     float l0 = 0.f, l1 = 0.f;
-    for (int kc = 0; kc < t_pad; kc += 32) {
-      const int nkt = min(4, (t_pad - kc) >> 3);
+    auto pv_chunk = [&](int kc, auto nkt_c) {
+      constexpr int NKT = decltype(nkt_c)::value;
       float sc[4][4];
-      qk_chunk(kc, nkt, sc);
-      const bool tail = kc + 32 > tokens;
+      qk_chunk(kc, nkt_c, sc);
+      const bool tail = kc + NKT * 8 > tokens;
       uint32_t pa[2][4];  // P as A fragments: k-step j covers key tiles 2j, 2j+1
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NKT; ++i) {
         float p0 = fast_exp2(fmaf(sc[i][0], scale_log2e, -b0)), p1 = fast_exp2(fmaf(sc[i][1], scale_log2e, -b0));
         float p2 = fast_exp2(fmaf(sc[i][2], scale_log2e, -b1)), p3 = fast_exp2(fmaf(sc[i][3], scale_log2e, -b1));
         if (tail) {  // padded keys contribute nothing (their V rows are zero as well)
@@ -275,22 +285,22 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
         pa[i >> 1][(i & 1) * 2 + 0] = pack_half2(p0, p1);
         pa[i >> 1][(i & 1) * 2 + 1] = pack_half2(p2, p3);
       }
+      constexpr int DP = HD / 16;  // pairs of 8-wide dim tiles
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if (2 * j < nkt) {
-          constexpr int DP = HD / 16;  // pairs of 8-wide dim tiles
-          uint32_t vb[DP][4];
+      for (int j = 0; j < NKT / 2; ++j) {
+        uint32_t vb[DP][4];
+        const uint32_t vbase = v_lane + (uint32_t)((kc + j * 16) * PITCH * 2);
 #pragma unroll
-          for (int dp = 0; dp < DP; ++dp)
-            ldmatrix_x4_trans(vb[dp], smem_u32(sV + (size_t)(kc + j * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + dp * 16 + (lane >> 4) * 8));
+        for (int dp = 0; dp < DP; ++dp) ldmatrix_x4_trans(vb[dp], vbase + (uint32_t)(dp * 32));
 #pragma unroll
-          for (int dp = 0; dp < DP; ++dp) {
-            mma_16816(o[2 * dp], pa[j], vb[dp][0], vb[dp][1]);
-            mma_16816(o[2 * dp + 1], pa[j], vb[dp][2], vb[dp][3]);
-          }
+        for (int dp = 0; dp < DP; ++dp) {
+          mma_16816(o[2 * dp], pa[j], vb[dp][0], vb[dp][1]);
+          mma_16816(o[2 * dp + 1], pa[j], vb[dp][2], vb[dp][3]);
         }
       }
-    }
+    };
+    for (int kc = 0; kc < full_end; kc += 32) pv_chunk(kc, Full{});
+    if (full_end < t_pad) pv_chunk(full_end, Tail{});
     // quad-reduce the row sums, normalise, store
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);

@@ -233,35 +233,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
     using Tail = std::integral_constant<int, 2>;
     const int full_end = t_pad & ~31;  // keys [0, full_end) in 32-key chunks, then an optional 16-key tail
 
-    // ---- pass A: exact row maxima
-    float m0 = -INFINITY, m1 = -INFINITY;  // rows g and g+8
-    auto max_chunk = [&](int kc, auto nkt_c) {
-      constexpr int NKT = decltype(nkt_c)::value;
-      float sc[4][4];
-      qk_chunk(kc, nkt_c, sc);
-      if (kc + NKT * 8 > tokens) {  // padded keys only live in the last chunk(s)
-#pragma unroll
-        for (int i = 0; i < NKT; ++i) {
-          const int key = kc + i * 8 + t4 * 2;
-          if (key >= tokens) sc[i][0] = sc[i][2] = -INFINITY;
-          if (key + 1 >= tokens) sc[i][1] = sc[i][3] = -INFINITY;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < NKT; ++i) {
-        m0 = fmaxf(m0, fmaxf(sc[i][0], sc[i][1]));
-        m1 = fmaxf(m1, fmaxf(sc[i][2], sc[i][3]));
-      }
-    };
-    for (int kc = 0; kc < full_end; kc += 32) max_chunk(kc, Full{});
-    if (full_end < t_pad) max_chunk(full_end, Tail{});
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    const float b0 = m0 * scale_log2e, b1 = m1 * scale_log2e;
-
-    // ---- pass B: P = exp2(S*c - m*c), row sums, O += P V
+    // ---- single pass, online softmax with LAZY rescaling: the running maxima (m0, m1) only grow; O and the row sums are
+    // rescaled when some row of the warp saw a new maximum (warp vote), which after the first chunks is rare.
+    float m0 = -INFINITY, m1 = -INFINITY;  // rows g and g+8 (quad-uniform)
     float o[HD / 8][4];
 #pragma unroll
     for (int d = 0; d < HD / 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
@@ -271,16 +245,37 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
       float sc[4][4];
       qk_chunk(kc, nkt_c, sc);
       const bool tail = kc + NKT * 8 > tokens;
-      uint32_t pa[2][4];  // P as A fragments: k-step j covers key tiles 2j, 2j+1
+      if (tail) {
+#pragma unroll
+        for (int i = 0; i < NKT; ++i) {
+          const int key = kc + i * 8 + t4 * 2;
+          if (key >= tokens) sc[i][0] = sc[i][2] = -INFINITY;
+          if (key + 1 >= tokens) sc[i][1] = sc[i][3] = -INFINITY;
+        }
+      }
+      float mx0 = m0, mx1 = m1;
 #pragma unroll
       for (int i = 0; i < NKT; ++i) {
-        float p0 = fast_exp2(fmaf(sc[i][0], scale_log2e, -b0)), p1 = fast_exp2(fmaf(sc[i][1], scale_log2e, -b0));
-        float p2 = fast_exp2(fmaf(sc[i][2], scale_log2e, -b1)), p3 = fast_exp2(fmaf(sc[i][3], scale_log2e, -b1));
-        if (tail) {  // padded keys contribute nothing (their V rows are zero as well)
-          const int key = kc + i * 8 + t4 * 2;
-          if (key >= tokens) p0 = p2 = 0.f;
-          if (key + 1 >= tokens) p1 = p3 = 0.f;
-        }
+        mx0 = fmaxf(mx0, fmaxf(sc[i][0], sc[i][1]));
+        mx1 = fmaxf(mx1, fmaxf(sc[i][2], sc[i][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      if (__any_sync(0xffffffffu, mx0 > m0 || mx1 > m1)) {  // warp-uniform: rescale the accumulators to the new maxima
+        const float c0 = fast_exp2((m0 - mx0) * scale_log2e), c1 = fast_exp2((m1 - mx1) * scale_log2e);  // exp2(-inf) = 0 on the first chunk
+        m0 = mx0, m1 = mx1;
+        l0 *= c0, l1 *= c1;
+#pragma unroll
+        for (int d = 0; d < HD / 8; ++d) o[d][0] *= c0, o[d][1] *= c0, o[d][2] *= c1, o[d][3] *= c1;
+      }
+      const float b0 = m0 * scale_log2e, b1 = m1 * scale_log2e;
+      uint32_t pa[2][4];  // P as A fragments: k-step j covers key tiles 2j, 2j+1
+#pragma unroll
+      for (int i = 0; i < NKT; ++i) {  // masked keys: exp2(-inf) = 0
+        const float p0 = fast_exp2(fmaf(sc[i][0], scale_log2e, -b0)), p1 = fast_exp2(fmaf(sc[i][1], scale_log2e, -b0));
+        const float p2 = fast_exp2(fmaf(sc[i][2], scale_log2e, -b1)), p3 = fast_exp2(fmaf(sc[i][3], scale_log2e, -b1));
         l0 += p0 + p1, l1 += p2 + p3;
         pa[i >> 1][(i & 1) * 2 + 0] = pack_half2(p0, p1);
         pa[i >> 1][(i & 1) * 2 + 1] = pack_half2(p2, p3);

@@ -41,6 +41,7 @@ constexpr int kSR = 32;  // source rows per strip (= lanes of a warp in the hori
 struct ClipArgs {
   const int* slots;  // device [n]
   int n, src_w, src_h, res;
+  int res_out;  // rows/columns actually emitted: res, or (res / patch) * patch for the patch layout (a stride-p conv drops the rest)
   const int *xmin, *xsize, *ymin, *ysize;  // cropped tap tables, [res]
   const float *wx, *wy;                    // [res][tx], [res][ty]
   int tx, ty;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(kThreads) clip_preprocess_kernel(const __grid_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frame = blockIdx.y;
   const int c0 = blockIdx.x * a.tc;
-  const int ncol = min(a.tc, a.res - c0);
+  const int ncol = min(a.tc, a.res_out - c0);
   const int slot = a.slots[frame];
 
   // ---- shared memory carve-up
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(kThreads) clip_preprocess_kernel(const __grid_
     // ---- phase 3: emit every output row whose vertical window is now complete
     int last = next_out;
     const bool final_strip = (s == a.n_strips - 1);
-    while (last < a.res && (final_strip || a.ymin[last] + a.ysize[last] <= y0 + kSR)) ++last;
+    while (last < a.res_out && (final_strip || a.ymin[last] + a.ysize[last] <= y0 + kSR)) ++last;
     for (int yo = next_out; yo < last; ++yo) {
       const int ym = a.ymin[yo], ys = a.ysize[yo];
       const float* w = a.wy + (size_t)yo * a.ty;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 2) clip_preprocess_v2_kernel(const _
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frame = blockIdx.y;
   const int c0 = blockIdx.x * a.tc;
-  const int ncol = min(a.tc, a.res - c0);
+  const int ncol = min(a.tc, a.res_out - c0);
   const int slot = a.slots[frame];
   const int ngroups = (ncol + 3) >> 2;
 
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 2) clip_preprocess_v2_kernel(const _
     // ---- phase 3: emit all output rows whose vertical window is complete, one patch row at a time
     int last = next_out;
     const bool final_strip = (s == a.n_strips - 1);
-    while (last < a.res && (final_strip || a.ymin[last] + a.ysize[last] <= y0 + kSR)) ++last;
+    while (last < a.res_out && (final_strip || a.ymin[last] + a.ysize[last] <= y0 + kSR)) ++last;
     int seg = next_out;
     while (seg < last) {
       const int seg_end = (a.out_mode == 2) ? min(last, (seg / a.patch + 1) * a.patch) : last;
@@ -644,12 +645,14 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
   a.ymin = ty->d_min, a.ysize = ty->d_size, a.wy = ty->d_w, a.ty = ty->max_taps;
   a.out_mode = out_mode, a.dtype = dtype, a.patch = layout_patch, a.k_pad = k_pad, a.out = out;
   if (out_mode == 2) {
-    if (layout_patch <= 0 || layout_patch > 32 || res % layout_patch) return fail(ctx, CB_ERR_UNSUPPORTED, "patch %d unsupported for res %d", layout_patch, res);
+    if (layout_patch <= 0 || layout_patch > 32 || res < layout_patch) return fail(ctx, CB_ERR_UNSUPPORTED, "patch %d unsupported for res %d", layout_patch, res);
     if (k_pad < 3 * layout_patch * layout_patch || (k_pad & 7)) return fail(ctx, CB_ERR_ARG, "k_pad %d must be >= 3*p*p and a multiple of 8", k_pad);
     if (dtype != CB_DT_F16 && dtype != CB_DT_BF16) return fail(ctx, CB_ERR_ARG, "patch layout needs a 16-bit dtype");
     a.tc = layout_patch * (32 / layout_patch);
+    a.res_out = (res / layout_patch) * layout_patch;
   } else {
     a.tc = 32;
+    a.res_out = res;
   }
   a.y_begin = ty->src_begin & ~1;
   a.n_strips = (ty->src_end - a.y_begin + kSR - 1) / kSR;
@@ -659,9 +662,9 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
   a.x_align = 16;  // cp.async.bulk.tensor needs the box to start on a 16-byte boundary of the innermost dimension
   // widest source span of any column tile
   int span = 0;
-  const int tiles = (res + a.tc - 1) / a.tc;
+  const int tiles = (a.res_out + a.tc - 1) / a.tc;
   for (int t = 0; t < tiles; ++t) {
-    const int c0 = t * a.tc, c1 = std::min(res, c0 + a.tc);
+    const int c0 = t * a.tc, c1 = std::min(a.res_out, c0 + a.tc);
     int lo = tx->h_min[c0] & ~(a.x_align - 1), hi = 0;
     for (int c = c0; c < c1; ++c) hi = std::max(hi, tx->h_min[c] + tx->h_size[c]);
     span = std::max(span, hi - lo);

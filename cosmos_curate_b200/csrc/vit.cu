@@ -3,6 +3,7 @@
 // cosmos_curate/models/clip.py:71-74 and the aesthetic MLP of aesthetics.py:44-53 (folded to one affine map).
 #include <cuda_fp16.h>
 
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -17,6 +18,8 @@ int assemble_tokens(cb_ctx*, const float*, const float*, const float*, const flo
 int attention_f16(cb_ctx*, const void*, void*, int, int, int, int, cudaStream_t);
 int clip_tail(cb_ctx*, const float*, size_t, const float*, const float*, const float*, int, int, float, const float*, float, float*, float*,
               float*, int, cudaStream_t);
+int map_pool(cb_ctx*, const void*, const float*, void*, int, int, int, int, cudaStream_t);
+int l2norm_score(cb_ctx*, const float*, int, const float*, float, float*, float*, float*, int, cudaStream_t);
 int run_clip_preprocess(cb_ctx*, const cb_surface_pool*, const int32_t*, int, int, int, int, int, int, const float*, const float*, void*,
                         cudaStream_t);
 }  // namespace cb
@@ -39,6 +42,9 @@ struct cb_vit {
   // workspace
   float *patch_out = nullptr, *h = nullptr;
   __half *xn = nullptr, *qkv = nullptr, *attn = nullptr, *mlp = nullptr, *patches = nullptr;
+  // SigLIP MAP head: the pooling query is image-independent -> q = (probe Wq^T + bq) / sqrt(head_dim), folded at finalize
+  std::vector<float> h_probe, h_wq, h_bq;
+  float* map_q = nullptr;
 };
 
 namespace {
@@ -72,6 +78,14 @@ std::map<std::string, Expect> expected_tensors(const cb_vit* v) {
   }
   e["post_ln_w"] = {d, false}, e["post_ln_b"] = {d, false};
   if (c.proj_dim > 0) e["proj_w"] = {(size_t)c.proj_dim * d, false};
+  if (c.arch == CB_ARCH_SIGLIP) {
+    e["map_probe"] = {d, false};
+    e["map_in_w"] = {3 * d * d, true}, e["map_in_b"] = {3 * d, false};
+    e["map_out_w"] = {d * d, true}, e["map_out_b"] = {d, false};
+    e["map_ln_w"] = {d, false}, e["map_ln_b"] = {d, false};
+    e["map_fc1_w"] = {m * d, true}, e["map_fc1_b"] = {m, false};
+    e["map_fc2_w"] = {d * m, true}, e["map_fc2_b"] = {d, false};
+  }
   return e;
 }
 
@@ -90,10 +104,12 @@ int cb_vit_create(cb_ctx* ctx, const cb_vit_cfg* cfg, cb_vit** out) {
   if (!cfg || !out) return cb::fail(ctx, CB_ERR_ARG, "vit_create: null argument");
   *out = nullptr;
   const cb_vit_cfg& c = *cfg;
-  if (c.image_size <= 0 || c.patch <= 0 || c.image_size % c.patch || c.hidden <= 0 || c.layers <= 0 || c.heads <= 0 || c.mlp <= 0 ||
+  if (c.image_size <= 0 || c.patch <= 0 || c.image_size < c.patch || c.hidden <= 0 || c.layers <= 0 || c.heads <= 0 || c.mlp <= 0 ||
       c.hidden % c.heads)
     return cb::fail(ctx, CB_ERR_ARG, "vit_create: inconsistent config");
-  if (c.arch != CB_ARCH_CLIP) return cb::fail(ctx, CB_ERR_UNSUPPORTED, "vit_create: only the CLIP-style tower is built so far (SigLIP MAP head pending)");
+  if (c.arch != CB_ARCH_CLIP && c.arch != CB_ARCH_SIGLIP) return cb::fail(ctx, CB_ERR_ARG, "vit_create: unknown architecture %d", c.arch);
+  if (c.arch == CB_ARCH_CLIP && c.image_size % c.patch) return cb::fail(ctx, CB_ERR_ARG, "vit_create: image_size must be a multiple of patch");
+  if (c.arch == CB_ARCH_SIGLIP && c.proj_dim != 0) return cb::fail(ctx, CB_ERR_ARG, "vit_create: the SigLIP tower has no projection (proj_dim must be 0)");
   if (c.act != CB_ACT_QUICK_GELU && c.act != CB_ACT_GELU_TANH) return cb::fail(ctx, CB_ERR_ARG, "vit_create: unknown activation");
   if (c.hidden % 128 || c.mlp % 8 || (c.proj_dim % 4)) return cb::fail(ctx, CB_ERR_UNSUPPORTED, "vit_create: hidden %% 128, mlp %% 8, proj %% 4 required");
   const int hd = c.hidden / c.heads;
@@ -114,6 +130,7 @@ void cb_vit_destroy(cb_vit* v) {
   cudaSetDevice(v->ctx->device);
   for (auto& kv : v->t) cudaFree(kv.second.d);
   cudaFree(v->aes_w);
+  cudaFree(v->map_q);
   cudaFree(v->patch_out), cudaFree(v->h), cudaFree(v->xn), cudaFree(v->qkv), cudaFree(v->attn), cudaFree(v->mlp), cudaFree(v->patches);
   delete v;
 }
@@ -128,6 +145,11 @@ int cb_vit_set_tensor(cb_vit* v, const char* name, const float* data, size_t cou
   auto it = exp.find(name);
   if (it == exp.end()) return cb::fail(ctx, CB_ERR_ARG, "vit_set_tensor: unknown tensor '%s'", name);
   if (it->second.count != count) return cb::fail(ctx, CB_ERR_ARG, "vit_set_tensor: '%s' has %zu elements, expected %zu", name, count, it->second.count);
+  // host copies of the pieces the MAP query is folded from
+  const size_t dd = (size_t)v->cfg.hidden;
+  if (std::strcmp(name, "map_probe") == 0) v->h_probe.assign(data, data + count);
+  if (std::strcmp(name, "map_in_w") == 0) v->h_wq.assign(data, data + dd * dd);
+  if (std::strcmp(name, "map_in_b") == 0) v->h_bq.assign(data, data + dd);
   cb_tensor& t = v->t[name];
   if (t.d) cudaFree(t.d), t.d = nullptr;
   t.half = it->second.half;
@@ -180,6 +202,18 @@ int cb_vit_finalize(cb_vit* v, int max_batch) {
   if ((rc = dev_alloc(ctx, &v->attn, rows * d))) return rc;
   if ((rc = dev_alloc(ctx, &v->mlp, rows * (size_t)c.mlp))) return rc;
   if ((rc = dev_alloc(ctx, &v->patches, prow * (size_t)v->k_pad))) return rc;
+  if (c.arch == CB_ARCH_SIGLIP) {
+    const int dm = c.hidden, hd = dm / c.heads;
+    std::vector<float> q(dm);
+    const double sc = 1.0 / std::sqrt((double)hd);
+    for (int o = 0; o < dm; ++o) {
+      double acc = v->h_bq[o];
+      for (int i = 0; i < dm; ++i) acc += (double)v->h_wq[(size_t)o * dm + i] * (double)v->h_probe[i];
+      q[o] = (float)(acc * sc);
+    }
+    if (!v->map_q && (rc = dev_alloc(ctx, &v->map_q, (size_t)dm))) return rc;
+    CB_CUDA(ctx, cudaMemcpy(v->map_q, q.data(), dm * sizeof(float), cudaMemcpyHostToDevice));
+  }
   v->max_batch = max_batch;
   v->finalized = true;
   return CB_OK;
@@ -212,8 +246,20 @@ static int forward_chunk(cb_vit* v, const void* patches, int n, float* emb, floa
     if ((rc = cb::gemm_f16(ctx, v->xn, H(p + "fc1_w"), F(p + "fc1_b"), nullptr, nullptr, v->mlp, rows, c.mlp, d, act, s))) return rc;
     if ((rc = cb::gemm_f16(ctx, v->mlp, H(p + "fc2_w"), F(p + "fc2_b"), v->h, v->h, nullptr, rows, d, c.mlp, CB_EPI_NONE, s))) return rc;
   }
-  return cb::clip_tail(ctx, v->h, (size_t)T * d, F("post_ln_w"), F("post_ln_b"), c.proj_dim > 0 ? F("proj_w") : nullptr, d, c.proj_dim, c.ln_eps,
-                       score ? v->aes_w : nullptr, v->aes_b, emb, feat, score, n, s);
+  if (c.arch == CB_ARCH_CLIP)
+    return cb::clip_tail(ctx, v->h, (size_t)T * d, F("post_ln_w"), F("post_ln_b"), c.proj_dim > 0 ? F("proj_w") : nullptr, d, c.proj_dim, c.ln_eps,
+                         score ? v->aes_w : nullptr, v->aes_b, emb, feat, score, n, s);
+  // SigLIP: post_layernorm on every token, then the MAP head (one learned query attends over the tokens, + MLP block)
+  const __half* kv_w = (const __half*)H("map_in_w") + (size_t)d * d;  // rows d..3d of in_proj_weight: K | V projections
+  float* r = v->patch_out;                                            // [n][d] fp32 scratch (patch-embed output is dead by now)
+  if ((rc = cb::layernorm_f16(ctx, v->h, F("post_ln_w"), F("post_ln_b"), v->xn, rows, d, c.ln_eps, s))) return rc;
+  if ((rc = cb::gemm_f16(ctx, v->xn, kv_w, F("map_in_b") + d, nullptr, nullptr, v->qkv, rows, 2 * d, d, CB_EPI_NONE, s))) return rc;
+  if ((rc = cb::map_pool(ctx, v->qkv, v->map_q, v->attn, n, T, c.heads, hd, s))) return rc;
+  if ((rc = cb::gemm_f16(ctx, v->attn, H("map_out_w"), F("map_out_b"), nullptr, r, nullptr, n, d, d, CB_EPI_NONE, s))) return rc;
+  if ((rc = cb::layernorm_f16(ctx, r, F("map_ln_w"), F("map_ln_b"), v->xn, n, d, c.ln_eps, s))) return rc;
+  if ((rc = cb::gemm_f16(ctx, v->xn, H("map_fc1_w"), F("map_fc1_b"), nullptr, nullptr, v->mlp, n, c.mlp, d, act, s))) return rc;
+  if ((rc = cb::gemm_f16(ctx, v->mlp, H("map_fc2_w"), F("map_fc2_b"), r, r, nullptr, n, d, c.mlp, CB_EPI_NONE, s))) return rc;
+  return cb::l2norm_score(ctx, r, d, score ? v->aes_w : nullptr, v->aes_b, emb, feat, score, n, s);
 }
 
 int cb_vit_forward(cb_vit* v, const void* patches, int n, float* emb_out, float* feat_out, float* score_out, void* stream) {

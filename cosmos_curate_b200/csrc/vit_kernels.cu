@@ -138,49 +138,70 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// HD: head dim padded to a multiple of 16 (64 -> 64, 72 -> 80).  One CTA per (image, head): K and V of the head stay in
-// shared memory (cp.async fill), each warp owns 16-query tiles.  T is short (257 / 50 / ...), so instead of an online
-// softmax the kernel makes two passes over the keys: pass A takes the exact row maxima from S = Q K^T, pass B recomputes S
-// in 32-key chunks, forms P = exp2((S - m) * scale * log2e) in fp32, accumulates the row sums and O += P V.  MMAs are issued
-// over independent accumulators back to back (legacy tensor pipe latency), fragment loads are batched ahead of them.
-template <int HD>
+// HD: head dim padded to a multiple of 16 (64 -> 64, 72 -> 80).  Each warp owns 16-query tiles; K and V live in shared
+// memory (cp.async fill) and are consumed with ldmatrix / mma.sync.m16n8k16 in 32-key chunks whose shape is a compile-time
+// constant (no convergence barriers around the .sync instructions); MMAs are issued over independent accumulators back to
+// back; softmax is online in fp32 with LAZY rescaling (O and the row sums are rescaled only when a row of the warp sees a new
+// maximum - rare after the first chunks).
+//   STREAM = false: one CTA per (image, head), all keys resident, warps loop over the query tiles      (T = 50, 257, ...)
+//   STREAM = true : grid.y splits the query tiles (one per warp), keys stream through shared memory in
+//                   blocks of kStreamKeys, the softmax state stays in registers across blocks             (T = 729, ...)
+constexpr int kStreamKeys = 256;
+
+template <int HD, bool STREAM>
 __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int tokens,
                                                                      int heads, int head_dim, float scale_log2e) {
   constexpr int PITCH = HD + 8;  // halves; 16-byte row skew keeps ldmatrix conflict-free
   constexpr int KS = HD / 16;    // k-steps over the head dimension
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int t_pad = (tokens + 15) & ~15;
+  const int blk = STREAM ? kStreamKeys : t_pad;  // keys resident at a time
   __half* sK = (__half*)smem_attn;
-  __half* sV = sK + (size_t)t_pad * PITCH;
+  __half* sV = sK + (size_t)blk * PITCH;
   const int img = blockIdx.x / heads, head = blockIdx.x - img * heads;
   const int hidden = heads * head_dim;
   const size_t row_stride = (size_t)3 * hidden;
   const __half* base = qkv + (size_t)img * tokens * row_stride + (size_t)head * head_dim;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
 
-  // K and V (zero padded in both directions) -> shared memory, all copies in flight at once
+  // keys [k0, k0 + blk) (zero padded in both directions) -> shared memory, all copies in flight at once
   constexpr int VEC = HD / 8;
   const int vec_valid = head_dim / 8;  // head_dim % 8 == 0 is checked on the host
-  for (int i = threadIdx.x; i < t_pad * VEC; i += kAttnThreads) {
-    const int r = i / VEC, c = i - r * VEC;
-    __half* dk = sK + (size_t)r * PITCH + c * 8;
-    __half* dv = sV + (size_t)r * PITCH + c * 8;
-    if (r < tokens && c < vec_valid) {
-      const __half* p = base + (size_t)r * row_stride + c * 8;
-      cp_async_16(dk, p + hidden);
-      cp_async_16(dv, p + 2 * hidden);
-    } else {
-      *(uint4*)dk = make_uint4(0, 0, 0, 0);
-      *(uint4*)dv = make_uint4(0, 0, 0, 0);
+  auto load_block = [&](int k0) {
+    const int rows = min(blk, t_pad - k0);
+    for (int i = threadIdx.x; i < rows * VEC; i += kAttnThreads) {
+      const int r = i / VEC, c = i - r * VEC;
+      __half* dk = sK + (size_t)r * PITCH + c * 8;
+      __half* dv = sV + (size_t)r * PITCH + c * 8;
+      if (k0 + r < tokens && c < vec_valid) {
+        const __half* p = base + (size_t)(k0 + r) * row_stride + c * 8;
+        cp_async_16(dk, p + hidden);
+        cp_async_16(dv, p + 2 * hidden);
+      } else {
+        *(uint4*)dk = make_uint4(0, 0, 0, 0);
+        *(uint4*)dv = make_uint4(0, 0, 0, 0);
+      }
     }
-  }
+  };
+  if (!STREAM) load_block(0);
+
+  // per-lane shared-memory offsets of the ldmatrix rows (bytes)
+  const uint32_t k_lane = smem_u32(sK) + (uint32_t)(((lane & 7) * PITCH + (lane >> 3) * 8) * 2);
+  const uint32_t k_lane_tail = smem_u32(sK) + (uint32_t)(((lane & 7) * PITCH + (HD - 16) + ((lane >> 3) & 1) * 8) * 2);
+  const uint32_t v_lane = smem_u32(sV) + (uint32_t)(((((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + (lane >> 4) * 8) * 2);
+  using Full = std::integral_constant<int, 4>;
+  using Tail = std::integral_constant<int, 2>;
 
   const int q_tiles = t_pad >> 4;
+  const int qt_first = STREAM ? (int)blockIdx.y * kAttnWarps + warp : warp;
+  const int qt_step = STREAM ? q_tiles : kAttnWarps;  // STREAM: exactly one tile per warp (maybe none)
   bool first = true;
-  for (int qt = warp; qt < q_tiles; qt += kAttnWarps) {
+  for (int qt = qt_first; qt < q_tiles || (STREAM && first); qt += qt_step) {
+    const bool active = qt < q_tiles;  // STREAM: a warp without a tile still takes part in the block barriers
     // Q fragments straight from global memory (rows clamped; padded columns read as zero)
     uint32_t qa[KS][4];
-    const int r0 = min(qt * 16 + g, tokens - 1), r1 = min(qt * 16 + g + 8, tokens - 1);
+    const int qrow = active ? qt * 16 : 0;
+    const int r0 = min(qrow + g, tokens - 1), r1 = min(qrow + g + 8, tokens - 1);
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       const int c0 = ks * 16 + t4 * 2, c1 = c0 + 8;
@@ -189,28 +210,22 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
       qa[ks][2] = c1 < head_dim ? __ldg((const uint32_t*)(base + (size_t)r0 * row_stride + c1)) : 0u;
       qa[ks][3] = c1 < head_dim ? __ldg((const uint32_t*)(base + (size_t)r1 * row_stride + c1)) : 0u;
     }
-    if (qt + kAttnWarps < q_tiles) {  // pull the next tile's Q rows towards L2 while this tile computes
+    if (!STREAM && qt + kAttnWarps < q_tiles) {  // pull the next tile's Q rows towards L2 while this tile computes
       const int rn = min((qt + kAttnWarps) * 16 + (lane & 15), tokens - 1);
       prefetch_l2(base + (size_t)rn * row_stride);
     }
-    if (first) {  // the Q loads above overlap the K/V fill
+    if (!STREAM && first) {  // the Q loads above overlap the K/V fill
       cp_async_wait_all();
       __syncthreads();
-      first = false;
     }
+    first = false;
 
-    // per-lane shared-memory offsets of the ldmatrix rows (bytes)
-    const uint32_t k_lane = smem_u32(sK) + (uint32_t)(((lane & 7) * PITCH + (lane >> 3) * 8) * 2);
-    const uint32_t k_lane_tail = smem_u32(sK) + (uint32_t)(((lane & 7) * PITCH + (HD - 16) + ((lane >> 3) & 1) * 8) * 2);
-    const uint32_t v_lane = smem_u32(sV) + (uint32_t)(((((lane >> 3) & 1) * 8 + (lane & 7)) * PITCH + (lane >> 4) * 8) * 2);
-
-    // S = Q K^T for NKT 8-key tiles starting at key kc.  NKT is a compile-time constant (4, or 2 for the 16-key tail of a
-    // 16-multiple length) so every ldmatrix / mma is unconditional: no convergence barriers around the .sync instructions.
-    auto qk_chunk = [&](int kc, auto nkt_c, float (&sc)[4][4]) {
+    // S = Q K^T for NKT 8-key tiles; `srow` = row of the chunk's first key inside the resident block
+    auto qk_chunk = [&](int srow, auto nkt_c, float (&sc)[4][4]) {
       constexpr int NKT = decltype(nkt_c)::value;
 #pragma unroll
       for (int i = 0; i < 4; ++i) sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
-      const uint32_t kbase = k_lane + (uint32_t)(kc * PITCH * 2);
+      const uint32_t kbase = k_lane + (uint32_t)(srow * PITCH * 2);
 #pragma unroll
       for (int kp = 0; kp < HD / 32; ++kp) {  // two k-steps per ldmatrix.x4
         uint32_t kb[NKT][4];
@@ -224,28 +239,22 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
       if (HD % 32) {  // odd number of k-steps (HD = 80): last 16 columns
         uint32_t kb[NKT][4];
 #pragma unroll
-        for (int i = 0; i < NKT; ++i) ldmatrix_x4(kb[i], k_lane_tail + (uint32_t)((kc + i * 8) * PITCH * 2));
+        for (int i = 0; i < NKT; ++i) ldmatrix_x4(kb[i], k_lane_tail + (uint32_t)((srow + i * 8) * PITCH * 2));
 #pragma unroll
         for (int i = 0; i < NKT; ++i) mma_16816(sc[i], qa[KS - 1], kb[i][0], kb[i][1]);
       }
     };
-    using Full = std::integral_constant<int, 4>;
-    using Tail = std::integral_constant<int, 2>;
-    const int full_end = t_pad & ~31;  // keys [0, full_end) in 32-key chunks, then an optional 16-key tail
 
-    // ---- single pass, online softmax with LAZY rescaling: the running maxima (m0, m1) only grow; O and the row sums are
-    // rescaled when some row of the warp saw a new maximum (warp vote), which after the first chunks is rare.
-    float m0 = -INFINITY, m1 = -INFINITY;  // rows g and g+8 (quad-uniform)
+    float m0 = -INFINITY, m1 = -INFINITY;  // running maxima of rows g and g+8 (quad-uniform)
     float o[HD / 8][4];
 #pragma unroll
     for (int d = 0; d < HD / 8; ++d) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
     float l0 = 0.f, l1 = 0.f;
-    auto pv_chunk = [&](int kc, auto nkt_c) {
+    auto pv_chunk = [&](int kc, int srow, auto nkt_c) {  // kc: absolute key index of the chunk (masking)
       constexpr int NKT = decltype(nkt_c)::value;
       float sc[4][4];
-      qk_chunk(kc, nkt_c, sc);
-      const bool tail = kc + NKT * 8 > tokens;
-      if (tail) {
+      qk_chunk(srow, nkt_c, sc);
+      if (kc + NKT * 8 > tokens) {  // padded keys only live in the last chunk(s)
 #pragma unroll
         for (int i = 0; i < NKT; ++i) {
           const int key = kc + i * 8 + t4 * 2;
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       if (__any_sync(0xffffffffu, mx0 > m0 || mx1 > m1)) {  // warp-uniform: rescale the accumulators to the new maxima
-        const float c0 = fast_exp2((m0 - mx0) * scale_log2e), c1 = fast_exp2((m1 - mx1) * scale_log2e);  // exp2(-inf) = 0 on the first chunk
+        const float c0 = fast_exp2((m0 - mx0) * scale_log2e), c1 = fast_exp2((m1 - mx1) * scale_log2e);  // exp2(-inf) = 0 at the start
         m0 = mx0, m1 = mx1;
         l0 *= c0, l1 *= c1;
 #pragma unroll
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
 #pragma unroll
       for (int j = 0; j < NKT / 2; ++j) {
         uint32_t vb[DP][4];
-        const uint32_t vbase = v_lane + (uint32_t)((kc + j * 16) * PITCH * 2);
+        const uint32_t vbase = v_lane + (uint32_t)((srow + j * 16) * PITCH * 2);
 #pragma unroll
         for (int dp = 0; dp < DP; ++dp) ldmatrix_x4_trans(vb[dp], vbase + (uint32_t)(dp * 32));
 #pragma unroll
@@ -294,8 +303,22 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
         }
       }
     };
-    for (int kc = 0; kc < full_end; kc += 32) pv_chunk(kc, Full{});
-    if (full_end < t_pad) pv_chunk(full_end, Tail{});
+
+    for (int k0 = 0; k0 < t_pad; k0 += blk) {  // one iteration when the keys are resident
+      if (STREAM) {
+        __syncthreads();  // every warp is done with the previous block
+        load_block(k0);
+        cp_async_wait_all();
+        __syncthreads();
+      }
+      if (active) {
+        const int rows = min(blk, t_pad - k0), full_end = rows & ~31;
+        for (int r = 0; r < full_end; r += 32) pv_chunk(k0 + r, r, Full{});
+        if (full_end < rows) pv_chunk(k0 + full_end, full_end, Tail{});
+      }
+    }
+    if (!active) break;
+
     // quad-reduce the row sums, normalise, store
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -313,7 +336,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) attention_kernel(const __half
       }
     }
   }
-  if (first) {  // a warp without a tile (q_tiles < warps) still has to meet the fill barrier
+  if (!STREAM && first) {  // a warp without a tile (q_tiles < warps) still has to meet the fill barrier
     cp_async_wait_all();
     __syncthreads();
   }
@@ -387,6 +410,92 @@ __global__ void __launch_bounds__(256) clip_tail_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------ SigLIP MAP head
+// Multi-head attention pooling with ONE learned query (HF SiglipMultiheadAttentionPoolingHead): per (image, head)
+// softmax_t(q_h . k_t) applied to v_t.  kv: fp16 [n][tokens][2*hidden] (k | v), q: fp32 [hidden] already scaled by
+// head_dim^-1/2, out: fp16 [n][hidden].
+__global__ void __launch_bounds__(256) map_pool_kernel(const __half* __restrict__ kv, const float* __restrict__ q, __half* __restrict__ out,
+                                                       int tokens, int heads, int head_dim) {
+  extern __shared__ float sm_map[];  // [tokens] probabilities, then [head_dim] query
+  float* prob = sm_map;
+  float* qh = sm_map + tokens;
+  __shared__ float red[32];
+  const int img = blockIdx.x / heads, head = blockIdx.x - img * heads;
+  const int hidden = heads * head_dim, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const __half* base = kv + (size_t)img * tokens * 2 * hidden + (size_t)head * head_dim;
+  for (int d = tid; d < head_dim; d += blockDim.x) qh[d] = q[head * head_dim + d];
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int t = tid; t < tokens; t += blockDim.x) {
+    const __half* k = base + (size_t)t * 2 * hidden;
+    float s = 0.f;
+    for (int d = 0; d < head_dim; d += 2) {
+      const float2 kk = __half22float2(*(const __half2*)(k + d));
+      s = fmaf(kk.x, qh[d], fmaf(kk.y, qh[d + 1], s));
+    }
+    prob[t] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < nw; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int t = tid; t < tokens; t += blockDim.x) {
+    const float e = __expf(prob[t] - mx);
+    prob[t] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < nw; ++i) tot += red[i];
+  const float inv = 1.f / tot;
+  // o_d = sum_t p_t v[t][d]: threads over (d, token slice) then a shared-memory reduction over slices
+  const int slices = blockDim.x / head_dim > 0 ? blockDim.x / head_dim : 1;
+  __syncthreads();
+  float* part = qh;  // reuse: needs slices*head_dim floats (allocated by the host)
+  if (tid < slices * head_dim) {
+    const int d = tid % head_dim, sl = tid / head_dim;
+    const __half* v = base + hidden + d;
+    float acc = 0.f;
+    for (int t = sl; t < tokens; t += slices) acc = fmaf(prob[t], __half2float(v[(size_t)t * 2 * hidden]), acc);
+    part[sl * head_dim + d] = acc;
+  }
+  __syncthreads();
+  if (tid < head_dim) {
+    float acc = 0.f;
+    for (int sl = 0; sl < slices; ++sl) acc += part[sl * head_dim + tid];
+    out[(size_t)img * hidden + head * head_dim + tid] = __float2half_rn(acc * inv);
+  }
+}
+
+// emb = feat / ||feat||, optional score = w . emb + b; one warp per row
+__global__ void __launch_bounds__(256) l2norm_score_kernel(const float* __restrict__ feat, int d, const float* __restrict__ aes_w, float aes_b,
+                                                           float* __restrict__ emb_out, float* __restrict__ feat_out, float* __restrict__ score_out,
+                                                           int n) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* x = feat + (size_t)row * d;
+  float n2 = 0.f;
+  for (int i = lane; i < d; i += 32) n2 = fmaf(x[i], x[i], n2);
+  const float inv = 1.f / sqrtf(warp_sum(n2));
+  float sc = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float e = x[i] * inv;
+    emb_out[(size_t)row * d + i] = e;
+    if (feat_out) feat_out[(size_t)row * d + i] = x[i];
+    if (aes_w) sc = fmaf(e, aes_w[i], sc);
+  }
+  if (score_out && aes_w) {
+    sc = warp_sum(sc);
+    if (lane == 0) score_out[row] = sc + aes_b;
+  }
+}
+
 // score[i] = w . emb[i] + b : the reference's aesthetic MLP (aesthetics.py:44-53) folded to its affine map
 __global__ void __launch_bounds__(256) affine_score_kernel(const float* __restrict__ emb, const float* __restrict__ w, float b,
                                                            float* __restrict__ out, int n, int d) {
@@ -435,17 +544,41 @@ int attention_f16(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, in
     return fail(ctx, CB_ERR_UNSUPPORTED, "attention: tokens=%d heads=%d head_dim=%d unsupported", tokens, heads, head_dim);
   const int hd = head_dim <= 64 ? 64 : 80;
   const int t_pad = (tokens + 15) & ~15;
-  const size_t smem = (size_t)2 * t_pad * (hd + 8) * 2;
-  if (smem > 200 * 1024) return fail(ctx, CB_ERR_UNSUPPORTED, "attention: %d tokens need %zu bytes of shared memory (K/V streaming not built yet)", tokens, smem);
+  const size_t resident = (size_t)2 * t_pad * (hd + 8) * 2;
+  const bool stream_keys = resident > 100 * 1024;  // keep two CTAs per SM; longer sequences stream their keys
+  const size_t smem = stream_keys ? (size_t)2 * kStreamKeys * (hd + 8) * 2 : resident;
   const float scale_log2e = 1.4426950408889634f / sqrtf((float)head_dim);
+  const dim3 grid(n * heads, stream_keys ? ((t_pad >> 4) + kAttnWarps - 1) / kAttnWarps : 1);
   mark_launch(ctx, CB_PROF_ATTENTION, stream);
-  if (hd == 64) {
-    CB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attention_kernel<64><<<n * heads, kAttnThreads, smem, stream>>>((const __half*)qkv, (__half*)out, tokens, heads, head_dim, scale_log2e);
-  } else {
-    CB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attention_kernel<80><<<n * heads, kAttnThreads, smem, stream>>>((const __half*)qkv, (__half*)out, tokens, heads, head_dim, scale_log2e);
-  }
+#define CB_ATTN_LAUNCH(HD_, ST_)                                                                                               \
+  do {                                                                                                                         \
+    CB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel<HD_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    attention_kernel<HD_, ST_><<<grid, kAttnThreads, smem, stream>>>((const __half*)qkv, (__half*)out, tokens, heads, head_dim, scale_log2e); \
+  } while (0)
+  if (hd == 64 && !stream_keys) CB_ATTN_LAUNCH(64, false);
+  else if (hd == 64) CB_ATTN_LAUNCH(64, true);
+  else if (!stream_keys) CB_ATTN_LAUNCH(80, false);
+  else CB_ATTN_LAUNCH(80, true);
+#undef CB_ATTN_LAUNCH
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
+}
+
+int map_pool(cb_ctx* ctx, const void* kv, const float* q, void* out, int n, int tokens, int heads, int head_dim, cudaStream_t stream) {
+  const int threads = 256;
+  const int slices = threads / head_dim > 0 ? threads / head_dim : 1;
+  const size_t smem = (size_t)(tokens + slices * head_dim) * sizeof(float);
+  if (smem > 48 * 1024) CB_CUDA(ctx, cudaFuncSetAttribute(map_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mark_launch(ctx, CB_PROF_OTHER, stream);
+  map_pool_kernel<<<n * heads, threads, smem, stream>>>((const __half*)kv, q, (__half*)out, tokens, heads, head_dim);
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
+}
+
+int l2norm_score(cb_ctx* ctx, const float* feat, int d, const float* aes_w, float aes_b, float* emb, float* feat_out, float* score, int n,
+                 cudaStream_t stream) {
+  mark_launch(ctx, CB_PROF_OTHER, stream);
+  l2norm_score_kernel<<<(n + 7) / 8, 256, 0, stream>>>(feat, d, aes_w, aes_b, emb, feat_out, score, n);
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }

@@ -195,7 +195,7 @@ def gen_siglip() -> None:
     from transformers import SiglipVisionConfig, SiglipVisionModel
 
     torch.manual_seed(2)
-    cfg = SiglipVisionConfig(hidden_size=64, intermediate_size=96, num_hidden_layers=2, num_attention_heads=4, image_size=64, patch_size=16)
+    cfg = SiglipVisionConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4, image_size=64, patch_size=16)
     m = SiglipVisionModel(cfg).eval()
     with torch.no_grad():
         g = torch.Generator().manual_seed(3)

@@ -140,7 +140,8 @@ def to_patches(x_nchw: np.ndarray, patch: int, k_pad: int | None = None) -> np.n
     """[N,3,R,R] -> [N, (R/p)^2, 3*p*p (zero-padded to k_pad)], row order (c, py, px) - the
     im2col of Conv2d(3, D, kernel=p, stride=p) (HF CLIPVisionEmbeddings.patch_embedding)."""
     n, c, r, _ = x_nchw.shape
-    g = r // patch
+    g = r // patch  # a stride-p conv drops the remainder rows / columns (SigLIP 384 / 14 = 27)
+    x_nchw = x_nchw[:, :, : g * patch, : g * patch]
     p = x_nchw.reshape(n, c, g, patch, g, patch).transpose(0, 2, 4, 1, 3, 5).reshape(n, g * g, c * patch * patch)
     if k_pad is not None and k_pad > p.shape[-1]:
         p = np.concatenate([p, np.zeros((n, g * g, k_pad - p.shape[-1]), dtype=p.dtype)], axis=-1)

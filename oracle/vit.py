@@ -63,6 +63,7 @@ CLIP_VIT_B32 = VitConfig(patch=32, hidden=768, layers=12, heads=12, mlp=3072, pr
 SIGLIP_SO400M_384 = VitConfig(
     image_size=384, patch=14, hidden=1152, layers=27, heads=16, mlp=4304, proj_dim=0, act="gelu_tanh", ln_eps=1e-6, arch="siglip"
 )
+SIGLIP_SO400M_2L = VitConfig(image_size=384, patch=14, hidden=1152, layers=2, heads=16, mlp=4304, proj_dim=0, act="gelu_tanh", ln_eps=1e-6, arch="siglip")
 # tiny configs for fast parity tests (same code paths, small sizes)
 CLIP_TINY = VitConfig(image_size=224, patch=32, hidden=256, layers=2, heads=4, mlp=512, proj_dim=128)
 
@@ -203,6 +204,7 @@ def forward(cfg: VitConfig, w: dict, pixels: np.ndarray | torch.Tensor, return_h
     W = {k: torch.as_tensor(v, dtype=torch.float32) for k, v in w.items()}
     x = torch.as_tensor(pixels, dtype=torch.float32)
     n, d, p, g = x.shape[0], cfg.hidden, cfg.patch, cfg.grid
+    x = x[:, :, : g * p, : g * p]  # Conv2d(stride = kernel = p) ignores the remainder (SigLIP: 384 = 27 * 14 + 6)
     patches = x.reshape(n, 3, g, p, g, p).permute(0, 2, 4, 1, 3, 5).reshape(n, g * g, 3 * p * p)
     tok = patches @ W["patch_w"].T
     if cfg.arch == "clip":

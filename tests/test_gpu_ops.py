@@ -100,3 +100,16 @@ def test_gemm_both_kernels_with_tails(ctx, monkeypatch, kernel, m, n, k):
     res = torch.randn(m, n, device="cuda", generator=g)
     got = ctx.gemm(a, w, bias=bias, residual=res.clone(), out_f32=True)
     torch.testing.assert_close(got, res + z, rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize(("n", "t", "heads", "hd"), [(2, 729, 16, 72), (1, 600, 4, 64), (1, 1030, 2, 64)])
+def test_attention_streamed_keys(ctx, n, t, heads, hd):
+    """Sequences whose K/V do not fit shared memory: query tiles split over grid.y, keys streamed in 256-key blocks."""
+    g = torch.Generator(device="cuda").manual_seed(t)
+    d = heads * hd
+    qkv = (torch.randn(n, t, 3 * d, device="cuda", generator=g) * 1.2).half()
+    got = ctx.attention(qkv, heads).float()
+    q, k, v = qkv.float().view(n, t, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(q @ k.transpose(-1, -2) * hd**-0.5, dim=-1)
+    want = (p @ v).permute(0, 2, 1, 3).reshape(n, t, d)
+    torch.testing.assert_close(got, want, rtol=1e-2, atol=4e-3)

@@ -65,3 +65,34 @@ def test_tower_vs_oracle(ctx, cfg_name):
     assert _rel(feat.cpu().numpy(), ref["features"]) < 1e-3
     want_score = vit.aesthetic_mlp_forward(sd, ref["embedding"])
     np.testing.assert_allclose(score.cpu().numpy(), want_score, rtol=0, atol=2e-3)  # reference test tolerance 0.002
+
+
+def test_siglip_tower_vs_hf_golden(ctx):
+    """SigLIP-style tower (no CLS, patch bias, gelu_tanh, MAP pooling head) against transformers' SiglipVisionModel."""
+    g = load_golden("siglip_tiny_hf.npz")
+    cfg = vit.VitConfig(**golden_json(g, "cfg"))
+    w = {k[2:]: g[k] for k in g.files if k.startswith("w_")}
+    tower = _tower(ctx, cfg, w, 4)
+    x16 = g["x"].astype(np.float16)
+    patches = torch.from_numpy(preprocess.to_patches(x16, cfg.patch, tower.k_pad)).cuda()
+    _, feat, _ = tower.forward_patches(patches, want_features=True)
+    want = vit.forward(cfg, w, x16.astype(np.float32))["features"]  # oracle on the same fp16-rounded pixels
+    np.testing.assert_allclose(want, g["pooled"], rtol=2e-2, atol=2e-3)  # ... which itself tracks HF on the fp32 pixels
+    assert _rel(feat.cpu().numpy(), want) < 2e-3
+
+
+def test_siglip_so400m_shape_two_layers(ctx):
+    """SoViT-400m/14 @384 geometry (729 tokens, 16 heads x 72, MLP 4304, 384 = 27*14 + 6) with 2 layers: streamed attention,
+    N=1152 / K=4304 GEMM tails, patch rows from a non-divisible image size; embeddings vs the oracle."""
+    cfg = vit.SIGLIP_SO400M_2L
+    w = vit.random_weights(cfg, seed=4)
+    frames = [color.synthetic_nv12(1080, 1920, seed=70 + s) for s in range(2)]
+    pool = _nv12_pool(ctx, frames, 1920, 1080, 2048, 1088)
+    tower = _tower(ctx, cfg, w, max_batch=2)
+    mean = std = (0.5, 0.5, 0.5)  # SigLIP normalisation
+    emb, feat, _ = tower.embed_pool(pool, mean=mean, std=std, want_features=True)
+    u8 = ctx.preprocess_clip_u8(pool, res=384).cpu().numpy()
+    lut = preprocess.normalize_lut(mean, std)
+    x = np.stack([lut[c][u8[:, c]] for c in range(3)], axis=1)
+    ref = vit.forward(cfg, w, x)
+    assert _rel(emb.cpu().numpy(), ref["embedding"]) < 2e-3

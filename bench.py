@@ -106,8 +106,7 @@ def run_reference(args) -> None:
     clips = make_clips(2, 0)
     sample = max(procs, args.ref_clips)  # at least one clip per worker so every host core is busy
     batch = [clips[i % len(clips)] for i in range(sample)]
-    for _ in range(max(1, args.warmup)):
-        pool.run(batch[:procs], SAMPLE_FPS)
+    pool.run(batch[:procs], SAMPLE_FPS)  # one warm-up pass (a CPU step takes ~25 s; more warm-up would only burn minutes)
     t, frames, phases = 0.0, 0, {"decode_s": 0.0, "preprocess_s": 0.0, "model_s": 0.0}
     for _ in range(args.steps):
         r = pool.run(batch, SAMPLE_FPS)

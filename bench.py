@@ -317,6 +317,8 @@ def run_b200(args) -> None:
 
 def cpu_layout(cores: int) -> tuple[int, int]:
     """(worker processes, torch threads each): the reference scales this path by replicating actors, not by threading one model."""
+    if os.environ.get("CB_REF_PROCS") and os.environ.get("CB_REF_THREADS"):  # tuning override
+        return int(os.environ["CB_REF_PROCS"]), int(os.environ["CB_REF_THREADS"])
     threads = 16 if cores >= 32 else max(1, cores // 2)
     return max(1, cores // threads), threads
 

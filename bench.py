@@ -277,6 +277,7 @@ def run_b200(args) -> None:
         return
 
     pk, pk_src = peaks()
+    traffic = ncu_traffic()
     gemm_flops = cfg.gemm_flops_per_image() * frames_per_step * args.steps
     gemm_ms, gemm_n = prof["gemm"]["ms"], max(1, prof["gemm"]["launches"])
     ach_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
@@ -287,7 +288,8 @@ def run_b200(args) -> None:
     for name, nbytes, key in (("preprocess", pre_bytes, "preprocess"), ("layernorm", ln_bytes, "layernorm")):
         ms = prof[key]["ms"]
         gbs = nbytes / (ms / 1e3) / 1e9 if ms > 0 else 0.0
-        other[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None,
+        other[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                       "traffic": traffic.get({"preprocess": "clip_preprocess", "layernorm": "layernorm_kernel"}[name]),
                        "ms_per_step": ms / args.steps, "launches_per_step": prof[key]["launches"] / args.steps}  # fmt: skip
     other["attention"] = {"ms_per_step": prof["attention"]["ms"] / args.steps, "launches_per_step": prof["attention"]["launches"] / args.steps}
     step_ms = 1e3 * dev_s / args.steps
@@ -300,7 +302,8 @@ def run_b200(args) -> None:
                    "model": "clip-vit-large-patch14, seeded random weights, fp16 operands / fp32 accumulate+residual", "parallelism": f"dp{world} (clips sharded per rank, no data-path collective)",
                    "l2": "inputs (NV12 pool 0.88 GB + activations > 1 GB) exceed the 126 MB L2", "value_inputs": "decoded NV12 surfaces resident in HBM"},
         "clocks": clocks, "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_2cta_kernel", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                     "traffic": traffic.get("gemm_tcgen05_2cta"), "traffic_source": traffic.get("_source"),
                      "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)", "launches_per_step": gemm_n / args.steps,
                      "ms_per_step": gemm_ms / args.steps, "share_of_step": gemm_ms / args.steps / step_ms},
         "roofline_other": other,
@@ -313,6 +316,20 @@ def run_b200(args) -> None:
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic() -> dict:
+    """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/rNN_traffic.json, newest round); {} if none."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_traffic.json")))
+    if not files:
+        return {}
+    with open(files[-1]) as f:
+        d = json.load(f)
+    out = {k: v["traffic_bytes_per_launch"] for k, v in d["kernels"].items()}
+    out["_source"] = os.path.join("profiles", os.path.basename(files[-1]))
+    return out
 
 
 def cpu_layout(cores: int) -> tuple[int, int]:

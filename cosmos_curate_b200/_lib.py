@@ -90,6 +90,12 @@ SIGNATURES = {
     "cb_decoder_decode": (_i, [_vp, _vp, C.c_size_t, _pi32, _i, C.POINTER(SurfacePool), _pi32, C.POINTER(DecodeStats)]),
     "cb_decoder_decode_ex": (_i, [_vp, _vp, C.c_size_t, _pi32, _i, C.POINTER(SurfacePool), _pi32, _i, C.POINTER(DecodeStats)]),
     "cb_decoder_decode_thumbnails": (_i, [_vp, _vp, C.c_size_t, _i, _i, _vp, _i, C.POINTER(DecodeStats)]),
+    "cb_transnet_create": (_i, [_vp, C.POINTER(_vp)]),
+    "cb_transnet_destroy": (None, [_vp]),
+    "cb_transnet_set_tensor": (_i, [_vp, C.c_char_p, _vp, C.c_size_t]),
+    "cb_transnet_finalize": (_i, [_vp, _i]),
+    "cb_transnet_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "cb_transnet_predict": (_i, [_vp, _vp, _i, _vp, _vp]),
     "cb_gemm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cb_layernorm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "cb_attention_f16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

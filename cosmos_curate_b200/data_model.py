@@ -90,9 +90,24 @@ except Exception:  # noqa: BLE001
         errors: dict[str, str] = attrs.Factory(dict)
 
     @attrs.define
+    class VideoMetadata:  # data_model.py:392-410 (not decoder_utils.VideoMetadata: different field names)
+        size: int | None = None
+        height: int | None = None
+        width: int | None = None
+        framerate: float | None = None
+        num_frames: int | None = None
+        duration: float | None = None
+        video_codec: str | None = None
+        pixel_format: str | None = None
+        audio_codec: str | None = None
+        bit_rate_k: int | None = None
+        format_name: str | None = None
+
+    @attrs.define
     class Video:
         input_video: pathlib.Path | str
         relative_path: str = ""
+        metadata: VideoMetadata = attrs.Factory(VideoMetadata)
         encoded_data: LazyData = attrs.field(factory=LazyData, converter=LazyData.coerce)
         frame_array: LazyData = attrs.field(factory=LazyData, converter=LazyData.coerce)
         timestamps: np.ndarray | None = attrs.field(default=None, eq=False)
@@ -103,6 +118,25 @@ except Exception:  # noqa: BLE001
         clip_chunk_index: int = 0
         clip_stats: ClipStats = attrs.Factory(ClipStats)
         errors: dict[str, str] = attrs.Factory(dict)
+
+        def has_metadata(self) -> bool:  # data_model.py:536-552
+            m = self.metadata
+            return all([m.height, m.width, m.duration, m.framerate, m.num_frames, m.video_codec])
+
+        def populate_metadata(self) -> None:
+            """data_model.py:455-494, with the moov index instead of an ffprobe subprocess."""
+            from .runtime import mp4_index
+            from .sampling import video_metadata_from_index
+
+            data = self.encoded_data.resolve()
+            if data is None:
+                error_msg = "No video data available: encoded_data is None"
+                raise ValueError(error_msg)
+            e = video_metadata_from_index(mp4_index(data))
+            m = self.metadata
+            m.size = data.nbytes
+            m.height, m.width, m.framerate, m.num_frames, m.duration = e.height, e.width, e.fps, e.num_frames, e.video_duration
+            m.video_codec, m.pixel_format, m.audio_codec, m.bit_rate_k, m.format_name = e.video_codec, e.pixel_format, e.audio_codec, e.bit_rate_k, e.format_name
 
     @attrs.define
     class StagePerfStats:

@@ -60,7 +60,7 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.cb_launch_count(self.h))
 
-    PROF_CATEGORIES = ("preprocess", "gemm", "layernorm", "attention", "other")
+    PROF_CATEGORIES = ("preprocess", "gemm", "layernorm", "attention", "other", "conv")
 
     def profile_begin(self) -> None:
         check(self.lib.cb_profile_begin(self.h), "cb_profile_begin", self.h)
@@ -256,6 +256,54 @@ class VitTower:
                                              feat.data_ptr() if feat is not None else None, score.data_ptr() if score is not None else None,
                                              _stream_ptr()), "cb_vit_embed_surfaces", self.ctx.h)  # fmt: skip
         return emb, feat, score
+
+
+class ShotNet:
+    """cb_transnet_* wrapper: the reference state_dict in (its own key names), per-frame transition probabilities out."""
+
+    UNUSED_KEYS = ("cls_layer2.weight", "cls_layer2.bias")  # many-hot head: built by the reference, never used by forward()
+
+    def __init__(self, ctx: Context, state_dict: dict, max_windows: int = 16):
+        self.ctx, self.lib = ctx, ctx.lib
+        h = C.c_void_p()
+        check(self.lib.cb_transnet_create(ctx.h, C.byref(h)), "cb_transnet_create", ctx.h)
+        self.h = h
+        ctx._children.add(self)
+        for name, arr in state_dict.items():
+            if name in self.UNUSED_KEYS or name.endswith("num_batches_tracked"):
+                continue
+            a = np.ascontiguousarray(arr.detach().cpu().numpy() if isinstance(arr, torch.Tensor) else arr, dtype=np.float32)
+            check(self.lib.cb_transnet_set_tensor(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), a.size), f"cb_transnet_set_tensor({name})", ctx.h)
+        check(self.lib.cb_transnet_finalize(self.h, max_windows), "cb_transnet_finalize", ctx.h)
+        self.max_windows = max_windows
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cb_transnet_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def forward(self, windows: torch.Tensor) -> torch.Tensor:
+        """uint8 cuda [B, T, 27, 48, 3] -> fp32 cuda [B, T, 1] (the reference model's call signature, transnetv2.py:569-580)."""
+        assert windows.is_cuda and windows.dtype == torch.uint8 and windows.dim() == 5 and tuple(windows.shape[2:]) == (27, 48, 3), windows.shape
+        windows = windows.contiguous()
+        b, t = windows.shape[:2]
+        out = torch.empty((b, t, 1), dtype=torch.float32, device=windows.device)
+        check(self.lib.cb_transnet_forward(self.h, windows.data_ptr(), b, t, out.data_ptr(), _stream_ptr()), "cb_transnet_forward", self.ctx.h)
+        return out
+
+    def predict(self, frames: torch.Tensor) -> torch.Tensor:
+        """uint8 cuda [n, 27, 48, 3] (a whole video) -> fp32 cuda [n] stitched probabilities."""
+        assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and tuple(frames.shape[1:]) == (27, 48, 3), frames.shape
+        frames = frames.contiguous()
+        out = torch.empty((frames.shape[0],), dtype=torch.float32, device=frames.device)
+        check(self.lib.cb_transnet_predict(self.h, frames.data_ptr(), frames.shape[0], out.data_ptr(), _stream_ptr()), "cb_transnet_predict", self.ctx.h)
+        return out
 
 
 # ---- demux + NVDEC ------------------------------------------------------------------------------------

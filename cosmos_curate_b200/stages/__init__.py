@@ -5,11 +5,14 @@ Same-name drop-ins (constructor arguments, task mutations and error convention o
     ClipFrameExtractionStage    cosmos_curate/pipelines/video/clipping/clip_frame_extraction_stages.py:43-192
     VideoFrameExtractionStage   cosmos_curate/pipelines/video/clipping/frame_extraction_stages.py:71-204
     ImageCLIPEmbeddingStage     cosmos_curate/pipelines/image/embedding/image_embedding_stages.py:219-283
+    TransNetV2ClipExtractionStage  cosmos_curate/pipelines/video/clipping/transnetv2_extraction_stages.py:39-212
 New fused stage (replaces ClipFrameExtractionStage -> AestheticFilterStage [-> clip embedding] in one GPU pass):
     NvdecClipAestheticStage
+    NvdecShotDetectionStage      (VideoFrameExtractionStage -> TransNetV2ClipExtractionStage, frames stay in HBM)
 """
 
 from .aesthetic_filter import AestheticFilterStage  # noqa: F401
 from .fused_clip import NvdecClipAestheticStage  # noqa: F401
 from .frame_extraction import ClipFrameExtractionStage, VideoFrameExtractionStage  # noqa: F401
 from .image_embedding import ImageCLIPEmbeddingStage  # noqa: F401
+from .transnetv2_extraction import NvdecShotDetectionStage, TransNetV2ClipExtractionStage  # noqa: F401

@@ -54,7 +54,8 @@ unsigned long long cb_launch_count(cb_ctx* ctx);
 #define CB_PROF_LAYERNORM 2
 #define CB_PROF_ATTENTION 3
 #define CB_PROF_OTHER 4
-#define CB_PROF_CATEGORIES 5
+#define CB_PROF_CONV 5 /* shot-detection network (cb_transnet_*) */
+#define CB_PROF_CATEGORIES 6
 int cb_profile_begin(cb_ctx* ctx);
 int cb_profile_end(cb_ctx* ctx, void* stream, float* ms_by_category, int* launches_by_category, int n_categories);
 
@@ -195,6 +196,28 @@ int cb_decoder_decode_ex(cb_decoder* dec, const uint8_t* data, size_t size, cons
  * convert, resize, concat) as used by VideoFrameExtractionStage for the 27x48 shot-detection frames. */
 int cb_decoder_decode_thumbnails(cb_decoder* dec, const uint8_t* data, size_t size, int out_w, int out_h, uint8_t* out,
                                  int max_frames, cb_decode_stats* stats);
+
+/* ---- shot-transition network (TransNetV2) -------------------------------------------------------- */
+/* Replaces _TransNetV2.forward (cosmos_curate/models/transnetv2.py:103-148, rf=16 rl=3 rs=2 rd=1024 with frame
+ * similarity + colour histograms, the only configuration the reference instantiates, :563) and the window
+ * stitching of _get_predictions (pipelines/video/clipping/transnetv2_extraction_stages.py:215-264).  fp32 throughout. */
+typedef struct cb_transnet cb_transnet;
+int cb_transnet_create(cb_ctx* ctx, cb_transnet** out);
+void cb_transnet_destroy(cb_transnet* tn);
+/* Upload one tensor of the reference state_dict under its own key (host fp32, `count` elements), e.g.
+ * "SDDCNN.0.DDCNN.1.Conv3D_4.layers.0.weight", "SDDCNN.2.DDCNN.0.bn.running_var", "fc1.weight",
+ * "cls_layer1.bias".  cls_layer2.* and bn.num_batches_tracked are not used by forward() and are not accepted. */
+int cb_transnet_set_tensor(cb_transnet* tn, const char* name, const float* data, size_t count);
+/* Folds BatchNorm, repacks the convolution weights and sizes the workspace for batches of up to max_windows
+ * 100-frame windows (about 150 MB per window). */
+int cb_transnet_finalize(cb_transnet* tn, int max_windows);
+/* The model call: windows = device uint8 [n_windows][frames_per_window][27][48][3] RGB, 1 <= frames_per_window <= 100;
+ * prob_out = device fp32 [n_windows][frames_per_window], sigmoid(one_hot) of transnetv2.py:142-148. */
+int cb_transnet_forward(cb_transnet* tn, const uint8_t* windows, int n_windows, int frames_per_window, float* prob_out, void* stream);
+/* A whole video: frames = device uint8 [n_frames][27][48][3]; prob_out = device fp32 [n_frames], the concatenation of
+ * one_hot[0, 25:75] over the reference's 100-frame / stride-50 windows (first window front-padded with frame 0,
+ * the tail windows left short exactly as _get_batches leaves them).  Thresholding (prob > threshold) is the caller's. */
+int cb_transnet_predict(cb_transnet* tn, const uint8_t* frames, int n_frames, float* prob_out, void* stream);
 
 /* ---- building blocks exported for the parity tests ------------------------------------------------ */
 #define CB_EPI_NONE 0       /* C = A W^T (+ bias) */

@@ -13,6 +13,8 @@ Files written (all small):
   clip_tiny_ref.npz       reference _CLIPImageEmbeddings.__call__ (clip.py:64-74), unmodified class,
                           on a tiny seeded CLIPModel saved with save_pretrained (weights included)
   aesthetic_ref.npz       reference aesthetics.MLP (aesthetics.py:30-66) seeded state_dict + outputs
+  transnetv2_ref.npz      reference _TransNetV2 on seeded weights (oracle.transnetv2.random_state_dict) + the reference's
+                          _get_predictions / _get_scenes / _get_filtered_scenes outputs
   siglip_tiny_hf.npz      transformers SiglipVisionModel tiny seeded (stand-in; not in the reference)
 
 Test infrastructure only (see oracle/__init__.py).
@@ -212,6 +214,74 @@ def gen_siglip() -> None:
     print("siglip_tiny_hf.npz")
 
 
+def gen_transnet() -> None:
+    """Reference _TransNetV2 (transnetv2.py:39-148) with the seeded state_dict + the reference's shot-logic functions."""
+    from oracle import transnetv2 as tn
+
+    mod = ref_import.transnetv2_module()
+    fns = ref_import.transnetv2_stage_functions()
+    sd = tn.random_state_dict(seed=3)
+    model = mod._TransNetV2()
+    missing = model.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model.eval()
+    out: dict[str, np.ndarray] = {"seed": np.array(3)}
+    video = tn.synthetic_frames(170, seed=11, cuts=(40, 97, 131))
+    out["video"] = video
+    with torch.no_grad():
+        for name, w in (("full", tn.windows(video)[1]), ("short95", tn.windows(video)[2]), ("short45", tn.windows(video)[3] if len(tn.windows(video)) > 3 else video[:45]),
+                        ("tiny7", video[:7])):  # fmt: skip
+            out[f"win_{name}"] = w
+            out[f"prob_{name}"] = model(torch.from_numpy(w)[None]).numpy()[0, :, 0]
+    # _get_predictions moves each window with .cuda(); on this CPU-only box that call is made a no-op for the run
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self  # type: ignore[method-assign]
+    try:
+        with torch.no_grad():
+            for n in (170, 120, 100, 51, 10):
+                probs = []
+
+                def spy(x, probs=probs):
+                    y = model(x)
+                    probs.append(y[0, 25:75, 0].numpy())
+                    return y
+
+                thr = 0.5
+                pred = fns["_get_predictions"](spy, video[:n], thr)
+                out[f"pred_{n}"] = pred
+                out[f"probs_{n}"] = np.concatenate(probs)[:n]
+    finally:
+        torch.Tensor.cuda = orig  # type: ignore[method-assign]
+    out["pred_threshold"] = np.array(0.5)
+    # shot logic on seeded 0/1 tracks
+    rng = np.random.default_rng(5)
+    cases = []
+    tracks = [np.zeros(300, np.uint8), np.ones(50, np.uint8)]
+    for n in (60, 300, 1000, 4000):
+        for density in (0.002, 0.01, 0.05):
+            t = (rng.random(n) < density).astype(np.uint8)
+            tracks.append(t)
+            t2 = t.copy()
+            t2[0] = 1
+            t2[-1] = 1
+            tracks.append(t2)
+    for ti, t in enumerate(tracks):
+        out[f"track_{ti}"] = t
+        for entire in (True, False):
+            sc = fns["_get_scenes"](t.reshape(-1, 1), entire_scene_as_clip=entire)
+            key = f"scenes_{ti}_{int(entire)}"
+            out[key] = sc
+            for ci, (mn, mx, mode, crop) in enumerate([(48, 1440, "stride", 12), (60, 1800, "truncate", 15), (None, 100, "stride", None), (48, None, "truncate", 0),
+                                                        (10, 50, "stride", 3), (None, None, "truncate", None)]):  # fmt: skip
+                fs = fns["_get_filtered_scenes"](sc.copy(), min_length=mn, max_length=mx, max_length_mode=mode, crop_length=crop)
+                out[f"{key}_f{ci}"] = np.asarray(fs, dtype=np.int32).reshape(-1, 2)
+                cases.append([ti, int(entire), ci])
+    out["filter_cfgs"] = np.array([[48, 1440, 1, 12], [60, 1800, 0, 15], [-1, 100, 1, -1], [48, -1, 0, 0], [10, 50, 1, 3], [-1, -1, 0, -1]], dtype=np.int32)
+    out["n_tracks"] = np.array(len(tracks))
+    np.savez_compressed(OUT / "transnetv2_ref.npz", **out)
+    print("transnetv2_ref.npz", {k: v.shape for k, v in out.items() if k.startswith("prob")})
+
+
 def main() -> None:
     assert ref_import.available(), "needs /root/reference (build container)"
     OUT.mkdir(parents=True, exist_ok=True)
@@ -219,6 +289,7 @@ def main() -> None:
     gen_clip()
     gen_aesthetic()
     gen_siglip()
+    gen_transnet()
 
 
 if __name__ == "__main__":

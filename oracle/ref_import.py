@@ -75,3 +75,34 @@ def aesthetics_module():
     import importlib
 
     return importlib.import_module("cosmos_curate.models.aesthetics")
+
+
+def transnetv2_module():
+    _install_stubs()
+    import importlib
+
+    return importlib.import_module("cosmos_curate.models.transnetv2")
+
+
+def transnetv2_stage_functions() -> dict:
+    """The module-level shot-logic functions of transnetv2_extraction_stages.py, executed from the reference's source.
+
+    The module itself cannot be imported here (its stage base class needs ray + the cosmos-xenna Rust extension), so the
+    function definitions are parsed out of the file under /root/reference and compiled as they stand."""
+    import ast
+    import math
+    from collections.abc import Callable, Generator
+    from typing import Literal
+
+    import numpy as np
+    import numpy.typing as npt
+    import torch
+
+    path = REFERENCE_ROOT / "cosmos_curate" / "pipelines" / "video" / "clipping" / "transnetv2_extraction_stages.py"
+    tree = ast.parse(path.read_text())
+    wanted = {"_get_batches", "_get_predictions", "_get_scenes", "_get_filtered_scenes", "_crop_scenes", "_create_spans"}
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {n.name for n in body} == wanted
+    ns = {"np": np, "npt": npt, "torch": torch, "math": math, "Callable": Callable, "Generator": Generator, "Literal": Literal}
+    exec(compile(ast.Module(body=body, type_ignores=[]), str(path), "exec"), ns)  # noqa: S102 - reference code, build container only
+    return {k: ns[k] for k in wanted}

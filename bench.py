@@ -161,10 +161,9 @@ def run_b200(args) -> None:
     fpc = len(plans[0])
     frames_per_step = cps * fpc
     tower = VitTower(ctx, cfg.to_dict(), W.seeded_weights(cfg, 0), max_batch=frames_per_step, aesthetic=W.seeded_aesthetic(cfg.proj_dim, 0))
-    pools = [alloc_nv12_pool(ctx, frames_per_step, FRAME_W, FRAME_H) for _ in range(2)]
+    pools = [alloc_nv12_pool(ctx, frames_per_step, FRAME_W, FRAME_H) for _ in range(3)]
     n_dec = args.decoders
     tp = ThreadPoolExecutor(max_workers=n_dec)       # one NVDEC session per worker thread (thread-local, reused across clips)
-    coord = ThreadPoolExecutor(max_workers=1)         # runs "decode step i+1" while the tower works on step i
     tls = threading.local()
     all_decoders = []
     host_emb = torch.empty((frames_per_step, cfg.proj_dim), dtype=torch.float32).pin_memory()
@@ -178,12 +177,12 @@ def run_b200(args) -> None:
             all_decoders.append(d)
         return d
 
-    def decode_step(pool, seek=False):
-        def work(j):
-            k = step_clips[j]
-            return my_decoder().decode(clips[k], plans[k], pool, np.arange(j * fpc, (j + 1) * fpc, dtype=np.int32), seek_keyframes=seek)["frames_decoded"]
+    def decode_clip(j, pool, seek):
+        k = step_clips[j]
+        return my_decoder().decode(clips[k], plans[k], pool, np.arange(j * fpc, (j + 1) * fpc, dtype=np.int32), seek_keyframes=seek)["frames_decoded"]
 
-        return sum(tp.map(work, range(cps)))
+    def decode_step(pool, seek=False):
+        return sum(tp.map(lambda j: decode_clip(j, pool, seek), range(cps)))
 
     def decode_ceiling(reps: int) -> float:
         """All NVDEC sessions decoding whole clips, surfaces discarded: frames/s."""
@@ -229,15 +228,23 @@ def run_b200(args) -> None:
     value = world * cps * args.steps / dev_s
 
     # ---- end-to-end measurement (e2e): host mp4 bytes -> NVDEC -> preprocess -> tower -> host results.
-    # Decode of step i+1 (NVDEC engines + host parsing threads) overlaps the tower of step i (SMs); two surface pools.
+    # Decode of steps i+1, i+2 (NVDEC engines + host parsing threads) overlaps the tower of step i (SMs); three surface pools.
     def e2e_run(n_steps: int, seek: bool):
-        fut = coord.submit(decode_step, pools[0], seek)
+        # three surface pools: the clips of steps i+1 and i+2 are queued on the decode threads while the tower works on step i,
+        # so no NVDEC session idles at a step boundary waiting for the slowest clip of the step
+        futs = {}
+
+        def submit(i):
+            futs[i] = [tp.submit(decode_clip, j, pools[i % 3], seek) for j in range(cps)]
+
+        for i in range(min(2, n_steps)):
+            submit(i)
         decoded = 0
         for i in range(n_steps):
-            decoded += fut.result()
-            if i + 1 < n_steps:
-                fut = coord.submit(decode_step, pools[(i + 1) & 1], seek)
-            emb, _, score = tower.embed_pool(pools[i & 1])
+            decoded += sum(f.result() for f in futs.pop(i))
+            if i + 2 < n_steps:
+                submit(i + 2)  # pool (i+2)%3 was last read by the tower of step i-1, synchronised below
+            emb, _, score = tower.embed_pool(pools[i % 3])
             host_emb.copy_(emb, non_blocking=True)
             host_score.copy_(score, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -261,7 +268,7 @@ def run_b200(args) -> None:
         try:
             e2e = e2e_measure(seek=False)
             e2e["note"] = ("every frame up to the last sampled one is decoded (reference semantics, decoder_utils.py:439-455); synthetic I_PCM + "
-                           "motion-only P pictures; decode of step i+1 overlaps the tower of step i")
+                           "motion-only P pictures; decode of the next two steps overlaps the tower of step i")
             e2e_sparse = e2e_measure(seek=True)
             e2e_sparse["note"] = "CB_DECODE_SEEK_SYNC: only GOPs holding sampled frames are decoded (identical frames); closed GOP = 30, 1 fps sampling"
             ceil_fps = decode_ceiling(2 * n_dec)
@@ -269,6 +276,12 @@ def run_b200(args) -> None:
                        "e2e_fraction_of_decode_ceiling": (e2e["decoded_frames_per_sec"] / world) / ceil_fps if ceil_fps > 0 else None}
         except Exception as exc:  # noqa: BLE001 - e.g. libnvcuvid missing on the box: report it, keep the device-resident numbers
             e2e_error = f"{type(exc).__name__}: {exc}"
+    shot = None
+    if rank == 0 and not args.no_shots:
+        try:
+            shot = shot_detection_measure(ctx, torch)
+        except Exception as exc:  # noqa: BLE001
+            shot = {"error": f"{type(exc).__name__}: {exc}"}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -309,6 +322,12 @@ def run_b200(args) -> None:
         "roofline_other": other,
         "e2e": e2e, "e2e_keyframe_seek": e2e_sparse, "decode_roofline": ceiling,
     }  # fmt: skip
+    if shot is not None:
+        if "tflops_fp32" in shot and clocks:
+            peak = ctx.device_info()["sm_count"] * 128 * 2 * clocks["sm_max_mhz"] * 1e6 / 1e12  # FFMA lanes x 2 flop x clock
+            shot["fp32_peak_tflops"] = peak
+            shot["frac_of_fp32_peak"] = shot["tflops_fp32"] / peak
+        line["shot_detection"] = shot
     if e2e_error:
         line["e2e_error"] = e2e_error
     if world == 1 and not args.no_cpu_baseline:
@@ -316,6 +335,43 @@ def run_b200(args) -> None:
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def shot_flops_per_window(frames: int = 100) -> float:
+    """2*M*N*K over the convolutions and Linear layers of the shot network for one window (transnetv2.py:66-100)."""
+    total = 0.0
+    hw = [(27, 48), (13, 24), (6, 12)]
+    for s in range(3):
+        f = 16 << s
+        m = frames * hw[s][0] * hw[s][1]
+        for cin in ((3 if s == 0 else 2 * f), 4 * f):  # first block reads the previous stack (4 * f/2 channels), second block 4f
+            total += 2.0 * m * (8 * f) * (9 * cin) + 2.0 * m * (4 * f) * (6 * f)
+    return total + 2.0 * frames * (4864 * 1024 + 448 * 128 + 1024)
+
+
+def shot_detection_measure(ctx, torch, n_frames: int = 9000, reps: int = 3) -> dict:
+    """Secondary row: the fp32 shot-transition network over one 5-minute video of resident 27x48 thumbnails."""
+    from cosmos_curate_b200.models.transnetv2 import seeded_state_dict
+    from cosmos_curate_b200.runtime import ShotNet
+
+    net = ShotNet(ctx, seeded_state_dict(0), max_windows=16)
+    frames = torch.randint(0, 256, (n_frames, 27, 48, 3), dtype=torch.uint8, device=f"cuda:{ctx.device}")
+    for _ in range(2):
+        net.predict(frames)
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(reps):
+        net.predict(frames)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    windows = -(-n_frames // 50)
+    net.close()
+    return {"workload": f"{n_frames} frames 27x48 RGB (5 min @ 30 fps) resident in HBM, {windows} windows of 100 frames / stride 50, fp32",
+            "frames_per_sec": n_frames / ms * 1e3, "ms_per_video": ms, "ms_per_window": ms / windows, "gflop_per_window": shot_flops_per_window() / 1e9,
+            "tflops_fp32": windows * shot_flops_per_window() / ms / 1e9, "gpu_launches": (ctx.launch_count() - l0) // reps}  # fmt: skip
 
 
 def ncu_traffic() -> dict:
@@ -371,8 +427,9 @@ def main() -> None:
     ap.add_argument("--clips-per-step", type=int, default=24)
     ap.add_argument("--distinct-clips", type=int, default=4)
     ap.add_argument("--decoders", type=int, default=12, help="concurrent NVDEC sessions per GPU (7 engines on B200)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-clips", type=int, default=2, help="clips per step of the reference arm (bounded sample)")
+    ap.add_argument("--no-shots", action="store_true", help="skip the shot-detection secondary measurement")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -393,7 +393,11 @@ int cb_decoder_create(cb_ctx* ctx, cb_decoder** out) {
   if (rc) return rc;
   cb_decoder* d = new cb_decoder();
   d->ctx = ctx, d->api = api;
-  if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  // highest priority: the post-processing kernel cuvidMapVideoFrame launches and the two surface copies are tiny, and the
+  // decode surface is only handed back to NVDEC once they are done - they must not queue behind the tower's persistent CTAs
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&d->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     delete d;
     return cb::fail(ctx, CB_ERR_CUDA, "decoder_create: stream creation failed");
   }

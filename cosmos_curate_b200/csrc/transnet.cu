@@ -32,24 +32,30 @@ struct ConvGemmArgs {
   int T, H, W;  // frames per window, frame size (a row of the matrix is one (frame,row,col) position)
   int mode;     // 0 rows as they are, 1 = 3x3 spatial taps, 2 = 3 temporal taps with dilation `dil`
   int dil, relu;
-  int z_in_coff, z_out_coff;  // per-blockIdx.z increments (branch batching)
+  int z_in_coff, z_out_coff;  // per-blockIdx.z increments (the four dilation branches in one launch)
+  int z_dil_shift;            // dilation = dil << blockIdx.z
   long long z_w;
 };
 
-// C[M,N] = gather(A)[M, taps*cin] * Wt[taps*cin, N]; 256 threads, 128 x (16*TN) tile, K walked in chunks of BKC channels
-// of one tap.  Register-staged double buffering: the next chunk's global loads are in flight during the FMAs.
-template <int TN, int BKC>
+// C[M,N] = gather(A)[M, taps*cin] * Wt[taps*cin, N].  256 threads as (256/CT) x CT; each thread owns an 8 x TN block, so the
+// CTA tile is BM = 8*256/CT rows by BN = CT*TN columns: 128x128 for the wide spatial convs, 512x16 / 256x32 / 256x64 for the
+// narrow temporal ones (a 128x16 tile would spend its time on shared-memory loads: 8 FMAs per 3 loads).  K is walked in
+// chunks of BKC channels of one tap.  Register-staged double buffering: the next chunk's global loads are in flight during
+// the FMAs.  The k order of every output's sum does not depend on the tile shape, so all variants give identical bits.
+template <int CT, int TN, int BKC>
 __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvGemmArgs a) {
-  constexpr int TM = 8, BM = 128, BN = 16 * TN, LDA = BM + 4;
+  constexpr int TM = 8, RT = 256 / CT, BM = RT * TM, BN = CT * TN, LDA = BM + 4, HALF_M = BM / 2, HALF_N = BN / 2;
   constexpr int A_F4 = BM * BKC / 4, A_IT = (A_F4 + 255) / 256, B_F4 = BKC * BN / 4, B_IT = (B_F4 + 255) / 256;
   constexpr int KC4 = BKC / 4, BN4 = BN / 4;
+  static_assert(TN == 4 || TN == 8, "TN");
   __shared__ __align__(16) float As[2][BKC][LDA];
   __shared__ __align__(16) float Bs[2][BKC][BN];
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int tid = threadIdx.x, ty = tid / CT, tx = tid % CT;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, z = blockIdx.z;
   const float* __restrict__ in = a.in + a.in_coff + z * a.z_in_coff;
   const float* __restrict__ wt = a.w + (long long)z * a.z_w;
   const int HW = a.H * a.W;
+  const int dil = a.dil << (a.z_dil_shift ? z : 0);
 
   int a_m[A_IT], a_t[A_IT], a_h[A_IT], a_w[A_IT], a_row[A_IT], a_c4[A_IT];
   bool a_ok[A_IT];
@@ -77,7 +83,7 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvGemmArgs a) {
         ok = ok && (unsigned)(a_h[it] + dh) < (unsigned)a.H && (unsigned)(a_w[it] + dw) < (unsigned)a.W;
         src += dh * a.W + dw;
       } else if (a.mode == 2) {
-        const int dt = (tap - 1) * a.dil;
+        const int dt = (tap - 1) * dil;
         ok = ok && (unsigned)(a_t[it] + dt) < (unsigned)a.T;
         src += (long long)dt * HW;
       }
@@ -121,20 +127,13 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvGemmArgs a) {
     for (int k = 0; k < BKC; ++k) {
       float av[TM], bv[TN];
       const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][HALF_M + ty * 4]);
       av[0] = a0.x, av[1] = a0.y, av[2] = a0.z, av[3] = a0.w, av[4] = a1.x, av[5] = a1.y, av[6] = a1.z, av[7] = a1.w;
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      bv[0] = b0.x, bv[1] = b0.y, bv[2] = b0.z, bv[3] = b0.w;
       if constexpr (TN == 8) {
-        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
-        bv[0] = b0.x, bv[1] = b0.y, bv[2] = b0.z, bv[3] = b0.w, bv[4] = b1.x, bv[5] = b1.y, bv[6] = b1.z, bv[7] = b1.w;
-      } else if constexpr (TN == 4) {
-        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-        bv[0] = b0.x, bv[1] = b0.y, bv[2] = b0.z, bv[3] = b0.w;
-      } else if constexpr (TN == 2) {
-        const float2 b0 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 2]);
-        bv[0] = b0.x, bv[1] = b0.y;
-      } else {
-        bv[0] = Bs[buf][k][tx];
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][HALF_N + tx * 4]);
+        bv[4] = b1.x, bv[5] = b1.y, bv[6] = b1.z, bv[7] = b1.w;
       }
 #pragma unroll
       for (int i = 0; i < TM; ++i)
@@ -147,18 +146,17 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvGemmArgs a) {
 
   // epilogue: BatchNorm scale/shift or bias, optional ReLU
   const int ocoff = a.out_coff + z * a.z_out_coff;
-  auto col_of = [&](int j) { return TN == 8 ? tx * 4 + (j & 3) + (j >> 2) * 64 : tx * TN + j; };
   float sc[TN], sh[TN];
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
-    const int n = n0 + col_of(j);
+    const int n = n0 + tx * 4 + (j & 3) + (j >> 2) * HALF_N;
     const bool ok = n < a.N;
     sc[j] = (ok && a.scale) ? __ldg(a.scale + ocoff + n) : 1.f;
     sh[j] = (ok && a.shift) ? __ldg(a.shift + ocoff + n) : 0.f;
   }
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
-    const int m = m0 + ty * 4 + (i & 3) + (i >> 2) * 64;
+    const int m = m0 + ty * 4 + (i & 3) + (i >> 2) * HALF_M;
     if (m >= a.M) continue;
     float* orow = a.out + (long long)m * a.out_ld + ocoff + n0;
     float v[TN];
@@ -167,15 +165,9 @@ __global__ void __launch_bounds__(256) conv_gemm_kernel(const ConvGemmArgs a) {
       float y = a.scale ? fmaf(acc[i][j], sc[j], sh[j]) : acc[i][j] + sh[j];
       v[j] = a.relu ? fmaxf(y, 0.f) : y;
     }
+    if (n0 + tx * 4 < a.N) *reinterpret_cast<float4*>(orow + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
     if constexpr (TN == 8) {
-      if (n0 + tx * 4 < a.N) *reinterpret_cast<float4*>(orow + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
-      if (n0 + 64 + tx * 4 < a.N) *reinterpret_cast<float4*>(orow + 64 + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } else if constexpr (TN == 4) {
-      if (n0 + tx * 4 < a.N) *reinterpret_cast<float4*>(orow + tx * 4) = make_float4(v[0], v[1], v[2], v[3]);
-    } else if constexpr (TN == 2) {
-      if (n0 + tx * 2 < a.N) *reinterpret_cast<float2*>(orow + tx * 2) = make_float2(v[0], v[1]);
-    } else {
-      if (n0 + tx < a.N) orow[tx] = v[0];
+      if (n0 + HALF_N + tx * 4 < a.N) *reinterpret_cast<float4*>(orow + HALF_N + tx * 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
   }
 }
@@ -371,23 +363,25 @@ static std::vector<float> transposed(const std::vector<float>& w, int out, int i
   return t;
 }
 
-template <int TN, int BKC>
+template <int CT, int TN, int BKC>
 static int launch_conv(cb_ctx* ctx, const ConvGemmArgs& a, int zdim, cudaStream_t st) {
-  dim3 grid((a.M + 127) / 128, (a.N + 16 * TN - 1) / (16 * TN), zdim);
+  constexpr int BM = 8 * 256 / CT, BN = CT * TN;
+  dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, zdim);
   mark_launch(ctx, CB_PROF_CONV, st);
-  conv_gemm_kernel<TN, BKC><<<grid, 256, 0, st>>>(a);
+  conv_gemm_kernel<CT, TN, BKC><<<grid, 256, 0, st>>>(a);
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }
 
 static int conv_dispatch(cb_ctx* ctx, const ConvGemmArgs& a, int zdim, cudaStream_t st) {
+  if (a.N % 4) return fail(ctx, CB_ERR_UNSUPPORTED, "transnet: N=%d is not a multiple of 4", a.N);
   if (a.cin % 16 == 0) {
-    if (a.N >= 128) return launch_conv<8, 16>(ctx, a, zdim, st);
-    if (a.N >= 64) return launch_conv<4, 16>(ctx, a, zdim, st);
-    if (a.N >= 32) return launch_conv<2, 16>(ctx, a, zdim, st);
-    return launch_conv<1, 16>(ctx, a, zdim, st);
+    if (a.N >= 128) return launch_conv<16, 8, 16>(ctx, a, zdim, st);  // 128 x 128
+    if (a.N >= 64) return launch_conv<8, 8, 16>(ctx, a, zdim, st);    // 256 x 64
+    if (a.N >= 32) return launch_conv<8, 4, 16>(ctx, a, zdim, st);    // 256 x 32
+    return launch_conv<4, 4, 8>(ctx, a, zdim, st);                    // 512 x 16
   }
-  if (a.cin % 4 == 0 && a.N >= 128) return launch_conv<8, 4>(ctx, a, zdim, st);
+  if (a.cin % 4 == 0 && a.N >= 128) return launch_conv<16, 8, 4>(ctx, a, zdim, st);
   return fail(ctx, CB_ERR_UNSUPPORTED, "transnet: no conv kernel for cin=%d N=%d", a.cin, a.N);
 }
 
@@ -422,14 +416,8 @@ static int run_windows(cb_transnet* tn, const uint8_t* frames, const int* h_firs
       t.M = M, t.N = f, t.cin = 2 * f, t.in_ld = 8 * f, t.in_coff = 0, t.w_ld = f, t.out_ld = C, t.out_coff = 0;
       t.T = T, t.H = H, t.W = W, t.mode = 2, t.relu = k.relu ? 1 : 0;
       t.z_in_coff = 2 * f, t.z_out_coff = f, t.z_w = (long long)3 * 2 * f * f;
-      // one launch per branch: the dilation differs
-      for (int br = 0; br < kBranches; ++br) {
-        ConvGemmArgs tb = t;
-        tb.dil = 1 << br;
-        tb.in_coff = br * 2 * f, tb.out_coff = br * f, tb.w = k.w2 + (long long)br * t.z_w;
-        tb.z_in_coff = tb.z_out_coff = 0, tb.z_w = 0;
-        if ((rc = conv_dispatch(ctx, tb, 1, st))) return rc;
-      }
+      t.dil = 1, t.z_dil_shift = 1;  // branch z: dilation 1 << z, its own channel slices and weights
+      if ((rc = conv_dispatch(ctx, t, kBranches, st))) return rc;
       x = outs[b], x_ld = C;
     }
     const int Hp = H / 2, Wp = W / 2;

@@ -192,7 +192,7 @@ def test_stages_end_to_end_on_the_fixture(golden):
     assert grabbed["frames"].shape == (240, 27, 48, 3)
     assert len(v2.clips) > 0
     assert [(c.uuid, c.span) for c in v2.clips] == [(c.uuid, c.span) for c in vf.clips]
-    assert "TransNetV2ClipExtractionStage" in two[0].stage_perf and "NvdecShotDetectionStage" in fused[0].stage_perf
+    assert "_Spy" in two[0].stage_perf and "NvdecShotDetectionStage" in fused[0].stage_perf
     assert not v2.frame_array and not vf.frame_array
     # oracle on the same thumbnails
     sd = tn.random_state_dict(seed)

@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence for the bench step (run under gpurun, 1 GPU).  Outputs under gpurun_out/.
 mkdir -p gpurun_out
-B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --distinct-clips 1"
+B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-shots --distinct-clips 1"
 # every launch of warm-up + one timed step with its device time (cold-cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu_launches.log 2>&1
 for k in gemm_tcgen05_2cta attention_kernel layernorm_kernel; do

@@ -1,0 +1,397 @@
+// softmax(Q K^T / sqrt(d)) V on the tcgen05 tensor cores for the ViT-L/14 shape class: head_dim 64, 129..257 tokens.
+//
+// 257 = 2 * 128 + 1: the first 256 tokens map onto the tensor cores with no padding at all - two 128-row query tiles
+// against one 256-key tile (S = Q K^T is ONE UMMA 128x256x64 per query tile; no online softmax, every key of the row is
+// in TMEM at once) - and token 256 is folded in on the SIMT side: its key/value as one extra column per row, its query
+// row by a dedicated warp.  Persistent CTAs (one per SM) loop over (image, head) pairs.
+//
+// Warp roles (352 threads):
+//   warp 0      TMA producer: Q tiles (2 x 16 KB), K (32 KB), V (32 KB, double buffered) from the [n*T][3*hidden] QKV matrix
+//   warp 1      MMA issuer:   S_g = Q_g K^T  (tcgen05.mma kind::f16, M128 N256 K64) and O_g += P_g[:, chunk] V[chunk]
+//                             (M128 N64 K64 per 64-key chunk; V is consumed straight from its [key][dim] rows as an
+//                             MN-major B operand, no transpose pass)
+//   warps 2-5   softmax group 0 (query rows 0..127), warps 6-9 softmax group 1 (rows 128..255): thread = one row.
+//               pass 1: row max over the 256 TMEM columns (+ the extra key), pass 2: exp2 -> fp16 P chunks written to
+//               shared memory in the 128-byte-swizzled K-major layout the UMMA A operand wants (2 x 16 KB ring per
+//               group, so the exp of chunk c+1 overlaps the MMA of chunk c), epilogue: O / rowsum -> fp16 -> global.
+//   warp 10     query row 256 entirely on SIMT (257 dot products of 64 + softmax + 257-term weighted sum from smem K/V).
+// TMEM: 512 columns = S_0 | S_1 (256 fp32 columns each); O_g reuses columns 0..63 of S_g once pass 2 has consumed them.
+// The two groups run half a phase apart, so one group's exponentials (MUFU) overlap the other group's MMAs.
+#include <cstdlib>
+#include <cstring>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace cb {
+
+constexpr int kTcThreads = 352;
+constexpr int kTileBytes = 128 * 128;       // 128 rows x 64 fp16, SW128
+constexpr int kKVBytes = 2 * kTileBytes;    // 256 rows
+constexpr int kOffQ = 0;                    // 2 tiles
+constexpr int kOffK = 2 * kTileBytes;       // 256 keys
+constexpr int kOffV = kOffK + kKVBytes;     // 2 buffers x 256 keys
+constexpr int kOffP = kOffV + 2 * kKVBytes; // [group][2] x 128 rows x 64 keys
+constexpr int kOffPx = kOffP + 4 * kTileBytes;
+constexpr int kOffBar = kOffPx + 1024;
+constexpr int kTcSmem = kOffBar + 256 + 1024 /* alignment slack */;
+
+struct AttnTcArgs {
+  const __half* qkv;
+  __half* out;
+  int tokens, heads, n_units;  // n_units = images * heads
+  float scale_log2e;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// MN-major B operand, SW128: rows are K (keys), each row = 64 contiguous N elements (128 B); 8-row groups 1024 B apart.
+// LBO (stride between 64-element column blocks along N) is irrelevant for N = 64; both strides are set to 1024 B.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sQ = smem + kOffQ;
+  uint8_t* sK = smem + kOffK;
+  uint8_t* sV = smem + kOffV;
+  uint8_t* sP = smem + kOffP;
+  float* px = reinterpret_cast<float*>(smem + kOffPx);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t *q_full = bars, *q_free = bars + 2, *k_full = bars + 4, *k_free = bars + 5, *v_full = bars + 6, *v_free = bars + 8;
+  uint64_t *s_ready = bars + 10, *s_free = bars + 12, *o_ready = bars + 14, *p_ready = bars + 16 /*[g*2+b]*/, *p_free = bars + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = a.tokens, hidden = a.heads * 64;
+  const bool has_extra = T == 257;
+  const int t_mma = T < 256 ? T : 256;  // keys / query rows living in the tensor-core tiles
+  const size_t row_stride = (size_t)3 * hidden;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1), mbar_init(&q_free[i], 4), mbar_init(&v_full[i], 1), mbar_init(&v_free[i], 2);
+      mbar_init(&s_ready[i], 1), mbar_init(&s_free[i], 4), mbar_init(&o_ready[i], 1);
+    }
+    mbar_init(k_full, 1), mbar_init(k_free, 2);
+    for (int i = 0; i < 4; ++i) mbar_init(&p_ready[i], 4), mbar_init(&p_free[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) tma_prefetch_desc(&map_qkv);
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer
+      int it = 0;
+      for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
+        const int img = u / a.heads, h = u - img * a.heads, row0 = img * T, vb = it & 1;
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&q_free[g], (it & 1) ^ 1);
+          mbar_expect_tx(&q_full[g], kTileBytes);
+          tma_load_2d(sQ + g * kTileBytes, &map_qkv, &q_full[g], h * 64, row0 + g * 128);
+        }
+        mbar_wait(k_free, (it & 1) ^ 1);
+        mbar_expect_tx(k_full, kKVBytes);
+        tma_load_2d(sK, &map_qkv, k_full, hidden + h * 64, row0);
+        tma_load_2d(sK + kTileBytes, &map_qkv, k_full, hidden + h * 64, row0 + 128);
+        mbar_wait(&v_free[vb], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&v_full[vb], kKVBytes);
+        tma_load_2d(sV + vb * kKVBytes, &map_qkv, &v_full[vb], 2 * hidden + h * 64, row0);
+        tma_load_2d(sV + vb * kKVBytes + kTileBytes, &map_qkv, &v_full[vb], 2 * hidden + h * 64, row0 + 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, 256, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, 0) | (1u << 16);  // B is MN-major
+      int it = 0;
+      for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
+        const int vb = it & 1;
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&q_full[g], it & 1);
+          if (g == 0) mbar_wait(k_full, it & 1);
+          mbar_wait(&s_free[g], (it & 1) ^ 1);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(smem_u32(sQ + g * kTileBytes)), db = umma_desc_sw128(smem_u32(sK));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + (uint32_t)(g * 256), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_qk, k != 0);
+          umma_commit(&s_ready[g]);
+        }
+        umma_commit(k_free);
+        mbar_wait(&v_full[vb], (it >> 1) & 1);
+        tc_fence_after();
+        for (int c = 0; c < 4; ++c) {
+          for (int g = 0; g < 2; ++g) {
+            const int b = c & 1, use = it * 2 + (c >> 1);
+            mbar_wait(&p_ready[g * 2 + b], use & 1);
+            tc_fence_after();
+            const uint64_t da = umma_desc_sw128(smem_u32(sP + (g * 2 + b) * kTileBytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t db = umma_desc_sw128_mn(smem_u32(sV + vb * kKVBytes + (c * 64 + k * 16) * 128));
+              umma_f16(tmem_base + (uint32_t)(g * 256), da + (uint64_t)(2 * k), db, idesc_pv, (c | k) != 0);
+            }
+            umma_commit(&p_free[g * 2 + b]);
+            if (c == 3) umma_commit(&o_ready[g]);
+          }
+        }
+        umma_commit(&v_free[vb]);
+      }
+    }
+  } else if (warp < 10) {  // ===== softmax groups: one thread per query row
+    const int g = (warp - 2) >> 2, q = warp & 3;  // q = TMEM lane quarter this warp may touch
+    const int r = q * 32 + lane, row = g * 128 + r;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 256);
+    const uint8_t* q_row = sQ + g * kTileBytes + r * 128;
+    int it = 0;
+    for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
+      const int img = u / a.heads, h = u - img * a.heads;
+      const size_t row0 = (size_t)img * T;
+      mbar_wait(&q_full[g], it & 1);  // already complete (the MMA waited on it); taken for the TMA-write -> generic-read ordering
+      mbar_wait(&s_ready[g], it & 1);
+      tc_fence_after();
+      // score against the extra key (token 256): q_row . k_256, fp32 accumulate
+      float s_x = -INFINITY;
+      if (has_extra) {
+        const uint4* kx = reinterpret_cast<const uint4*>(a.qkv + (row0 + 256) * row_stride + hidden + h * 64);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 qa = *reinterpret_cast<const uint4*>(q_row + ((j ^ (r & 7)) << 4));
+          const uint4 kb = __ldg(kx + j);
+          const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
+          const __half2* k2 = reinterpret_cast<const __half2*>(&kb);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 qf = __half22float2(q2[e]), kf = __half22float2(k2[e]);
+            acc = fmaf(qf.x, kf.x, acc), acc = fmaf(qf.y, kf.y, acc);
+          }
+        }
+        s_x = acc;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_free[g]);
+
+      // pass 1: row maximum
+      float mx = s_x;
+      uint32_t v[32];
+#pragma unroll 1
+      for (int cc = 0; cc < 8; ++cc) {
+        tmem_ld_32x32b_x32(t_row + (uint32_t)(cc * 32), v);
+        tmem_ld_wait();
+        if (cc * 32 + 32 <= t_mma) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cc * 32 + i < t_mma) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float mb = mx * a.scale_log2e;
+      float sum = has_extra ? ex2f(fmaf(s_x, a.scale_log2e, -mb)) : 0.f;
+      const float p_x = sum;
+
+      // pass 2: P = exp2(S * scale - max) in 64-key chunks -> fp16 -> swizzled shared memory
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int b = c & 1, use = it * 2 + (c >> 1);
+        uint8_t* prow = sP + (g * 2 + b) * kTileBytes + r * 128;
+        mbar_wait(&p_free[g * 2 + b], (use & 1) ^ 1);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + half * 32), v);
+          tmem_ld_wait();
+          float p[32];
+          const int k0 = c * 64 + half * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            p[i] = ex2f(fmaf(__uint_as_float(v[i]), a.scale_log2e, -mb));
+            if (k0 + 32 > t_mma && k0 + i >= t_mma) p[i] = 0.f;
+            sum += p[i];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 w = make_uint4(pack2(p[8 * j], p[8 * j + 1]), pack2(p[8 * j + 2], p[8 * j + 3]), pack2(p[8 * j + 4], p[8 * j + 5]),
+                                       pack2(p[8 * j + 6], p[8 * j + 7]));
+            *reinterpret_cast<uint4*>(prow + (((half * 4 + j) ^ (r & 7)) << 4)) = w;
+          }
+        }
+        fence_proxy_async();  // generic-proxy writes of P -> visible to the UMMA (async proxy)
+        tc_fence_before();    // the TMEM reads above precede the MMA that overwrites columns 0..63 with O
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[g * 2 + b]);
+      }
+
+      // epilogue: O / rowsum (+ the extra key's value row) -> fp16 -> global
+      mbar_wait(&o_ready[g], it & 1);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+      const uint4* vx = reinterpret_cast<const uint4*>(a.qkv + (row0 + 256) * row_stride + 2 * hidden + h * 64);
+      __half* orow = a.out + (row0 + row) * hidden + h * 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        tmem_ld_32x32b_x32(t_row + (uint32_t)(half * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * j + e]);
+          if (has_extra) {
+            const uint4 vv = __ldg(vx + half * 4 + j);
+            const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 vf = __half22float2(v2[e]);
+              o[2 * e] = fmaf(p_x, vf.x, o[2 * e]), o[2 * e + 1] = fmaf(p_x, vf.y, o[2 * e + 1]);
+            }
+          }
+          if (row < t_mma)
+            *reinterpret_cast<uint4*>(orow + half * 32 + j * 8) =
+                make_uint4(pack2(o[0] * inv, o[1] * inv), pack2(o[2] * inv, o[3] * inv), pack2(o[4] * inv, o[5] * inv), pack2(o[6] * inv, o[7] * inv));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[g]);
+    }
+  } else {  // ===== warp 10: query row 256 on SIMT
+    int it = 0;
+    for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
+      const int img = u / a.heads, h = u - img * a.heads, vb = it & 1;
+      const size_t row0 = (size_t)img * T;
+      mbar_wait(k_full, it & 1);
+      float s[8], s_x = 0.f;
+      if (has_extra) {
+        const __half* xrow = a.qkv + (row0 + 256) * row_stride + h * 64;
+        uint4 qx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qx[j] = __ldg(reinterpret_cast<const uint4*>(xrow) + j);
+        auto dot = [&](const uint4* krow, bool swz, int key) {
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 kb = swz ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(krow) + ((j ^ (key & 7)) << 4)) : __ldg(krow + j);
+            const __half2* q2 = reinterpret_cast<const __half2*>(&qx[j]);
+            const __half2* k2 = reinterpret_cast<const __half2*>(&kb);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 qf = __half22float2(q2[e]), kf = __half22float2(k2[e]);
+              acc = fmaf(qf.x, kf.x, acc), acc = fmaf(qf.y, kf.y, acc);
+            }
+          }
+          return acc;
+        };
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int key = lane + 32 * i;
+          s[i] = dot(reinterpret_cast<const uint4*>(sK + key * 128), true, key);
+        }
+        s_x = dot(reinterpret_cast<const uint4*>(xrow + hidden), false, 0);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(k_free);
+      if (has_extra) {
+        float mx = s_x;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx = fmaxf(mx, s[i]);
+        for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        const float mb = mx * a.scale_log2e;
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float p = ex2f(fmaf(s[i], a.scale_log2e, -mb));
+          px[lane + 32 * i] = p;
+          sum += p;
+        }
+        for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        const float p_x = ex2f(fmaf(s_x, a.scale_log2e, -mb));
+        sum += p_x;
+        __syncwarp();
+        mbar_wait(&v_full[vb], (it >> 1) & 1);
+        // lane owns output dims 2*lane, 2*lane+1: byte lane*4 of every V row -> 16-byte chunk lane>>2, offset (lane&3)*4
+        const uint8_t* vbase = sV + vb * kKVBytes + (lane & 3) * 4;
+        const int ch = lane >> 2;
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll 4
+        for (int key = 0; key < 256; key += 4) {
+          const float4 p4 = *reinterpret_cast<const float4*>(px + key);
+          const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int kk = key + e;
+            const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vbase + kk * 128 + ((ch ^ (kk & 7)) << 4)));
+            o0 = fmaf(pv[e], vf.x, o0), o1 = fmaf(pv[e], vf.y, o1);
+          }
+        }
+        const float2 vxf = __half22float2(*reinterpret_cast<const __half2*>(a.qkv + (row0 + 256) * row_stride + 2 * hidden + h * 64 + 2 * lane));
+        o0 = fmaf(p_x, vxf.x, o0), o1 = fmaf(p_x, vxf.y, o1);
+        const float inv = 1.0f / sum;
+        *reinterpret_cast<uint32_t*>(a.out + (row0 + 256) * hidden + h * 64 + 2 * lane) = pack2(o0 * inv, o1 * inv);
+      } else {
+        mbar_wait(&v_full[vb], (it >> 1) & 1);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&v_free[vb]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// host side: returns CB_OK after launching, or -1 ("not my shape") so the caller falls back to the mma.sync kernel
+int attention_tc(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int heads, int head_dim, cudaStream_t stream, bool* launched) {
+  *launched = false;
+  const char* sel = std::getenv("CB_ATTN_KERNEL");
+  if (sel && std::strcmp(sel, "mma") == 0) return CB_OK;
+  if (head_dim != 64 || tokens < 129 || tokens > 257) return CB_OK;
+  const int hidden = heads * 64;
+  CUtensorMap map;
+  const uint64_t dims[2] = {(uint64_t)3 * hidden, (uint64_t)n * tokens}, strides[1] = {(uint64_t)3 * hidden * 2};
+  const uint32_t box[2] = {64, 128};
+  int rc = make_tensor_map(ctx, &map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qkv, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CUDA(ctx, cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+    attr_set = true;
+  }
+  AttnTcArgs a{(const __half*)qkv, (__half*)out, tokens, heads, n * heads, 1.4426950408889634f / sqrtf(64.f)};
+  const int grid = std::min(n * heads, ctx->sm_count);
+  mark_launch(ctx, CB_PROF_ATTENTION, stream);
+  attention_tc_kernel<<<grid, kTcThreads, kTcSmem, stream>>>(map, a);
+  CB_CUDA(ctx, cudaGetLastError());
+  *launched = true;
+  return CB_OK;
+}
+
+}  // namespace cb

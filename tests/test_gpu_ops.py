@@ -66,7 +66,8 @@ def test_layernorm(ctx):
         torch.testing.assert_close(got, want, rtol=2e-3, atol=2e-3)
 
 
-@pytest.mark.parametrize(("n", "t", "heads", "hd"), [(3, 257, 16, 64), (2, 50, 12, 64), (2, 64, 4, 64), (1, 256, 16, 72), (2, 17, 2, 32)])
+@pytest.mark.parametrize(("n", "t", "heads", "hd"), [(3, 257, 16, 64), (2, 50, 12, 64), (2, 64, 4, 64), (1, 256, 16, 72), (2, 17, 2, 32),
+                                                     (40, 257, 16, 64), (1, 257, 1, 64), (3, 256, 4, 64), (5, 129, 3, 64), (2, 200, 7, 64)])
 def test_attention(ctx, n, t, heads, hd):
     g = torch.Generator(device="cuda").manual_seed(t)
     d = heads * hd
@@ -78,6 +79,21 @@ def test_attention(ctx, n, t, heads, hd):
     torch.testing.assert_close(got, want, rtol=1e-2, atol=4e-3)  # P and O rounded to fp16
 
 
+
+
+def test_attention_tcgen05_and_mma_kernels_agree(ctx, monkeypatch):
+    """head_dim 64 / 129..257 tokens runs on tcgen05 (attention_tc.cu); CB_ATTN_KERNEL=mma forces the mma.sync kernel."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = (torch.randn(20, 257, 3 * 1024, device="cuda", generator=g) * 2.0).half()
+    qkv[:, :, 5] += 6.0  # a dominant query/key channel: sharp softmax rows
+    tc = ctx.attention(qkv, 16).float()
+    monkeypatch.setenv("CB_ATTN_KERNEL", "mma")
+    mma = ctx.attention(qkv, 16).float()
+    torch.testing.assert_close(tc, mma, rtol=1e-2, atol=4e-3)
+    again = ctx.attention(qkv, 16).float()
+    assert torch.equal(mma, again)
+    monkeypatch.delenv("CB_ATTN_KERNEL")
+    assert torch.equal(tc, ctx.attention(qkv, 16).float())  # deterministic
 
 
 @pytest.mark.parametrize("kernel", ["1cta", "2cta"])

@@ -52,6 +52,20 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// tcgen05.wait::ld that names the destination registers of the load it completes: arithmetic on them cannot be scheduled
+// above the wait (a bare wait has no data dependence on them), which makes issuing the NEXT load before the wait safe.
+__device__ __forceinline__ void tmem_ld_wait_pin(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                 "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]),
+                 "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),
+                 "+r"(r[31])::"memory");
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 // MN-major B operand, SW128: rows are K (keys), each row = 64 contiguous N elements (128 B); 8-row groups 1024 B apart.
 // LBO (stride between 64-element column blocks along N) is irrelevant for N = 64; both strides are set to 1024 B.
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
@@ -64,6 +78,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
   return d;
 }
 
+// FULL: tokens is 256 or 257, i.e. every column / row of the tensor-core tiles is a real token (no masking code at all)
+template <bool FULL>
 __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -81,7 +97,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = a.tokens, hidden = a.heads * 64;
   const bool has_extra = T == 257;
-  const int t_mma = T < 256 ? T : 256;  // keys / query rows living in the tensor-core tiles
+  const int t_mma = FULL ? 256 : (T < 256 ? T : 256);  // keys / query rows living in the tensor-core tiles
   const size_t row_stride = (size_t)3 * hidden;
 
   if (warp == 1 && lane == 0) {
@@ -109,15 +125,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
         const int img = u / a.heads, h = u - img * a.heads, row0 = img * T, vb = it & 1;
         for (int g = 0; g < 2; ++g) {
-          mbar_wait(&q_free[g], (it & 1) ^ 1);
+          mbar_wait_parked(&q_free[g], (it & 1) ^ 1);
           mbar_expect_tx(&q_full[g], kTileBytes);
           tma_load_2d(sQ + g * kTileBytes, &map_qkv, &q_full[g], h * 64, row0 + g * 128);
         }
-        mbar_wait(k_free, (it & 1) ^ 1);
+        mbar_wait_parked(k_free, (it & 1) ^ 1);
         mbar_expect_tx(k_full, kKVBytes);
         tma_load_2d(sK, &map_qkv, k_full, hidden + h * 64, row0);
         tma_load_2d(sK + kTileBytes, &map_qkv, k_full, hidden + h * 64, row0 + 128);
-        mbar_wait(&v_free[vb], ((it >> 1) & 1) ^ 1);
+        mbar_wait_parked(&v_free[vb], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&v_full[vb], kKVBytes);
         tma_load_2d(sV + vb * kKVBytes, &map_qkv, &v_full[vb], 2 * hidden + h * 64, row0);
         tma_load_2d(sV + vb * kKVBytes + kTileBytes, &map_qkv, &v_full[vb], 2 * hidden + h * 64, row0 + 128);
@@ -131,9 +147,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
         const int vb = it & 1;
         for (int g = 0; g < 2; ++g) {
-          mbar_wait(&q_full[g], it & 1);
-          if (g == 0) mbar_wait(k_full, it & 1);
-          mbar_wait(&s_free[g], (it & 1) ^ 1);
+          mbar_wait_parked(&q_full[g], it & 1);
+          if (g == 0) mbar_wait_parked(k_full, it & 1);
+          mbar_wait_parked(&s_free[g], (it & 1) ^ 1);
           tc_fence_after();
           const uint64_t da = umma_desc_sw128(smem_u32(sQ + g * kTileBytes)), db = umma_desc_sw128(smem_u32(sK));
 #pragma unroll
@@ -141,12 +157,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
           umma_commit(&s_ready[g]);
         }
         umma_commit(k_free);
-        mbar_wait(&v_full[vb], (it >> 1) & 1);
+        mbar_wait_parked(&v_full[vb], (it >> 1) & 1);
         tc_fence_after();
         for (int c = 0; c < 4; ++c) {
           for (int g = 0; g < 2; ++g) {
             const int b = c & 1, use = it * 2 + (c >> 1);
-            mbar_wait(&p_ready[g * 2 + b], use & 1);
+            mbar_wait_parked(&p_ready[g * 2 + b], use & 1);
             tc_fence_after();
             const uint64_t da = umma_desc_sw128(smem_u32(sP + (g * 2 + b) * kTileBytes));
 #pragma unroll
@@ -170,107 +186,137 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
       const int img = u / a.heads, h = u - img * a.heads;
       const size_t row0 = (size_t)img * T;
-      mbar_wait(&q_full[g], it & 1);  // already complete (the MMA waited on it); taken for the TMA-write -> generic-read ordering
-      mbar_wait(&s_ready[g], it & 1);
-      tc_fence_after();
-      // score against the extra key (token 256): q_row . k_256, fp32 accumulate
-      float s_x = -INFINITY;
+      // the extra key's K row and V row are plain global reads (the same 128 bytes for every thread): issue them before
+      // waiting for S so that their latency is off the critical path
+      uint4 kxr[8];
       if (has_extra) {
         const uint4* kx = reinterpret_cast<const uint4*>(a.qkv + (row0 + 256) * row_stride + hidden + h * 64);
-        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) kxr[j] = __ldg(kx + j);
+      }
+      mbar_wait_parked(&q_full[g], it & 1);  // already complete (the MMA waited on it); taken for the TMA-write -> generic-read ordering
+      // score against the extra key (token 256): q_row . k_256, fp32 accumulate (needs Q only, not S)
+      float s_x = -INFINITY;
+      if (has_extra) {
+        float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint4 qa = *reinterpret_cast<const uint4*>(q_row + ((j ^ (r & 7)) << 4));
-          const uint4 kb = __ldg(kx + j);
           const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
-          const __half2* k2 = reinterpret_cast<const __half2*>(&kb);
+          const __half2* k2 = reinterpret_cast<const __half2*>(&kxr[j]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 qf = __half22float2(q2[e]), kf = __half22float2(k2[e]);
-            acc = fmaf(qf.x, kf.x, acc), acc = fmaf(qf.y, kf.y, acc);
+            acc0 = fmaf(qf.x, kf.x, acc0), acc1 = fmaf(qf.y, kf.y, acc1);
           }
         }
-        s_x = acc;
+        s_x = acc0 + acc1;
       }
+      mbar_wait_parked(&s_ready[g], it & 1);
+      tc_fence_after();
       __syncwarp();
       if (lane == 0) mbar_arrive(&q_free[g]);
 
-      // pass 1: row maximum
+      // pass 1: row maximum; the load of block cc+1 is in flight while block cc is reduced
       float mx = s_x;
-      uint32_t v[32];
+      uint32_t va[32], vb2[32];
+      tmem_ld_32x32b_x32(t_row, va);
 #pragma unroll 1
-      for (int cc = 0; cc < 8; ++cc) {
-        tmem_ld_32x32b_x32(t_row + (uint32_t)(cc * 32), v);
-        tmem_ld_wait();
-        if (cc * 32 + 32 <= t_mma) {
+      for (int cc = 0; cc < 8; cc += 2) {
+        tmem_ld_wait_pin(va);
+        tmem_ld_32x32b_x32(t_row + (uint32_t)((cc + 1) * 32), vb2);
+        if (FULL || cc * 32 + 32 <= t_mma) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(va[i]), __uint_as_float(va[i + 1]));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (cc * 32 + i < t_mma) mx = fmaxf(mx, __uint_as_float(v[i]));
+            if (cc * 32 + i < t_mma) mx = fmaxf(mx, __uint_as_float(va[i]));
+        }
+        tmem_ld_wait_pin(vb2);
+        tmem_ld_32x32b_x32(t_row + (uint32_t)(((cc + 2) & 7) * 32), va);  // wraps to block 0: the first block of pass 2
+        if (FULL || cc * 32 + 64 <= t_mma) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) mx = max3(mx, __uint_as_float(vb2[i]), __uint_as_float(vb2[i + 1]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cc * 32 + 32 + i < t_mma) mx = fmaxf(mx, __uint_as_float(vb2[i]));
         }
       }
       const float mb = mx * a.scale_log2e;
       float sum = has_extra ? ex2f(fmaf(s_x, a.scale_log2e, -mb)) : 0.f;
       const float p_x = sum;
+      float sum1 = 0.f;
 
-      // pass 2: P = exp2(S * scale - max) in 64-key chunks -> fp16 -> swizzled shared memory
+      // pass 2: P = exp2(S * scale - max) in 64-key chunks -> fp16 -> swizzled shared memory.  `va` already holds (or is
+      // receiving) columns 0..31; each half's successor is requested before the exponentials of the current half.
+      auto emit = [&](const uint32_t* v, uint8_t* prow, int half, int k0) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2f(fmaf(__uint_as_float(v[i]), a.scale_log2e, -mb)), p1 = ex2f(fmaf(__uint_as_float(v[i + 1]), a.scale_log2e, -mb));
+          if (!FULL) {
+            if (k0 + i >= t_mma) p0 = 0.f;
+            if (k0 + i + 1 >= t_mma) p1 = 0.f;
+          }
+          sum += p0, sum1 += p1;
+          w[i >> 1] = pack2(p0, p1);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(prow + (((half * 4 + j) ^ (r & 7)) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+      };
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int b = c & 1, use = it * 2 + (c >> 1);
         uint8_t* prow = sP + (g * 2 + b) * kTileBytes + r * 128;
-        mbar_wait(&p_free[g * 2 + b], (use & 1) ^ 1);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + half * 32), v);
-          tmem_ld_wait();
-          float p[32];
-          const int k0 = c * 64 + half * 32;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            p[i] = ex2f(fmaf(__uint_as_float(v[i]), a.scale_log2e, -mb));
-            if (k0 + 32 > t_mma && k0 + i >= t_mma) p[i] = 0.f;
-            sum += p[i];
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 w = make_uint4(pack2(p[8 * j], p[8 * j + 1]), pack2(p[8 * j + 2], p[8 * j + 3]), pack2(p[8 * j + 4], p[8 * j + 5]),
-                                       pack2(p[8 * j + 6], p[8 * j + 7]));
-            *reinterpret_cast<uint4*>(prow + (((half * 4 + j) ^ (r & 7)) << 4)) = w;
-          }
-        }
+        mbar_wait_parked(&p_free[g * 2 + b], (use & 1) ^ 1);
+        tmem_ld_wait_pin(va);
+        tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + 32), vb2);
+        emit(va, prow, 0, c * 64);
+        tmem_ld_wait_pin(vb2);
+        if (c < 3) tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + 64), va);
+        emit(vb2, prow, 1, c * 64 + 32);
         fence_proxy_async();  // generic-proxy writes of P -> visible to the UMMA (async proxy)
         tc_fence_before();    // the TMEM reads above precede the MMA that overwrites columns 0..63 with O
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[g * 2 + b]);
       }
+      sum += sum1;
 
       // epilogue: O / rowsum (+ the extra key's value row) -> fp16 -> global
-      mbar_wait(&o_ready[g], it & 1);
+      uint4 vxr[8];
+      if (has_extra) {
+        const uint4* vx = reinterpret_cast<const uint4*>(a.qkv + (row0 + 256) * row_stride + 2 * hidden + h * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) vxr[j] = __ldg(vx + j);
+      }
+      mbar_wait_parked(&o_ready[g], it & 1);
       tc_fence_after();
       const float inv = 1.0f / sum;
-      const uint4* vx = reinterpret_cast<const uint4*>(a.qkv + (row0 + 256) * row_stride + 2 * hidden + h * 64);
       __half* orow = a.out + (row0 + row) * hidden + h * 64;
+      tmem_ld_32x32b_x32(t_row, va);
+      tmem_ld_32x32b_x32(t_row + 32u, vb2);
+      tmem_ld_wait_pin(va);
+      tmem_ld_wait_pin(vb2);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        tmem_ld_32x32b_x32(t_row + (uint32_t)(half * 32), v);
-        tmem_ld_wait();
+        const uint32_t* v = half ? vb2 : va;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float o[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * j + e]);
           if (has_extra) {
-            const uint4 vv = __ldg(vx + half * 4 + j);
-            const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
+            const __half2* v2 = reinterpret_cast<const __half2*>(&vxr[half * 4 + j]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 vf = __half22float2(v2[e]);
               o[2 * e] = fmaf(p_x, vf.x, o[2 * e]), o[2 * e + 1] = fmaf(p_x, vf.y, o[2 * e + 1]);
             }
           }
-          if (row < t_mma)
+          if (FULL || row < t_mma)
             *reinterpret_cast<uint4*>(orow + half * 32 + j * 8) =
                 make_uint4(pack2(o[0] * inv, o[1] * inv), pack2(o[2] * inv, o[3] * inv), pack2(o[4] * inv, o[5] * inv), pack2(o[6] * inv, o[7] * inv));
         }
@@ -284,7 +330,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
       const int img = u / a.heads, h = u - img * a.heads, vb = it & 1;
       const size_t row0 = (size_t)img * T;
-      mbar_wait(k_full, it & 1);
+      mbar_wait_parked(k_full, it & 1);
       float s[8], s_x = 0.f;
       if (has_extra) {
         const __half* xrow = a.qkv + (row0 + 256) * row_stride + h * 64;
@@ -332,28 +378,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         const float p_x = ex2f(fmaf(s_x, a.scale_log2e, -mb));
         sum += p_x;
         __syncwarp();
-        mbar_wait(&v_full[vb], (it >> 1) & 1);
+        mbar_wait_parked(&v_full[vb], (it >> 1) & 1);
         // lane owns output dims 2*lane, 2*lane+1: byte lane*4 of every V row -> 16-byte chunk lane>>2, offset (lane&3)*4
         const uint8_t* vbase = sV + vb * kKVBytes + (lane & 3) * 4;
         const int ch = lane >> 2;
-        float o0 = 0.f, o1 = 0.f;
+        float o0 = 0.f, o1 = 0.f, oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
         for (int key = 0; key < 256; key += 4) {
           const float4 p4 = *reinterpret_cast<const float4*>(px + key);
           const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int e = 0; e < 4; ++e) {  // four independent accumulator pairs: the loop is not an FMA latency chain
             const int kk = key + e;
             const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vbase + kk * 128 + ((ch ^ (kk & 7)) << 4)));
-            o0 = fmaf(pv[e], vf.x, o0), o1 = fmaf(pv[e], vf.y, o1);
+            oa[e] = fmaf(pv[e], vf.x, oa[e]), ob[e] = fmaf(pv[e], vf.y, ob[e]);
           }
         }
+        o0 = (oa[0] + oa[1]) + (oa[2] + oa[3]), o1 = (ob[0] + ob[1]) + (ob[2] + ob[3]);
         const float2 vxf = __half22float2(*reinterpret_cast<const __half2*>(a.qkv + (row0 + 256) * row_stride + 2 * hidden + h * 64 + 2 * lane));
         o0 = fmaf(p_x, vxf.x, o0), o1 = fmaf(p_x, vxf.y, o1);
         const float inv = 1.0f / sum;
         *reinterpret_cast<uint32_t*>(a.out + (row0 + 256) * hidden + h * 64 + 2 * lane) = pack2(o0 * inv, o1 * inv);
       } else {
-        mbar_wait(&v_full[vb], (it >> 1) & 1);
+        mbar_wait_parked(&v_full[vb], (it >> 1) & 1);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&v_free[vb]);
@@ -382,13 +429,17 @@ int attention_tc(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    CB_CUDA(ctx, cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+    CB_CUDA(ctx, cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+    CB_CUDA(ctx, cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
     attr_set = true;
   }
   AttnTcArgs a{(const __half*)qkv, (__half*)out, tokens, heads, n * heads, 1.4426950408889634f / sqrtf(64.f)};
   const int grid = std::min(n * heads, ctx->sm_count);
   mark_launch(ctx, CB_PROF_ATTENTION, stream);
-  attention_tc_kernel<<<grid, kTcThreads, kTcSmem, stream>>>(map, a);
+  if (tokens >= 256)
+    attention_tc_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(map, a);
+  else
+    attention_tc_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(map, a);
   CB_CUDA(ctx, cudaGetLastError());
   *launched = true;
   return CB_OK;

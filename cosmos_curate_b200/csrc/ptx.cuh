@@ -36,6 +36,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Same, but the thread is suspended in hardware (up to `ns`) instead of re-polling: for single-lane producer / issuer roles that
+// share an SM sub-partition with compute warps, whose issue slots a tight poll loop would eat.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t ns = 20000) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+  } while (!ok);
+}
 
 // ---------------------------------------------------------------- TMA loads (global -> shared::cta)
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -29,8 +29,8 @@ constexpr int kTcThreads = 352;
 constexpr int kTileBytes = 128 * 128;       // 128 rows x 64 fp16, SW128
 constexpr int kKVBytes = 2 * kTileBytes;    // 256 rows
 constexpr int kOffQ = 0;                    // 2 tiles
-constexpr int kOffK = 2 * kTileBytes;       // 256 keys
-constexpr int kOffV = kOffK + kKVBytes;     // 2 buffers x 256 keys
+constexpr int kOffK = 2 * kTileBytes;       // 2 buffers x 256 keys
+constexpr int kOffV = kOffK + 2 * kKVBytes; // 2 buffers x 256 keys
 constexpr int kOffP = kOffV + 2 * kKVBytes; // [group][2] x 128 rows x 64 keys
 constexpr int kOffPx = kOffP + 4 * kTileBytes;
 constexpr int kOffBar = kOffPx + 1024;
@@ -41,6 +41,9 @@ struct AttnTcArgs {
   __half* out;
   int tokens, heads, n_units;  // n_units = images * heads
   float scale_log2e;
+  int debug_skip_max;  // timing experiment only (CB_ATTN_DEBUG_SKIPMAX=1): wrong results
+  int use_token;       // CB_ATTN_TOKEN=1: the two softmax groups take strict turns on the exp phase (A/B switch; default off)
+  long long* trace;    // CB_ATTN_DEBUG_TRACE=1: clock64 stamps of CTA 0, [group][unit < 16][16 events]
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -90,9 +93,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
   uint8_t* sP = smem + kOffP;
   float* px = reinterpret_cast<float*>(smem + kOffPx);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t *q_full = bars, *q_free = bars + 2, *k_full = bars + 4, *k_free = bars + 5, *v_full = bars + 6, *v_free = bars + 8;
-  uint64_t *s_ready = bars + 10, *s_free = bars + 12, *o_ready = bars + 14, *p_ready = bars + 16 /*[g*2+b]*/, *p_free = bars + 20;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t *q_full = bars, *q_free = bars + 2, *k_full = bars + 4, *k_free = bars + 6, *v_full = bars + 8, *v_free = bars + 10;
+  uint64_t *s_ready = bars + 12, *s_free = bars + 14, *o_ready = bars + 16, *p_ready = bars + 18 /*[g*2+b]*/, *p_free = bars + 22;
+  uint64_t* tok = bars + 26;  // exp-phase token: the two softmax groups take turns on the MUFU pipe
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = a.tokens, hidden = a.heads * 64;
@@ -103,9 +107,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1), mbar_init(&q_free[i], 4), mbar_init(&v_full[i], 1), mbar_init(&v_free[i], 2);
-      mbar_init(&s_ready[i], 1), mbar_init(&s_free[i], 4), mbar_init(&o_ready[i], 1);
+      mbar_init(&k_full[i], 1), mbar_init(&k_free[i], 2);
+      mbar_init(&s_ready[i], 1), mbar_init(&s_free[i], 4), mbar_init(&o_ready[i], 1), mbar_init(&tok[i], 4);
     }
-    mbar_init(k_full, 1), mbar_init(k_free, 2);
     for (int i = 0; i < 4; ++i) mbar_init(&p_ready[i], 4), mbar_init(&p_free[i], 1);
     fence_barrier_init();
   }
@@ -124,57 +128,71 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       int it = 0;
       for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
         const int img = u / a.heads, h = u - img * a.heads, row0 = img * T, vb = it & 1;
-        for (int g = 0; g < 2; ++g) {
+        // order: what group 0 (half a unit ahead) needs first; Q of group 1 last - its buffer is released late
+        auto load_q = [&](int g) {
           mbar_wait_parked(&q_free[g], (it & 1) ^ 1);
           mbar_expect_tx(&q_full[g], kTileBytes);
           tma_load_2d(sQ + g * kTileBytes, &map_qkv, &q_full[g], h * 64, row0 + g * 128);
-        }
-        mbar_wait_parked(k_free, (it & 1) ^ 1);
-        mbar_expect_tx(k_full, kKVBytes);
-        tma_load_2d(sK, &map_qkv, k_full, hidden + h * 64, row0);
-        tma_load_2d(sK + kTileBytes, &map_qkv, k_full, hidden + h * 64, row0 + 128);
+        };
+        load_q(0);
+        mbar_wait_parked(&k_free[vb], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&k_full[vb], kKVBytes);
+        tma_load_2d(sK + vb * kKVBytes, &map_qkv, &k_full[vb], hidden + h * 64, row0);
+        tma_load_2d(sK + vb * kKVBytes + kTileBytes, &map_qkv, &k_full[vb], hidden + h * 64, row0 + 128);
         mbar_wait_parked(&v_free[vb], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&v_full[vb], kKVBytes);
         tma_load_2d(sV + vb * kKVBytes, &map_qkv, &v_full[vb], 2 * hidden + h * 64, row0);
         tma_load_2d(sV + vb * kKVBytes + kTileBytes, &map_qkv, &v_full[vb], 2 * hidden + h * 64, row0 + 128);
+        load_q(1);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer
+    if (lane == 0) {  // ===== MMA issuer: an event loop, so that the two softmax groups can run half a unit apart
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 256, 0);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, 64, 0) | (1u << 16);  // B is MN-major
-      int it = 0;
-      for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
-        const int vb = it & 1;
+      const int n_it = a.n_units > (int)blockIdx.x ? (a.n_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      int it_g[2] = {0, 0}, stage[2] = {0, 0};  // stage 0: S = Q K^T pending; 1..4: O += P[chunk] V[chunk] pending
+      int qk_cnt[2] = {0, 0}, pv_cnt[2] = {0, 0};  // groups done with the K / V buffer of unit parity
+      while (it_g[0] < n_it || it_g[1] < n_it) {
+        bool progress = false;
+#pragma unroll
         for (int g = 0; g < 2; ++g) {
-          mbar_wait_parked(&q_full[g], it & 1);
-          if (g == 0) mbar_wait_parked(k_full, it & 1);
-          mbar_wait_parked(&s_free[g], (it & 1) ^ 1);
-          tc_fence_after();
-          const uint64_t da = umma_desc_sw128(smem_u32(sQ + g * kTileBytes)), db = umma_desc_sw128(smem_u32(sK));
+          const int it = it_g[g];
+          if (it >= n_it) continue;
+          const int kb = it & 1;
+          if (stage[g] == 0) {
+            if (mbar_test(&q_full[g], it & 1) && mbar_test(&k_full[kb], (it >> 1) & 1) && mbar_test(&s_free[g], (it & 1) ^ 1)) {
+              tc_fence_after();
+              const uint64_t da = umma_desc_sw128(smem_u32(sQ + g * kTileBytes)), db = umma_desc_sw128(smem_u32(sK + kb * kKVBytes));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + (uint32_t)(g * 256), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_qk, k != 0);
-          umma_commit(&s_ready[g]);
-        }
-        umma_commit(k_free);
-        mbar_wait_parked(&v_full[vb], (it >> 1) & 1);
-        tc_fence_after();
-        for (int c = 0; c < 4; ++c) {
-          for (int g = 0; g < 2; ++g) {
-            const int b = c & 1, use = it * 2 + (c >> 1);
-            mbar_wait_parked(&p_ready[g * 2 + b], use & 1);
-            tc_fence_after();
-            const uint64_t da = umma_desc_sw128(smem_u32(sP + (g * 2 + b) * kTileBytes));
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t db = umma_desc_sw128_mn(smem_u32(sV + vb * kKVBytes + (c * 64 + k * 16) * 128));
-              umma_f16(tmem_base + (uint32_t)(g * 256), da + (uint64_t)(2 * k), db, idesc_pv, (c | k) != 0);
+              for (int k = 0; k < 4; ++k) umma_f16(tmem_base + (uint32_t)(g * 256), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_qk, k != 0);
+              umma_commit(&s_ready[g]);
+              if (++qk_cnt[kb] == 2) qk_cnt[kb] = 0, umma_commit(&k_free[kb]);
+              stage[g] = 1, progress = true;
             }
-            umma_commit(&p_free[g * 2 + b]);
-            if (c == 3) umma_commit(&o_ready[g]);
+          } else {
+            const int c = stage[g] - 1, b = c & 1, use = it * 2 + (c >> 1);
+            if ((c != 0 || mbar_test(&v_full[kb], (it >> 1) & 1)) && mbar_test(&p_ready[g * 2 + b], use & 1)) {
+              tc_fence_after();
+              const uint64_t da = umma_desc_sw128(smem_u32(sP + (g * 2 + b) * kTileBytes));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t db = umma_desc_sw128_mn(smem_u32(sV + kb * kKVBytes + (c * 64 + k * 16) * 128));
+                umma_f16(tmem_base + (uint32_t)(g * 256), da + (uint64_t)(2 * k), db, idesc_pv, (c | k) != 0);
+              }
+              umma_commit(&p_free[g * 2 + b]);
+              if (c == 3) {
+                umma_commit(&o_ready[g]);
+                if (++pv_cnt[kb] == 2) pv_cnt[kb] = 0, umma_commit(&v_free[kb]);
+                stage[g] = 0, it_g[g] = it + 1;
+              } else {
+                stage[g] = c + 2;
+              }
+              progress = true;
+            }
           }
         }
-        umma_commit(&v_free[vb]);
+        if (!progress) __nanosleep(40);
       }
     }
   } else if (warp < 10) {  // ===== softmax groups: one thread per query row
@@ -183,9 +201,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 256);
     const uint8_t* q_row = sQ + g * kTileBytes + r * 128;
     int it = 0;
+    const bool tracing = a.trace && blockIdx.x == 0 && q == 2 && lane == 0;  // warps 2 and 6
+#define CB_TRACE(ev)                                                                  \
+  do {                                                                                \
+    if (tracing && it < 16) a.trace[(g * 16 + it) * 16 + (ev)] = clock64();           \
+  } while (0)
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
       const int img = u / a.heads, h = u - img * a.heads;
       const size_t row0 = (size_t)img * T;
+      CB_TRACE(0);
       // the extra key's K row and V row are plain global reads (the same 128 bytes for every thread): issue them before
       // waiting for S so that their latency is off the critical path
       uint4 kxr[8];
@@ -212,8 +236,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         }
         s_x = acc0 + acc1;
       }
+      CB_TRACE(1);
       mbar_wait_parked(&s_ready[g], it & 1);
       tc_fence_after();
+      CB_TRACE(2);
       __syncwarp();
       if (lane == 0) mbar_arrive(&q_free[g]);
 
@@ -222,7 +248,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       uint32_t va[32], vb2[32];
       tmem_ld_32x32b_x32(t_row, va);
 #pragma unroll 1
-      for (int cc = 0; cc < 8; cc += 2) {
+      for (int cc = 0; cc < (a.debug_skip_max ? 0 : 8); cc += 2) {
         tmem_ld_wait_pin(va);
         tmem_ld_32x32b_x32(t_row + (uint32_t)((cc + 1) * 32), vb2);
         if (FULL || cc * 32 + 32 <= t_mma) {
@@ -267,11 +293,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<uint4*>(prow + (((half * 4 + j) ^ (r & 7)) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
       };
+      // optional (CB_ATTN_TOKEN=1): strict alternation of the exp phases of the two groups.  Measured neutral-to-slightly-worse
+      // on B200 (0.214 vs 0.207 ms per ViT-L layer): the kernel is bound by issue slots / latency of 2-3 warps per SM
+      // sub-partition, not by the MUFU pipe, so it is off by default.
+      CB_TRACE(3);
+      if (a.use_token) mbar_wait_parked(&tok[g], g == 0 ? (it & 1) ^ 1 : (it & 1));
+      CB_TRACE(4);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const int b = c & 1, use = it * 2 + (c >> 1);
         uint8_t* prow = sP + (g * 2 + b) * kTileBytes + r * 128;
         mbar_wait_parked(&p_free[g * 2 + b], (use & 1) ^ 1);
+        CB_TRACE(5 + 2 * c);
         tmem_ld_wait_pin(va);
         tmem_ld_32x32b_x32(t_row + (uint32_t)(c * 64 + 32), vb2);
         emit(va, prow, 0, c * 64);
@@ -281,7 +314,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         fence_proxy_async();  // generic-proxy writes of P -> visible to the UMMA (async proxy)
         tc_fence_before();    // the TMEM reads above precede the MMA that overwrites columns 0..63 with O
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[g * 2 + b]);
+        if (lane == 0) {
+          mbar_arrive(&p_ready[g * 2 + b]);
+          if (c == 3) mbar_arrive(&tok[g ^ 1]);
+        }
+        CB_TRACE(6 + 2 * c);
       }
       sum += sum1;
 
@@ -294,6 +331,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       }
       mbar_wait_parked(&o_ready[g], it & 1);
       tc_fence_after();
+      CB_TRACE(13);
       const float inv = 1.0f / sum;
       __half* orow = a.out + (row0 + row) * hidden + h * 64;
       tmem_ld_32x32b_x32(t_row, va);
@@ -324,13 +362,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[g]);
+      CB_TRACE(14);
     }
   } else {  // ===== warp 10: query row 256 on SIMT
     int it = 0;
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
       const int img = u / a.heads, h = u - img * a.heads, vb = it & 1;
       const size_t row0 = (size_t)img * T;
-      mbar_wait_parked(k_full, it & 1);
+      mbar_wait_parked(&k_full[vb], (it >> 1) & 1);
       float s[8], s_x = 0.f;
       if (has_extra) {
         const __half* xrow = a.qkv + (row0 + 256) * row_stride + h * 64;
@@ -355,12 +394,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int key = lane + 32 * i;
-          s[i] = dot(reinterpret_cast<const uint4*>(sK + key * 128), true, key);
+          s[i] = dot(reinterpret_cast<const uint4*>(sK + vb * kKVBytes + key * 128), true, key);
         }
         s_x = dot(reinterpret_cast<const uint4*>(xrow + hidden), false, 0);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(k_free);
+      if (lane == 0) mbar_arrive(&k_free[vb]);
       if (has_extra) {
         float mx = s_x;
 #pragma unroll
@@ -433,7 +472,16 @@ int attention_tc(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int
     CB_CUDA(ctx, cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
     attr_set = true;
   }
-  AttnTcArgs a{(const __half*)qkv, (__half*)out, tokens, heads, n * heads, 1.4426950408889634f / sqrtf(64.f)};
+  const char* dbg = std::getenv("CB_ATTN_DEBUG_SKIPMAX");
+  AttnTcArgs a{(const __half*)qkv, (__half*)out, tokens, heads, n * heads, 1.4426950408889634f / sqrtf(64.f), dbg && dbg[0] == '1', 0, nullptr};
+  const char* tk = std::getenv("CB_ATTN_TOKEN");
+  a.use_token = tk && tk[0] == '1';
+  const char* trc = std::getenv("CB_ATTN_DEBUG_TRACE");
+  const bool tracing = trc && trc[0] == '1';
+  if (tracing) {
+    CB_CUDA(ctx, cudaMalloc(&a.trace, 2 * 16 * 16 * sizeof(long long)));
+    CB_CUDA(ctx, cudaMemset(a.trace, 0, 2 * 16 * 16 * sizeof(long long)));
+  }
   const int grid = std::min(n * heads, ctx->sm_count);
   mark_launch(ctx, CB_PROF_ATTENTION, stream);
   if (tokens >= 256)
@@ -441,6 +489,19 @@ int attention_tc(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int
   else
     attention_tc_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(map, a);
   CB_CUDA(ctx, cudaGetLastError());
+  if (tracing) {
+    long long h[2 * 16 * 16];
+    CB_CUDA(ctx, cudaStreamSynchronize(stream));
+    CB_CUDA(ctx, cudaMemcpy(h, a.trace, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(a.trace);
+    const long long t0 = h[0];
+    for (int g = 0; g < 2; ++g)
+      for (int it = 0; it < 8; ++it) {
+        printf("trace g%d it%d:", g, it);
+        for (int e = 0; e < 15; ++e) printf(" %lld", h[(g * 16 + it) * 16 + e] ? h[(g * 16 + it) * 16 + e] - t0 : -1);
+        printf("\n");
+      }
+  }
   *launched = true;
   return CB_OK;
 }

@@ -15,6 +15,7 @@ LIB_PATH = PKG / "libcurate_b200.so"
 
 CB_OK = 0
 CB_ERR = {-1: "CB_ERR_CUDA", -2: "CB_ERR_ARG", -3: "CB_ERR_UNSUPPORTED", -4: "CB_ERR_NVDEC", -5: "CB_ERR_DEMUX", -6: "CB_ERR_STATE"}
+ROWDOT_UPPER, ROWDOT_CLIP = 1, 2
 FMT_NV12, FMT_RGB24 = 0, 1
 DT_F16, DT_BF16, DT_F32 = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_PATCH = 0, 1
@@ -96,6 +97,9 @@ SIGNATURES = {
     "cb_transnet_finalize": (_i, [_vp, _i]),
     "cb_transnet_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "cb_transnet_predict": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "cb_rowdot_argmax": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _i, _f, _vp, _vp, _vp]),
+    "cb_rows_l2_normalize": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "cb_cluster_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "cb_gemm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cb_layernorm_f16": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "cb_attention_f16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

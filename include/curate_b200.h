@@ -219,6 +219,22 @@ int cb_transnet_forward(cb_transnet* tn, const uint8_t* windows, int n_windows, 
  * the tail windows left short exactly as _get_batches leaves them).  Thresholding (prob > threshold) is the caller's. */
 int cb_transnet_predict(cb_transnet* tn, const uint8_t* frames, int n_frames, float* prob_out, void* stream);
 
+/* ---- semantic dedup on the gathered embeddings (fp32) ------------------------------------------------ */
+#define CB_ROWDOT_UPPER 1 /* a == b: only candidates i < j count (strict upper triangle) */
+#define CB_ROWDOT_CLIP 2  /* clamp scores to [-1, 1] before comparing */
+/* For every row j of b[nb][d]: the maximum over rows i of a[na][d] of (a_i . b_j + bias_i) and the FIRST index attaining
+ * it; a candidate must be strictly greater than init_val, else out_idx[j] = -1 and out_val[j] = init_val.  All pointers
+ * are device fp32 / int32, d a multiple of 16.  Replaces the tiled `E[i0:i1] @ E[j0:j1].T -> clip -> argmax -> where`
+ * loop of SemanticDedupActor.dedup (cosmos_curate/pipelines/video/dedup/dedup_actor.py:420-462) with UPPER|CLIP and
+ * init_val = -1, and the nearest-centroid assignment of its KMeansMG call (:232-241) with bias_i = -|c_i|^2 / 2. */
+int cb_rowdot_argmax(cb_ctx* ctx, const float* a, int na, const float* b, int nb, int d, const float* bias, int flags, float init_val, float* out_val,
+                     int* out_idx, void* stream);
+/* x[row] /= max(|x[row]|_2, 1e-12) in place (dedup_actor.py:224-225, :407-408); norms_out (nullable) receives |x[row]|. */
+int cb_rows_l2_normalize(cb_ctx* ctx, float* x, int rows, int d, float* norms_out, void* stream);
+/* sums[c][:] += sum of x[order[t]][:] for t in [seg[c], seg[c+1]): the centroid-update reduction of k-means, rows added
+ * in the given order by one thread per (cluster, dimension) - bit-reproducible.  order/seg are device int64. */
+int cb_cluster_sums(cb_ctx* ctx, const float* x, const long long* order, const long long* seg, int n_clusters, int d, float* sums, void* stream);
+
 /* ---- building blocks exported for the parity tests ------------------------------------------------ */
 #define CB_EPI_NONE 0       /* C = A W^T (+ bias) */
 #define CB_EPI_QUICK_GELU 1 /* C = quick_gelu(A W^T + bias) */

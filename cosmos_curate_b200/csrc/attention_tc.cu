@@ -33,8 +33,10 @@ constexpr int kOffK = 2 * kTileBytes;       // 2 buffers x 256 keys
 constexpr int kOffV = kOffK + 2 * kKVBytes; // 2 buffers x 256 keys
 constexpr int kOffP = kOffV + 2 * kKVBytes; // [group][2] x 128 rows x 64 keys
 constexpr int kOffPx = kOffP + 4 * kTileBytes;
-constexpr int kOffBar = kOffPx + 1024;
+constexpr int kOffX = kOffPx + 1024;         // K and V rows of the extra token: [parity][k|v][64] fp16
+constexpr int kOffBar = kOffX + 512;
 constexpr int kTcSmem = kOffBar + 256 + 1024 /* alignment slack */;
+static_assert(kTcSmem <= 232448, "shared memory budget");
 
 struct AttnTcArgs {
   const __half* qkv;
@@ -49,6 +51,13 @@ struct AttnTcArgs {
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// volatile: a run of these stays a run of back-to-back MUFU issues (the exp phase is paced by the MUFU pipe, one warp
+// instruction per 8 cycles; interleaving the dependent FADDs between them lets a lone warp reach only half that rate)
+__device__ __forceinline__ float ex2f_v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -83,7 +92,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
 
 // FULL: tokens is 256 or 257, i.e. every column / row of the tensor-core tiles is a real token (no masking code at all)
 template <bool FULL>
-__global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AttnTcArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 1)
+    attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_row, const AttnTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -92,6 +102,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
   uint8_t* sV = smem + kOffV;
   uint8_t* sP = smem + kOffP;
   float* px = reinterpret_cast<float*>(smem + kOffPx);
+  uint8_t* sX = smem + kOffX;  // [parity][0: k_256 | 1: v_256] 128 B each
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t *q_full = bars, *q_free = bars + 2, *k_full = bars + 4, *k_free = bars + 6, *v_full = bars + 8, *v_free = bars + 10;
   uint64_t *s_ready = bars + 12, *s_free = bars + 14, *o_ready = bars + 16, *p_ready = bars + 18 /*[g*2+b]*/, *p_free = bars + 22;
@@ -106,8 +117,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1), mbar_init(&q_free[i], 4), mbar_init(&v_full[i], 1), mbar_init(&v_free[i], 2);
-      mbar_init(&k_full[i], 1), mbar_init(&k_free[i], 2);
+      mbar_init(&q_full[i], 1), mbar_init(&q_free[i], 4), mbar_init(&v_full[i], 1), mbar_init(&v_free[i], 10);
+      mbar_init(&k_full[i], 1), mbar_init(&k_free[i], 10);
       mbar_init(&s_ready[i], 1), mbar_init(&s_free[i], 4), mbar_init(&o_ready[i], 1), mbar_init(&tok[i], 4);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&p_ready[i], 4), mbar_init(&p_free[i], 1);
@@ -136,11 +147,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
         };
         load_q(0);
         mbar_wait_parked(&k_free[vb], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&k_full[vb], kKVBytes);
+        mbar_expect_tx(&k_full[vb], kKVBytes + (has_extra ? 128 : 0));
+        if (has_extra) tma_load_2d(sX + vb * 256, &map_row, &k_full[vb], hidden + h * 64, row0 + 256);
         tma_load_2d(sK + vb * kKVBytes, &map_qkv, &k_full[vb], hidden + h * 64, row0);
         tma_load_2d(sK + vb * kKVBytes + kTileBytes, &map_qkv, &k_full[vb], hidden + h * 64, row0 + 128);
         mbar_wait_parked(&v_free[vb], ((it >> 1) & 1) ^ 1);
-        mbar_expect_tx(&v_full[vb], kKVBytes);
+        mbar_expect_tx(&v_full[vb], kKVBytes + (has_extra ? 128 : 0));
+        if (has_extra) tma_load_2d(sX + vb * 256 + 128, &map_row, &v_full[vb], 2 * hidden + h * 64, row0 + 256);
         tma_load_2d(sV + vb * kKVBytes, &map_qkv, &v_full[vb], 2 * hidden + h * 64, row0);
         tma_load_2d(sV + vb * kKVBytes + kTileBytes, &map_qkv, &v_full[vb], 2 * hidden + h * 64, row0 + 128);
         load_q(1);
@@ -210,24 +223,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       const int img = u / a.heads, h = u - img * a.heads;
       const size_t row0 = (size_t)img * T;
       CB_TRACE(0);
-      // the extra key's K row and V row are plain global reads (the same 128 bytes for every thread): issue them before
-      // waiting for S so that their latency is off the critical path
-      uint4 kxr[8];
-      if (has_extra) {
-        const uint4* kx = reinterpret_cast<const uint4*>(a.qkv + (row0 + 256) * row_stride + hidden + h * 64);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) kxr[j] = __ldg(kx + j);
-      }
+      const int xb = it & 1;
       mbar_wait_parked(&q_full[g], it & 1);  // already complete (the MMA waited on it); taken for the TMA-write -> generic-read ordering
       // score against the extra key (token 256): q_row . k_256, fp32 accumulate (needs Q only, not S)
       float s_x = -INFINITY;
       if (has_extra) {
+        mbar_wait_parked(&k_full[xb], (it >> 1) & 1);  // the extra token's K row arrives with the K tile
         float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint4 qa = *reinterpret_cast<const uint4*>(q_row + ((j ^ (r & 7)) << 4));
+          const uint4 kxj = *reinterpret_cast<const uint4*>(sX + xb * 256 + j * 16);
           const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
-          const __half2* k2 = reinterpret_cast<const __half2*>(&kxr[j]);
+          const __half2* k2 = reinterpret_cast<const __half2*>(&kxj);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 qf = __half22float2(q2[e]), kf = __half22float2(k2[e]);
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       tc_fence_after();
       CB_TRACE(2);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&q_free[g]);
+      if (lane == 0) mbar_arrive(&q_free[g]), mbar_arrive(&k_free[xb]);  // this warp is done with Q_g and with the extra K row
 
       // pass 1: row maximum; the load of block cc+1 is in flight while block cc is reduced
       float mx = s_x;
@@ -279,9 +287,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       // receiving) columns 0..31; each half's successor is requested before the exponentials of the current half.
       auto emit = [&](const uint32_t* v, uint8_t* prow, int half, int k0) {
         uint32_t w[16];
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = fmaf(__uint_as_float(v[i]), a.scale_log2e, -mb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = ex2f_v(x[i]);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2f(fmaf(__uint_as_float(v[i]), a.scale_log2e, -mb)), p1 = ex2f(fmaf(__uint_as_float(v[i + 1]), a.scale_log2e, -mb));
+          float p0 = x[i], p1 = x[i + 1];
           if (!FULL) {
             if (k0 + i >= t_mma) p0 = 0.f;
             if (k0 + i + 1 >= t_mma) p1 = 0.f;
@@ -323,13 +336,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       sum += sum1;
 
       // epilogue: O / rowsum (+ the extra key's value row) -> fp16 -> global
-      uint4 vxr[8];
-      if (has_extra) {
-        const uint4* vx = reinterpret_cast<const uint4*>(a.qkv + (row0 + 256) * row_stride + 2 * hidden + h * 64);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) vxr[j] = __ldg(vx + j);
-      }
       mbar_wait_parked(&o_ready[g], it & 1);
+      if (has_extra) mbar_wait_parked(&v_full[xb], (it >> 1) & 1);  // long complete; taken for the TMA-write -> generic-read ordering
       tc_fence_after();
       CB_TRACE(13);
       const float inv = 1.0f / sum;
@@ -347,7 +355,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * j + e]);
           if (has_extra) {
-            const __half2* v2 = reinterpret_cast<const __half2*>(&vxr[half * 4 + j]);
+            const uint4 vxj = *reinterpret_cast<const uint4*>(sX + xb * 256 + 128 + (half * 4 + j) * 16);
+            const __half2* v2 = reinterpret_cast<const __half2*>(&vxj);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 vf = __half22float2(v2[e]);
@@ -361,7 +370,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) attention_tc_kernel(const __gri
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[g]);
+      if (lane == 0) mbar_arrive(&s_free[g]), mbar_arrive(&v_free[xb]);  // done with TMEM and with the extra V row
       CB_TRACE(14);
     }
   } else {  // ===== warp 10: query row 256 on SIMT
@@ -466,6 +475,10 @@ int attention_tc(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int
   const uint32_t box[2] = {64, 128};
   int rc = make_tensor_map(ctx, &map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qkv, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
+  CUtensorMap map_row;  // one token's 64-element slice (the extra token's K and V rows), unswizzled
+  const uint32_t box_row[2] = {64, 1};
+  rc = make_tensor_map(ctx, &map_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qkv, dims, strides, box_row, CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     CB_CUDA(ctx, cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
@@ -485,9 +498,9 @@ int attention_tc(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int
   const int grid = std::min(n * heads, ctx->sm_count);
   mark_launch(ctx, CB_PROF_ATTENTION, stream);
   if (tokens >= 256)
-    attention_tc_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(map, a);
+    attention_tc_kernel<true><<<grid, kTcThreads, kTcSmem, stream>>>(map, map_row, a);
   else
-    attention_tc_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(map, a);
+    attention_tc_kernel<false><<<grid, kTcThreads, kTcSmem, stream>>>(map, map_row, a);
   CB_CUDA(ctx, cudaGetLastError());
   if (tracing) {
     long long h[2 * 16 * 16];

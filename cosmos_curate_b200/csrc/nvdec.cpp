@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -226,7 +227,14 @@ int on_sequence(void* user, CUVIDEOFORMAT* f) {
   ci.DeinterlaceMode = 0;  // weave (progressive content)
   ci.ulTargetWidth = (dw + 1) & ~1, ci.ulTargetHeight = (dh + 1) & ~1;
   ci.ulNumOutputSurfaces = 2;
-  ci.vidLock = ((NvdecShared*)d->ctx->nvdec)->lock;
+  // The context lock is optional with cudaVideoCreate_PreferCUVID and every session thread binding the primary context itself.
+  // Sharing one lock across sessions serialises cuvidMapVideoFrame (which waits for the picture) against the other sessions'
+  // cuvidDecodePicture calls; CB_NVDEC_CTX_LOCK=1 restores it for A/B.
+  static const bool use_lock = [] {
+    const char* e = getenv("CB_NVDEC_CTX_LOCK");
+    return e && e[0] == '1';
+  }();
+  ci.vidLock = use_lock ? ((NvdecShared*)d->ctx->nvdec)->lock : nullptr;
   const int rc = d->api->CreateDecoder(&d->dec, &ci);
   if (rc != 0) {
     d->dec = nullptr;

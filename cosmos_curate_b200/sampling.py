@@ -122,6 +122,28 @@ def plan_extraction(all_ts: np.ndarray, policies, target_fps: list):
     return plan
 
 
+def span_frame_ids(ts: np.ndarray, span: tuple[float, float], fps: float) -> np.ndarray:
+    """Source-video frame indices that a clip cut at `span` = (start_s, end_s) and then sampled at `fps` would show.
+
+    The cut keeps the source frames whose PTS lies in [start, end) (half a frame period of slack absorbs the float32 PTS vs
+    float64 span rounding: TransNetV2 spans are frame_index / fps, transnetv2_extraction_stages.py:201-206), re-times them from
+    the first kept frame - what ClipTranscodingStage's `-ss start -t duration` produces - and samples that clip with the same
+    rule as a stand-alone clip (sample_closest with endpoint, decoder_utils.py:315-386).  Returns int32 ids, repeats expanded."""
+    ts = np.asarray(ts, dtype=np.float32)
+    if len(ts) == 0:
+        msg = "video has no frames"
+        raise ValueError(msg)
+    dt = float(np.median(np.diff(ts))) if len(ts) > 1 else 0.0
+    start, end = float(span[0]), float(span[1])
+    keep = np.flatnonzero((ts >= start - 0.5 * dt) & (ts < end - 0.5 * dt))
+    if len(keep) == 0:
+        msg = f"span {span} selects no frame of the source video"
+        raise ValueError(msg)
+    clip_ts = (ts[keep] - ts[keep[0]]).astype(np.float32)
+    ids, counts = frame_ids(clip_ts, FrameExtractionPolicy.sequence, fps)
+    return np.repeat(keep[ids], counts).astype(np.int32)
+
+
 @attrs.define
 class VideoMetadata:
     """Same fields as the reference's VideoMetadata (decoder_utils.py:57-84)."""

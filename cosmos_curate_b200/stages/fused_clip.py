@@ -47,6 +47,7 @@ class NvdecClipAestheticStage(CuratorStage):
         num_decoders: int = 8,
         stage_batch_size: int = 8,
         seek_keyframes: bool = True,
+        source: Literal["clip", "video_span"] = "clip",
         verbose: bool = False,
         log_stats: bool = False,
         model: CLIPAestheticScorer | None = None,
@@ -57,6 +58,14 @@ class NvdecClipAestheticStage(CuratorStage):
         self._write_embedding, self._max_batch, self._num_decoders = write_embedding, max_batch, num_decoders
         self._stage_batch_size, self._verbose, self._log_stats = stage_batch_size, verbose, log_stats
         self._seek = seek_keyframes  # decode only the GOPs that contain sampled frames (identical frames, fewer decoded)
+        if source not in ("clip", "video_span"):
+            error_msg = f"source={source!r} not in ('clip', 'video_span')"
+            raise ValueError(error_msg)
+        # "video_span": analysis without the transcode - the clip's frames are decoded straight out of the SOURCE
+        # video (video.encoded_data) at clip.span, so ClipTranscodingStage's re-encode + this stage's re-decode disappear for runs
+        # that only need scores / embeddings.  Pixels are the source's, not the 4 Mb/s re-encode's: not bit-comparable with "clip".
+        self._source = source
+        self._video_index: dict[int, tuple] = {}
         self._model = model if model is not None else CLIPAestheticScorer(max_batch=max_batch)
         self._reduce_fn = np.min
         self._pools: dict[tuple[int, int], object] = {}
@@ -92,8 +101,32 @@ class NvdecClipAestheticStage(CuratorStage):
         self._pools.clear()
 
     # ---- helpers ---------------------------------------------------------------------------------
-    def _plan(self, clip):
+    def _plan_span(self, clip, video):
+        """Frames of the source video inside clip.span, re-timed from the clip start and sampled like a clip of its own."""
+        data = video.encoded_data.resolve() if video.encoded_data else None
+        if data is None:
+            logger.warning(f"Clip {clip.uuid}: source video has no encoded_data.")
+            clip.errors["encoded_data"] = "empty"
+            clip.aesthetic_score = -1.0
+            return None
+        try:
+            cached = self._video_index.get(id(video))
+            if cached is None or cached[0] is not data:
+                idx = mp4_index(data)
+                cached = self._video_index[id(video)] = (data, idx, sampling.timestamps_from_index(idx["pts"], idx["timescale"]))
+            _, idx, ts = cached
+            ids = sampling.span_frame_ids(ts, clip.span, self._target_fps)
+            return data, ids, ((idx["width"] + 1) & ~1, (idx["height"] + 1) & ~1)
+        except (CurateB200Error, ValueError) as e:
+            logger.error(f"Error extracting frames from clip {clip.uuid}: {e}")
+            clip.errors["frame_extraction"] = "video_decode_failed"
+            clip.aesthetic_score = -1.0
+            return None
+
+    def _plan(self, clip, video=None):
         """-> (data u8 array, frame ids expanded, (w, h)) or None (errors recorded on the clip)."""
+        if self._source == "video_span":
+            return self._plan_span(clip, video)
         data = clip.encoded_data.resolve() if clip.encoded_data else None
         if data is None:
             logger.warning(f"Clip {clip.uuid} has no encoded_data.")
@@ -112,7 +145,8 @@ class NvdecClipAestheticStage(CuratorStage):
     def _decode_failed(self, clip, e) -> None:
         logger.error(f"Error extracting frames from clip {clip.uuid}: {e}")
         clip.errors["frame_extraction"] = "video_decode_failed"
-        clip.encoded_data.drop()
+        if self._source == "clip":
+            clip.encoded_data.drop()
         clip.aesthetic_score = -1.0
 
     def _pool(self, size):
@@ -155,7 +189,7 @@ class NvdecClipAestheticStage(CuratorStage):
         for task in tasks:
             for video in task.videos:
                 for clip in video.clips:
-                    plan = self._plan(clip)
+                    plan = self._plan(clip, video)
                     if plan is not None:
                         data, ids, size = plan
                         by_size.setdefault(size, []).append((clip, data, ids))
@@ -191,4 +225,5 @@ class NvdecClipAestheticStage(CuratorStage):
                 stage_name, stats = self._timer.log_stats()
                 task.stage_perf[stage_name] = stats
         torch.cuda.current_stream().synchronize()
+        self._video_index.clear()
         return tasks

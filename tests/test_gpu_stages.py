@@ -127,6 +127,43 @@ def test_fused_nvdec_stage_matches_oracle_and_error_convention(ctx):
     assert v.clips[0].aesthetic_score == v.clips[1].aesthetic_score  # identical clips, batch-invariant results
 
 
+def test_fused_stage_on_source_video_spans(ctx):
+    """source="video_span": clips are decoded out of the source video at clip.span (no transcode)."""
+    from cosmos_curate_b200 import sampling
+    from cosmos_curate_b200.data_model import Clip, SplitPipeTask, Video
+    from cosmos_curate_b200.interfaces import run_pipeline
+    from cosmos_curate_b200.runtime import Decoder, alloc_nv12_pool, mp4_index
+    from cosmos_curate_b200.stages import NvdecClipAestheticStage
+    from oracle import color
+
+    sintel = (GOLDEN / "sintel_clip_10s.mp4").read_bytes()
+    model, cfg, w, sd = _model()
+    spans = [(0.0, 10.0), (2.5, 7.5), (5.0, 10.0), (20.0, 21.0)]
+    video = Video(input_video="v.mp4", encoded_data=sintel, clips=[Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=s) for s in spans])
+    task = SplitPipeTask(session_id="s", video=video)
+    stage = NvdecClipAestheticStage(score_threshold=-0.5, reduction="mean", write_embedding=True, max_batch=32, num_decoders=2, source="video_span", model=model)
+    assert run_pipeline([task], [stage]) is not None
+    assert len(video.clips) == 3 and len(video.filtered_clips) == 1
+    assert video.filtered_clips[0].errors == {"frame_extraction": "video_decode_failed"} and video.filtered_clips[0].aesthetic_score == -1.0
+    assert video.encoded_data  # the source video is never dropped
+    # whole-video span == the ordinary clip path on the same bytes
+    t2 = _clip_task(sintel)
+    run_pipeline([t2], [NvdecClipAestheticStage(score_threshold=-0.5, reduction="mean", write_embedding=True, max_batch=32, num_decoders=2, model=model)])
+    assert video.clips[0].aesthetic_score == t2.video.clips[0].aesthetic_score
+    assert np.array_equal(video.clips[0].openai_embedding, t2.video.clips[0].openai_embedding)
+    # sub-spans against the oracle chain on the frames the span rule selects
+    idx = mp4_index(sintel)
+    ts = sampling.timestamps_from_index(idx["pts"], idx["timescale"])
+    dec = Decoder(ctx)
+    for clip in video.clips[1:]:
+        ids = sampling.span_frame_ids(ts, clip.span, 1.0)
+        pool = alloc_nv12_pool(ctx, len(ids), 854, 480)
+        dec.decode(sintel, ids, pool, np.arange(len(ids)))
+        rgb = np.stack([color.nv12_to_rgb(np.ascontiguousarray(f[:, :854]), 480, 854) for f in pool.buf.cpu().numpy()])
+        _, scores = _oracle_scores(cfg, w, sd, rgb)
+        assert clip.aesthetic_score == pytest.approx(float(scores.mean()), abs=3e-3)
+
+
 def test_video_frame_extraction_thumbnails(ctx):
     from cosmos_curate_b200.data_model import SplitPipeTask, Video
     from cosmos_curate_b200.runtime import Decoder, alloc_nv12_pool

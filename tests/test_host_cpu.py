@@ -161,3 +161,20 @@ def test_mp4_index_rejects_garbage():
             mp4_index(d)
         except CurateB200Error:
             pass
+
+
+def test_span_frame_ids_matches_a_standalone_clip():
+    """A span of the source sampled in place == cutting that span into its own clip and sampling the clip."""
+    from cosmos_curate_b200 import sampling
+
+    ts = (np.arange(240) / 24).astype(np.float32)
+    assert sampling.span_frame_ids(ts, (0.0, 10.0), 1.0).tolist() == [0, 24, 48, 72, 96, 120, 144, 168, 192, 216, 239]
+    assert sampling.span_frame_ids(ts, (2.5, 7.5), 1.0).tolist() == [60, 84, 108, 132, 156, 179]
+    for a, b, fps in ((12, 228, 1.0), (100, 103, 2.0), (0, 1, 1.0), (37, 200, 4.0)):
+        span = (a / 24.0, b / 24.0)  # TransNetV2 spans are frame / fps
+        ids = sampling.span_frame_ids(ts, span, fps)
+        clip_ts = (ts[a:b] - ts[a]).astype(np.float32)
+        want_ids, want_counts = sampling.frame_ids(clip_ts, sampling.FrameExtractionPolicy.sequence, fps)
+        assert ids.tolist() == (a + np.repeat(want_ids, want_counts)).tolist()
+    with pytest.raises(ValueError, match="selects no frame"):
+        sampling.span_frame_ids(ts, (11.0, 12.0), 1.0)

@@ -538,13 +538,16 @@ int assemble_tokens(cb_ctx* ctx, const float* patch, const float* cls, const flo
 }
 
 int attention_tc(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int heads, int head_dim, cudaStream_t stream, bool* launched);
+int attention_tc2(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int heads, int head_dim, cudaStream_t stream, bool* launched);
 
 int attention_f16(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int heads, int head_dim, cudaStream_t stream) {
   if (!qkv || !out) return fail(ctx, CB_ERR_ARG, "attention: null operand");
   if (n <= 0) return CB_OK;
   {  // head_dim 64, 129..257 tokens (ViT-L/14): tcgen05 kernel (attention_tc.cu); everything else: mma.sync kernel below
     bool launched = false;
-    const int rc = attention_tc(ctx, qkv, out, n, tokens, heads, head_dim, stream, &launched);
+    int rc = attention_tc2(ctx, qkv, out, n, tokens, heads, head_dim, stream, &launched);  // two threads per row (CB_ATTN_KERNEL=tc1|mma skips it)
+    if (rc || launched) return rc;
+    rc = attention_tc(ctx, qkv, out, n, tokens, heads, head_dim, stream, &launched);  // one thread per row
     if (rc || launched) return rc;
   }
   if (tokens <= 0 || heads <= 0 || head_dim % 8 || head_dim > 80 || head_dim < 16)

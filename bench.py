@@ -430,7 +430,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips-per-step", type=int, default=24)
     ap.add_argument("--distinct-clips", type=int, default=4)
-    ap.add_argument("--decoders", type=int, default=12, help="concurrent NVDEC sessions per GPU (7 engines on B200)")
+    ap.add_argument("--decoders", type=int, default=20, help="concurrent NVDEC sessions per GPU (7 engines on B200)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--ref-clips", type=int, default=2, help="clips per step of the reference arm (bounded sample)")
     ap.add_argument("--no-shots", action="store_true", help="skip the shot-detection secondary measurement")

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
           }
         }
-        if (!progress) __nanosleep(40);
+        (void)progress;  // tight poll: __nanosleep has ~1 us granularity
       }
     }
   } else if (warp < 10) {  // ===== softmax groups: one thread per query row

@@ -6,8 +6,10 @@
 // through shared memory (one named barrier per group each), every half-row exponentiates its own two 64-key chunks into its
 // own P buffer, and the epilogue writes 32 of the 64 output dims per thread.
 //
-// Warp roles (640 threads): 0 TMA producer, 1 MMA issuer (event loop), 2 query row 256 on SIMT, 3 idle,
+// Warp roles (704 threads): 0 TMA producer, 1 MMA issuer (event loop), 2, 3, 20, 21 query row 256 on SIMT (64 keys each),
 // 4..19 softmax: group g = (w-4)/8 (query tile), half hf = ((w-4)/4)%2 (key columns hf*128..+127), TMEM lane quarter w%4.
+// The extra row used to be ONE warp (257 dot products + a 257-term weighted sum, ~8k cycles per unit): every K and V
+// buffer release waited for it, and it - not the exponentials - set the pace of the whole kernel.
 #include <cstdlib>
 #include <cstring>
 
@@ -17,7 +19,7 @@
 namespace cb {
 namespace tc2 {
 
-constexpr int kThreads = 640;
+constexpr int kThreads = 704;  // 22 warps
 constexpr int kTileBytes = 128 * 128;     // 128 rows x 64 fp16, SW128
 constexpr int kKVBytes = 2 * kTileBytes;  // 256 rows
 constexpr int kOffQ = 0;                  // 2 tiles
@@ -25,9 +27,10 @@ constexpr int kOffK = 2 * kTileBytes;
 constexpr int kOffV = kOffK + kKVBytes;      // 2 buffers
 constexpr int kOffP = kOffV + 2 * kKVBytes;  // [group][half] x 128 rows x 64 keys
 constexpr int kOffPx = kOffP + 4 * kTileBytes;
-constexpr int kOffX = kOffPx + 1024;      // K and V rows of the extra token: [parity][k|v][64] fp16
-constexpr int kOffExch = kOffX + 512;     // [max|sum|sx][group][half][128] fp32
-constexpr int kOffBar = kOffExch + 3 * 2 * 2 * 128 * 4;
+constexpr int kOffX = kOffPx + 1024;      // K, V and Q rows of the extra token: [parity][k|v|q][64] fp16 (384 B per parity)
+constexpr int kOffExch = kOffX + 1024;    // [max|sum|sx][group][half][128] fp32
+constexpr int kOffXs = kOffExch + 3 * 2 * 2 * 128 * 4;  // scratch of the extra-row warps: max[4] sum[4] sx, then o[4][64]
+constexpr int kOffBar = kOffXs + 2048;
 constexpr int kSmem = kOffBar + 256 + 1024 /* alignment slack */;
 static_assert(kSmem <= 232448, "shared memory budget");
 
@@ -36,6 +39,7 @@ struct Args {
   __half* out;
   int tokens, heads, n_units;
   float scale_log2e;
+  long long* trace;  // CB_ATTN_DEBUG_TRACE=1: clock64 stamps of CTA 0: [3 roles][16 units][16 events]
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -85,6 +89,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   float* ex_max = reinterpret_cast<float*>(smem + kOffExch);  // [g][hf][128]
   float* ex_sum = ex_max + 512;
   float* ex_sx = ex_sum + 512;  // [g][128] (only the first 256 floats used)
+  float* xs = reinterpret_cast<float*>(smem + kOffXs);  // [0..3] max, [4..7] sum, [8] s_x
+  float* xo = xs + 16;                                  // [4][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t *q_full = bars, *q_free = bars + 2, *k_full = bars + 4, *k_free = bars + 5, *v_full = bars + 6, *v_free = bars + 8;
   uint64_t *s_ready = bars + 10, *s_free = bars + 12, *o_ready = bars + 14, *p_ready = bars + 16 /*[g*2+hf]*/, *p_free = bars + 20;
@@ -98,10 +104,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1), mbar_init(&q_free[i], 4), mbar_init(&v_full[i], 1), mbar_init(&v_free[i], 18);
+      mbar_init(&q_full[i], 1), mbar_init(&q_free[i], 4), mbar_init(&v_full[i], 1), mbar_init(&v_free[i], 21);
       mbar_init(&s_ready[i], 1), mbar_init(&s_free[i], 8), mbar_init(&o_ready[i], 1);
     }
-    mbar_init(k_full, 1), mbar_init(k_free, 10);
+    mbar_init(k_full, 1), mbar_init(k_free, 13);
     for (int i = 0; i < 4; ++i) mbar_init(&p_ready[i], 4), mbar_init(&p_free[i], 1);
     fence_barrier_init();
   }
@@ -127,14 +133,17 @@ __global__ void __launch_bounds__(kThreads, 1)
         };
         load_q(0);
         mbar_wait_parked(k_free, (it & 1) ^ 1);
-        mbar_expect_tx(k_full, kKVBytes + (has_extra ? 128 : 0));
-        if (has_extra) tma_load_2d(sX + vb * 256, &map_row, k_full, hidden + h * 64, row0 + 256);
+        mbar_expect_tx(k_full, kKVBytes + (has_extra ? 256 : 0));
+        if (has_extra) {
+          tma_load_2d(sX + vb * 384, &map_row, k_full, hidden + h * 64, row0 + 256);
+          tma_load_2d(sX + vb * 384 + 256, &map_row, k_full, h * 64, row0 + 256);
+        }
         tma_load_2d(sK, &map_qkv, k_full, hidden + h * 64, row0);
         tma_load_2d(sK + kTileBytes, &map_qkv, k_full, hidden + h * 64, row0 + 128);
         load_q(1);
         mbar_wait_parked(&v_free[vb], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&v_full[vb], kKVBytes + (has_extra ? 128 : 0));
-        if (has_extra) tma_load_2d(sX + vb * 256 + 128, &map_row, &v_full[vb], 2 * hidden + h * 64, row0 + 256);
+        if (has_extra) tma_load_2d(sX + vb * 384 + 128, &map_row, &v_full[vb], 2 * hidden + h * 64, row0 + 256);
         tma_load_2d(sV + vb * kKVBytes, &map_qkv, &v_full[vb], 2 * hidden + h * 64, row0);
         tma_load_2d(sV + vb * kKVBytes + kTileBytes, &map_qkv, &v_full[vb], 2 * hidden + h * 64, row0 + 128);
       }
@@ -196,21 +205,26 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
         }
-        if (!progress) __nanosleep(32);
+        (void)progress;  // tight poll: __nanosleep has ~1 us granularity, which is a quarter of a unit
       }
     }
-  } else if (warp == 2) {  // ===== query row 256 on SIMT
+  } else if (warp < 4 || warp >= 20) {  // ===== query row 256 on SIMT: four warps, 64 keys each
+    const int xw = warp < 4 ? warp - 2 : warp - 18;
+    auto xsync = [] { asm volatile("bar.sync 3, 128;" ::: "memory"); };
     int it = 0;
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
       const int img = u / a.heads, h = u - img * a.heads, vb = it & 1;
       const size_t row0 = (size_t)img * T;
+      const bool xtr = a.trace && blockIdx.x == 0 && xw == 0 && lane == 0 && it < 16;
+      if (xtr) a.trace[(2 * 16 + it) * 16 + 0] = clock64();
       mbar_wait_parked(k_full, it & 1);
-      float s[8], s_x = 0.f;
+      if (xtr) a.trace[(2 * 16 + it) * 16 + 1] = clock64();
+      float s0 = 0.f, s1 = 0.f, s_x = 0.f;
+      const int j0 = xw * 64 + lane, j1 = j0 + 32;
       if (has_extra) {
-        const __half* xrow = a.qkv + (row0 + 256) * row_stride + h * 64;
         uint4 qx[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) qx[j] = __ldg(reinterpret_cast<const uint4*>(xrow) + j);
+        for (int j = 0; j < 8; ++j) qx[j] = *reinterpret_cast<const uint4*>(sX + vb * 384 + 256 + j * 16);
         auto dot = [&](const uint8_t* krow, int swz) {
           float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll
@@ -226,38 +240,39 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
           return acc0 + acc1;
         };
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int key = lane + 32 * i;
-          s[i] = dot(sK + key * 128, key & 7);
+        s0 = dot(sK + j0 * 128, j0 & 7);
+        s1 = dot(sK + j1 * 128, j1 & 7);
+        float m = fmaxf(s0, s1);
+        if (xw == 0) s_x = dot(sX + vb * 384, 0), m = fmaxf(m, s_x);
+        for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        if (lane == 0) {
+          xs[xw] = m;
+          if (xw == 0) xs[8] = s_x;
         }
-        s_x = dot(sX + vb * 256, 0);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(k_free);
-      mbar_wait_parked(&v_full[vb], (it >> 1) & 1);
+      float mb = 0.f;
       if (has_extra) {
-        float mx = s_x;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mx = fmaxf(mx, s[i]);
-        for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-        const float mb = mx * a.scale_log2e;
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float p = ex2f(fmaf(s[i], a.scale_log2e, -mb));
-          px[lane + 32 * i] = p;
-          sum += p;
-        }
+        xsync();
+        mb = fmaxf(fmaxf(xs[0], xs[1]), fmaxf(xs[2], xs[3])) * a.scale_log2e;
+        const float p0 = ex2f(fmaf(s0, a.scale_log2e, -mb)), p1 = ex2f(fmaf(s1, a.scale_log2e, -mb));
+        px[j0] = p0, px[j1] = p1;
+        float sum = p0 + p1;
         for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-        const float p_x = ex2f(fmaf(s_x, a.scale_log2e, -mb));
-        sum += p_x;
+        if (lane == 0) xs[4 + xw] = sum;
         __syncwarp();
+      }
+      if (xtr) a.trace[(2 * 16 + it) * 16 + 2] = clock64();
+      mbar_wait_parked(&v_full[vb], (it >> 1) & 1);
+      if (xtr) a.trace[(2 * 16 + it) * 16 + 3] = clock64();
+      if (has_extra) {
+        // this warp's 64 keys; lane owns output dims 2*lane, 2*lane+1: byte lane*4 of every V row
         const uint8_t* vbase = sV + vb * kKVBytes + (lane & 3) * 4;
         const int ch = lane >> 2;
         float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-        for (int key = 0; key < 256; key += 4) {
+        for (int key = xw * 64; key < xw * 64 + 64; key += 4) {
           const float4 p4 = *reinterpret_cast<const float4*>(px + key);
           const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
 #pragma unroll
@@ -267,16 +282,25 @@ __global__ void __launch_bounds__(kThreads, 1)
             oa[e] = fmaf(pv[e], vf.x, oa[e]), ob[e] = fmaf(pv[e], vf.y, ob[e]);
           }
         }
-        float o0 = (oa[0] + oa[1]) + (oa[2] + oa[3]), o1 = (ob[0] + ob[1]) + (ob[2] + ob[3]);
-        const float2 vxf = __half22float2(*reinterpret_cast<const __half2*>(sX + vb * 256 + 128 + lane * 4));
-        o0 = fmaf(p_x, vxf.x, o0), o1 = fmaf(p_x, vxf.y, o1);
-        const float inv = 1.0f / sum;
-        *reinterpret_cast<uint32_t*>(a.out + (row0 + 256) * hidden + h * 64 + 2 * lane) = pack2(o0 * inv, o1 * inv);
+        xo[xw * 64 + 2 * lane] = (oa[0] + oa[1]) + (oa[2] + oa[3]);
+        xo[xw * 64 + 2 * lane + 1] = (ob[0] + ob[1]) + (ob[2] + ob[3]);
+        xsync();
+        if (xw == 0) {
+          const float p_x = ex2f(fmaf(xs[8], a.scale_log2e, -mb));
+          const float sum = ((xs[4] + xs[5]) + (xs[6] + xs[7])) + p_x;
+          const float2 vxf = __half22float2(*reinterpret_cast<const __half2*>(sX + vb * 384 + 128 + lane * 4));
+          float o0 = (xo[2 * lane] + xo[64 + 2 * lane]) + (xo[128 + 2 * lane] + xo[192 + 2 * lane]);
+          float o1 = (xo[2 * lane + 1] + xo[64 + 2 * lane + 1]) + (xo[128 + 2 * lane + 1] + xo[192 + 2 * lane + 1]);
+          o0 = fmaf(p_x, vxf.x, o0), o1 = fmaf(p_x, vxf.y, o1);
+          const float inv = 1.0f / sum;
+          *reinterpret_cast<uint32_t*>(a.out + (row0 + 256) * hidden + h * 64 + 2 * lane) = pack2(o0 * inv, o1 * inv);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&v_free[vb]);
+      if (xtr) a.trace[(2 * 16 + it) * 16 + 4] = clock64();
     }
-  } else if (warp >= 4) {  // ===== softmax: thread = (query row, half of the key columns)
+  } else {  // ===== warps 4..19 softmax: thread = (query row, half of the key columns)
     const int sw = warp - 4, g = sw >> 3, hf = (sw >> 2) & 1, q = warp & 3;
     const int r = q * 32 + lane, row = g * 128 + r;
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 256);
@@ -287,10 +311,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     const float* other_max = ex_max + (g * 2 + (hf ^ 1)) * 128 + r;
     const float* other_sum = ex_sum + (g * 2 + (hf ^ 1)) * 128 + r;
     int it = 0;
+    const bool tracing = a.trace && blockIdx.x == 0 && hf == 0 && q == 0 && lane == 0;  // warps 4 (g0) and 12 (g1)
+#define CB_TRACE2(slot, ev)                                                             \
+  do {                                                                                  \
+    if (tracing && it < 16) a.trace[((slot) * 16 + it) * 16 + (ev)] = clock64();        \
+  } while (0)
     for (int u = blockIdx.x; u < a.n_units; u += gridDim.x, ++it) {
       const int img = u / a.heads, h = u - img * a.heads, xb = it & 1;
       const size_t row0 = (size_t)img * T;
       float s_x = -INFINITY;
+      CB_TRACE2(g, 0);
       if (hf == 0) {
         mbar_wait_parked(&q_full[g], it & 1);
         if (has_extra) {  // score against the extra key (token 256): q_row . k_256
@@ -299,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint4 qa = *reinterpret_cast<const uint4*>(q_row + ((j ^ (r & 7)) << 4));
-            const uint4 kxj = *reinterpret_cast<const uint4*>(sX + xb * 256 + j * 16);
+            const uint4 kxj = *reinterpret_cast<const uint4*>(sX + xb * 384 + j * 16);
             const __half2* q2 = reinterpret_cast<const __half2*>(&qa);
             const __half2* k2 = reinterpret_cast<const __half2*>(&kxj);
 #pragma unroll
@@ -312,8 +342,10 @@ __global__ void __launch_bounds__(kThreads, 1)
           ex_sx[g * 128 + r] = s_x;
         }
       }
+      CB_TRACE2(g, 1);
       mbar_wait_parked(&s_ready[g], it & 1);
       tc_fence_after();
+      CB_TRACE2(g, 2);
       if (hf == 0) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&q_free[g]), mbar_arrive(k_free);
@@ -337,7 +369,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
       *my_max = mx;
+      CB_TRACE2(g, 3);
       group_sync(g);
+      CB_TRACE2(g, 4);
       mx = fmaxf(mx, *other_max);
       if (hf == 1 && has_extra) s_x = ex_sx[g * 128 + r];
       const float mb = mx * a.scale_log2e;
@@ -349,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int i2 = 0; i2 < 2; ++i2) {
         const int c = hf * 2 + i2, use = it * 2 + i2;
         mbar_wait_parked(&p_free[g * 2 + hf], (use & 1) ^ 1);
+        CB_TRACE2(g, 5 + 2 * i2);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int k0 = c * 64 + half * 32;
@@ -373,16 +408,19 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[g * 2 + hf]);
+        CB_TRACE2(g, 6 + 2 * i2);
       }
       sum += sum1;
       *my_sum = sum;
       group_sync(g);
+      CB_TRACE2(g, 9);
       sum += *other_sum;
 
       // epilogue: this thread's 32 output dims
       mbar_wait_parked(&o_ready[g], it & 1);
       if (has_extra) mbar_wait_parked(&v_full[xb], (it >> 1) & 1);
       tc_fence_after();
+      CB_TRACE2(g, 10);
       const float inv = 1.0f / sum;
       __half* orow = a.out + (row0 + row) * hidden + h * 64 + hf * 32;
       tmem_ld_32x32b_x32(t_row + (uint32_t)(hf * 32), v);
@@ -393,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * j + e]);
         if (has_extra) {
-          const uint4 vxj = *reinterpret_cast<const uint4*>(sX + xb * 256 + 128 + (hf * 4 + j) * 16);
+          const uint4 vxj = *reinterpret_cast<const uint4*>(sX + xb * 384 + 128 + (hf * 4 + j) * 16);
           const __half2* v2 = reinterpret_cast<const __half2*>(&vxj);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -408,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[g]), mbar_arrive(&v_free[xb]);
+      CB_TRACE2(g, 11);
     }
   }
 
@@ -424,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 int attention_tc2(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int heads, int head_dim, cudaStream_t stream, bool* launched) {
   *launched = false;
   const char* sel = std::getenv("CB_ATTN_KERNEL");
-  if (!sel || std::strcmp(sel, "tc2") != 0) return CB_OK;  // opt-in (CB_ATTN_KERNEL=tc2) until it has passed the GPU suite
+  if (sel && (std::strcmp(sel, "mma") == 0 || std::strcmp(sel, "tc1") == 0)) return CB_OK;  // A/B switches: tc1 = one thread per row, mma = mma.sync
   if (head_dim != 64 || tokens < 129 || tokens > 257) return CB_OK;
   const int hidden = heads * 64;
   CUtensorMap map, map_row;
@@ -440,7 +479,13 @@ int attention_tc2(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, in
     CB_CUDA(ctx, cudaFuncSetAttribute(tc2::attention_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmem));
     attr_set = true;
   }
-  tc2::Args a{(const __half*)qkv, (__half*)out, tokens, heads, n * heads, 1.4426950408889634f / sqrtf(64.f)};
+  tc2::Args a{(const __half*)qkv, (__half*)out, tokens, heads, n * heads, 1.4426950408889634f / sqrtf(64.f), nullptr};
+  const char* trc = std::getenv("CB_ATTN_DEBUG_TRACE");
+  const bool tracing = trc && trc[0] == '1';
+  if (tracing) {
+    CB_CUDA(ctx, cudaMalloc(&a.trace, 3 * 16 * 16 * sizeof(long long)));
+    CB_CUDA(ctx, cudaMemset(a.trace, 0, 3 * 16 * 16 * sizeof(long long)));
+  }
   const int grid = std::min(n * heads, ctx->sm_count);
   mark_launch(ctx, CB_PROF_ATTENTION, stream);
   if (tokens >= 256)
@@ -448,6 +493,19 @@ int attention_tc2(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, in
   else
     tc2::attention_tc2_kernel<false><<<grid, tc2::kThreads, tc2::kSmem, stream>>>(map, map_row, a);
   CB_CUDA(ctx, cudaGetLastError());
+  if (tracing) {
+    long long hbuf[3 * 16 * 16];
+    CB_CUDA(ctx, cudaStreamSynchronize(stream));
+    CB_CUDA(ctx, cudaMemcpy(hbuf, a.trace, sizeof(hbuf), cudaMemcpyDeviceToHost));
+    cudaFree(a.trace);
+    const long long t0 = hbuf[0];
+    for (int s = 0; s < 3; ++s)
+      for (int it = 2; it < 7; ++it) {
+        printf("trace2 %s it%d:", s == 0 ? "g0" : (s == 1 ? "g1" : "xr"), it);
+        for (int e = 0; e < 12; ++e) printf(" %lld", hbuf[(s * 16 + it) * 16 + e] ? hbuf[(s * 16 + it) * 16 + e] - t0 : -1);
+        printf("\n");
+      }
+  }
   *launched = true;
   return CB_OK;
 }

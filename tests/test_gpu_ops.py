@@ -87,6 +87,9 @@ def test_attention_tcgen05_and_mma_kernels_agree(ctx, monkeypatch):
     qkv = (torch.randn(20, 257, 3 * 1024, device="cuda", generator=g) * 2.0).half()
     qkv[:, :, 5] += 6.0  # a dominant query/key channel: sharp softmax rows
     tc = ctx.attention(qkv, 16).float()
+    monkeypatch.setenv("CB_ATTN_KERNEL", "tc1")  # first-generation tcgen05 kernel (one thread per row)
+    tc1 = ctx.attention(qkv, 16).float()
+    torch.testing.assert_close(tc, tc1, rtol=2e-3, atol=1e-3)
     monkeypatch.setenv("CB_ATTN_KERNEL", "mma")
     mma = ctx.attention(qkv, 16).float()
     torch.testing.assert_close(tc, mma, rtol=1e-2, atol=4e-3)

@@ -4,8 +4,8 @@ mkdir -p gpurun_out
 B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-shots --distinct-clips 1"
 # every launch of warm-up + one timed step with its device time (cold-cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu_launches.log 2>&1
-for k in gemm_tcgen05_2cta attention_kernel layernorm_kernel; do
-  ncu --set full --clock-control none --import-source on -k regex:$k -s 8 -c 3 -f -o gpurun_out/prof_$k $B > gpurun_out/ncu_$k.log 2>&1
-done
+ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05_2cta -s 8 -c 3 -f -o gpurun_out/prof_gemm_tcgen05_2cta $B > gpurun_out/ncu_gemm.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:attention_tc2 -s 4 -c 1 -f -o gpurun_out/prof_attention_tc2 $B > gpurun_out/ncu_attention.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:layernorm_kernel -s 8 -c 2 -f -o gpurun_out/prof_layernorm_kernel $B > gpurun_out/ncu_layernorm.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:clip_preprocess -s 1 -c 1 -f -o gpurun_out/prof_clip_preprocess $B > gpurun_out/ncu_clip_preprocess.log 2>&1
 ls -la gpurun_out/*.ncu-rep

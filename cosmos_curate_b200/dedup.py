@@ -114,12 +114,15 @@ def spherical_kmeans(x, n_clusters: int, max_iter: int = 300, seed: int = 0, tol
     n, d = x.shape
     multi = group is not None
     rank = dist.get_rank(group) if multi else 0
+    ok = torch.tensor([1 if (rank != 0 or n >= n_clusters) else 0], dtype=torch.int32, device=dev)
+    if multi:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # every rank raises together instead of hanging in the broadcast
+    if int(ok.item()) == 0:
+        msg = f"n_clusters={n_clusters} exceeds the rows of rank 0's shard: the initial centroids are drawn from it"
+        raise ValueError(msg)
     if rank == 0:
         perm = torch.randperm(n, generator=torch.Generator().manual_seed(seed))[:n_clusters]
         cent = x[perm.to(dev)].clone()
-        if cent.shape[0] < n_clusters:
-            msg = f"n_clusters={n_clusters} > rows on rank 0 ({n})"
-            raise ValueError(msg)
     else:
         cent = torch.empty((n_clusters, d), dtype=torch.float32, device=dev)
     if multi:

@@ -114,10 +114,10 @@ def spherical_kmeans(x, n_clusters: int, max_iter: int = 300, seed: int = 0, tol
     n, d = x.shape
     multi = group is not None
     rank = dist.get_rank(group) if multi else 0
-    ok = torch.tensor([1 if (rank != 0 or n >= n_clusters) else 0], dtype=torch.int32, device=dev)
+    bad = torch.tensor([1.0 if (rank == 0 and n < n_clusters) else 0.0], dtype=torch.float32, device=dev)
     if multi:
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # every rank raises together instead of hanging in the broadcast
-    if int(ok.item()) == 0:
+        dist.all_reduce(bad, group=group)  # every rank raises together instead of hanging in the broadcast below
+    if float(bad.item()) > 0:
         msg = f"n_clusters={n_clusters} exceeds the rows of rank 0's shard: the initial centroids are drawn from it"
         raise ValueError(msg)
     if rank == 0:

@@ -96,7 +96,9 @@ def test_attention_tcgen05_and_mma_kernels_agree(ctx, monkeypatch):
     again = ctx.attention(qkv, 16).float()
     assert torch.equal(mma, again)
     monkeypatch.delenv("CB_ATTN_KERNEL")
-    assert torch.equal(tc, ctx.attention(qkv, 16).float())  # deterministic
+    # The second-generation kernel issues a tile's four P.V chunk products in the order the two half-row streams deliver them (0,2,1,3 or
+    # 0,2,3,1): fp32 accumulation order can differ between runs, i.e. repeat runs agree to the last fp16 bit almost everywhere, not bitwise.
+    torch.testing.assert_close(tc, ctx.attention(qkv, 16).float(), rtol=2e-3, atol=1e-3)
 
 
 @pytest.mark.parametrize("kernel", ["1cta", "2cta"])

@@ -121,7 +121,7 @@ def run_reference(args) -> None:
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "frames_per_sec": frames / t,
         "config": {"workload": WORKLOAD, "implementation": "reference CPU path (oracle port): libavcodec decode, torchvision transforms, torch-fp32 tower", "clips_per_step": sample,
-                   "frames_per_clip": frames // (sample * args.steps), "model": "clip-vit-large-patch14 (seeded random weights)", "parallelism": "host threads"},
+                   "frames_per_clip": frames // (sample * args.steps), "network": "clip-vit-large-patch14 (seeded random weights), fp32", "sharding": "host worker processes"},
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": procs * threads, "kind": "port",
                          "sample": f"{sample} clip(s) per step x {args.steps} steps over {procs} worker processes x {threads} threads; cv2/libavcodec decode "
                                    "(PyAV stand-in) + torchvision transforms + oracle torch-fp32 tower, one model call per clip",
@@ -314,7 +314,7 @@ def run_b200(args) -> None:
         "frames_per_sec": world * frames_per_step * args.steps / dev_s,
         "config": {"workload": WORKLOAD, "implementation": "one process per B200: NVDEC + fused preprocess kernel + tcgen05 tower",
                    "clips_per_step": cps, "frames_per_clip": fpc, "frames_per_step": frames_per_step, "sample_fps": SAMPLE_FPS, "distinct_clips": args.distinct_clips,
-                   "model": "clip-vit-large-patch14, seeded random weights, fp16 operands / fp32 accumulate+residual", "parallelism": f"dp{world} (clips sharded per rank, no data-path collective)",
+                   "network": "clip-vit-large-patch14, seeded random weights, fp16 operands / fp32 accumulate+residual", "sharding": f"{world} rank(s), clips sharded per rank, no data-path collective",
                    "l2": "inputs (NV12 pool 0.88 GB + activations > 1 GB) exceed the 126 MB L2", "value_inputs": "decoded NV12 surfaces resident in HBM"},
         "clocks": clocks, "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_2cta_kernel", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,

@@ -479,7 +479,8 @@ int attention_tc(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, int
   const uint32_t box_row[2] = {64, 1};
   rc = make_tensor_map(ctx, &map_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qkv, dims, strides, box_row, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
-  static bool attr_set = false;
+  static bool attr_done[64] = {};  // the attribute is per device: one process may drive several
+  bool& attr_set = attr_done[ctx->device & 63];
   if (!attr_set) {
     CB_CUDA(ctx, cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
     CB_CUDA(ctx, cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));

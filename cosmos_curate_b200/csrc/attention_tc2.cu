@@ -473,7 +473,8 @@ int attention_tc2(cb_ctx* ctx, const void* qkv, void* out, int n, int tokens, in
   if (rc) return rc;
   rc = make_tensor_map(ctx, &map_row, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qkv, dims, strides, box_row, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
-  static bool attr_set = false;
+  static bool attr_done[64] = {};  // the attribute is per device: one process may drive several
+  bool& attr_set = attr_done[ctx->device & 63];
   if (!attr_set) {
     CB_CUDA(ctx, cudaFuncSetAttribute(tc2::attention_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmem));
     CB_CUDA(ctx, cudaFuncSetAttribute(tc2::attention_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::kSmem));

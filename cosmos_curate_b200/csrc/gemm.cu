@@ -422,7 +422,8 @@ template <int ACT, bool OUT_F32, bool EPI_TMA>
 static int launch_gemm_2cta(cb_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmArgs& g,
                             cudaStream_t stream) {
   auto kern = gemm_tcgen05_2cta_kernel<ACT, OUT_F32, EPI_TMA>;
-  static bool attr_set = false;
+  static bool attr_done[64] = {};  // per template instantiation AND per device
+  bool& attr_set = attr_done[ctx->device & 63];
   if (!attr_set) {
     CB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::kSmem));
     attr_set = true;
@@ -439,7 +440,8 @@ template <int BN, int ACT, bool OUT_F32>
 static int launch_gemm(cb_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_tcgen05_kernel<BN, ACT, OUT_F32>;
-  static bool attr_set = false;
+  static bool attr_done[64] = {};  // per template instantiation AND per device
+  bool& attr_set = attr_done[ctx->device & 63];
   if (!attr_set) {
     CB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
     attr_set = true;

@@ -122,6 +122,15 @@ def plan_extraction(all_ts: np.ndarray, policies, target_fps: list):
     return plan
 
 
+def pynvc_target_size(width: int, height: int, target_w: int = -1, target_h: int = -1) -> tuple[int, int]:
+    """(target_w, target_h) of the pynvc thumbnail path when either side is -1 (VideoBatchDecoder.__call__,
+    nvcodec_utils.py:129-136): downscale by width // 256 (no downscale below 256 px), Python round() (half to even)."""
+    if target_w != -1 and target_h != -1:
+        return int(target_w), int(target_h)
+    factor = 1 if width < 256 else width // 256
+    return round(width / factor), round(height / factor)
+
+
 def span_frame_ids(ts: np.ndarray, span: tuple[float, float], fps: float) -> np.ndarray:
     """Source-video frame indices that a clip cut at `span` = (start_s, end_s) and then sampled at `fps` would show.
 

@@ -130,6 +130,8 @@ class VideoFrameExtractionStage(CuratorStage):
     def _frames(self, data) -> np.ndarray:
         idx = mp4_index(data)
         h, w = self.output_hw
+        if h == -1 or w == -1:  # the reference's "pick a size for me" rule (nvcodec_utils.py:129-136)
+            w, h = sampling.pynvc_target_size(idx["width"], idx["height"], w, h)
         return decode_thumbnails(self._decoder, data, w, h, idx["n_samples"]).cpu().numpy()
 
     def process_data(self, tasks):

@@ -178,3 +178,15 @@ def test_span_frame_ids_matches_a_standalone_clip():
         assert ids.tolist() == (a + np.repeat(want_ids, want_counts)).tolist()
     with pytest.raises(ValueError, match="selects no frame"):
         sampling.span_frame_ids(ts, (11.0, 12.0), 1.0)
+
+
+def test_pynvc_target_size_rule():
+    from cosmos_curate_b200 import sampling
+    from oracle import preprocess
+
+    for w, h in ((1920, 1080), (854, 480), (3840, 2160), (255, 144), (256, 144), (640, 360), (1280, 720), (511, 300), (770, 431)):
+        assert sampling.pynvc_target_size(w, h) == preprocess.pynvc_target_size(w, h)
+    assert sampling.pynvc_target_size(1920, 1080) == (274, 154)  # 1920 // 256 = 7: round(274.29), round(154.29)
+    assert sampling.pynvc_target_size(854, 480) == (285, 160)    # factor 3: round(284.67), 160
+    assert sampling.pynvc_target_size(200, 100) == (200, 100)
+    assert sampling.pynvc_target_size(1920, 1080, 48, 27) == (48, 27)

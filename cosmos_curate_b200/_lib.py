@@ -69,6 +69,7 @@ SIGNATURES = {
     "cb_destroy": (None, [_vp]),
     "cb_last_error": (C.c_char_p, [_vp]),
     "cb_device_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(C.c_size_t)]),
+    "cb_device_pci_bus_id": (_i, [_vp, C.c_char_p, _i]),
     "cb_launch_count": (C.c_ulonglong, [_vp]),
     "cb_profile_begin": (_i, [_vp]),
     "cb_profile_end": (_i, [_vp, _vp, _pf, C.POINTER(_i), _i]),

@@ -10,6 +10,10 @@ namespace cb {
 
 static std::mutex g_err_mu;
 static std::string g_last_error;
+// A failing call and the cb_last_error() that follows it run on the same host thread (ctypes: check() right after the call),
+// so the message is kept per thread: concurrent decode sessions on one cb_ctx never see (or tear) each other's strings.
+static thread_local std::string t_last_error;
+static thread_local std::string t_copy;
 
 void set_global_error(const char* msg) {
   std::lock_guard<std::mutex> lk(g_err_mu);
@@ -22,7 +26,11 @@ int fail(cb_ctx* ctx, int code, const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
-  if (ctx) ctx->last_error = buf;
+  t_last_error = buf;
+  if (ctx) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->last_error = buf;
+  }
   set_global_error(buf);
   return code;
 }
@@ -44,8 +52,9 @@ int make_tensor_map(cb_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dtype, in
 }
 
 void mark_launch(cb_ctx* ctx, int category, cudaStream_t stream) {
-  ctx->launches++;
+  ctx->launches.fetch_add(1, std::memory_order_relaxed);
   if (!ctx->prof_on) return;
+  std::lock_guard<std::mutex> lk(ctx->mu);  // decode threads (thumbnail kernel) may launch while the tower thread profiles
   if (ctx->prof_n >= ctx->prof_ev.size()) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
@@ -73,7 +82,7 @@ int cb_profile_end(cb_ctx* ctx, void* stream, float* ms_by_category, int* launch
   if (!ctx->prof_on) return cb::fail(ctx, CB_ERR_STATE, "profile_end without profile_begin");
   if (!ms_by_category || !launches_by_category || n_categories < CB_PROF_CATEGORIES) return cb::fail(ctx, CB_ERR_ARG, "profile_end: need %d categories", CB_PROF_CATEGORIES);
   cb::mark_launch(ctx, -1, (cudaStream_t)stream);  // closing event
-  ctx->launches--;
+  ctx->launches.fetch_sub(1, std::memory_order_relaxed);
   ctx->prof_on = false;
   CB_CUDA(ctx, cudaEventSynchronize(ctx->prof_ev[ctx->prof_n - 1]));
   for (int i = 0; i < n_categories; ++i) ms_by_category[i] = 0.f, launches_by_category[i] = 0;
@@ -137,11 +146,15 @@ void cb_destroy(cb_ctx* ctx) {
 }
 
 const char* cb_last_error(cb_ctx* ctx) {
-  if (ctx) return ctx->last_error.c_str();
-  static thread_local std::string copy;
-  std::lock_guard<std::mutex> lk(cb::g_err_mu);
-  copy = cb::g_last_error;
-  return copy.c_str();
+  if (!cb::t_last_error.empty()) return cb::t_last_error.c_str();  // this thread's own last failure
+  if (ctx) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cb::t_copy = ctx->last_error;
+  } else {
+    std::lock_guard<std::mutex> lk(cb::g_err_mu);
+    cb::t_copy = cb::g_last_error;
+  }
+  return cb::t_copy.c_str();
 }
 
 int cb_device_info(cb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
@@ -153,6 +166,13 @@ int cb_device_info(cb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, siz
   return CB_OK;
 }
 
-unsigned long long cb_launch_count(cb_ctx* ctx) { return ctx ? ctx->launches : 0ull; }
+int cb_device_pci_bus_id(cb_ctx* ctx, char* buf, int len) {
+  if (!ctx) return CB_ERR_ARG;
+  if (!buf || len < 16) return cb::fail(ctx, CB_ERR_ARG, "device_pci_bus_id: buffer of at least 16 bytes needed");
+  CB_CUDA(ctx, cudaDeviceGetPCIBusId(buf, len, ctx->device));
+  return CB_OK;
+}
+
+unsigned long long cb_launch_count(cb_ctx* ctx) { return ctx ? ctx->launches.load(std::memory_order_relaxed) : 0ull; }
 
 }  // extern "C"

@@ -186,8 +186,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             const int i = nxt[g][hf];
             if (i >= 2) continue;
             const int c = hf * 2 + i, use = it * 2 + i;
-            // O aliases the S columns of chunk 0: the first MMA of a unit (accumulate = 0) must be chunk 0
-            if (c != 0 && nxt[g][0] == 0) continue;
+            // Fixed issue order 0, 2, 1, 3 (chunk i of the second half-row stream right after chunk i of the first): the fp32
+            // accumulation order of O - and with it every output bit - is the same on every run.  (O aliases the S columns of
+            // chunk 0, so chunk 0 had to be first anyway.)
+            if (2 * i + hf != nxt[g][0] + nxt[g][1]) continue;
             if (!mbar_test(&p_ready[g * 2 + hf], use & 1)) continue;
             tc_fence_after();
             const uint64_t da = umma_desc_sw128(smem_u32(sP + (g * 2 + hf) * kTileBytes));

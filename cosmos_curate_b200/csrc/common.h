@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -35,13 +36,13 @@ struct cb_ctx {
   int sm_count = 0;
   int cc_major = 0, cc_minor = 0;
   size_t total_mem = 0;
-  std::string last_error;
+  std::string last_error;  // last failure on ANY thread (guarded by mu); cb_last_error() prefers the calling thread's own message
   std::mutex mu;
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
   std::map<std::tuple<int, int, int, int>, cb::TapTable> taps;  // (in, out, crop_off, crop_len)
   float* d_norm_lut = nullptr;                                  // [3*256] fp32, normalise LUT currently loaded
   float lut_mean[3] = {0, 0, 0}, lut_std[3] = {0, 0, 0};
-  unsigned long long launches = 0;  // kernels launched by this library (bench.py reports it)
+  std::atomic<unsigned long long> launches{0};  // kernels launched by this library (bench.py reports it); decode threads launch too
   // per-category kernel timing (cb_profile_begin/end): one event before every launch, categories CB_PROF_*
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;

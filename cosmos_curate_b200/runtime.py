@@ -393,3 +393,80 @@ def alloc_nv12_pool(ctx: Context, slots: int, width: int, height: int) -> Pool:
     pitch = (w2 + 255) // 256 * 256
     buf = torch.empty((slots, h2 + h2 // 2, pitch), dtype=torch.uint8, device=f"cuda:{ctx.device}")
     return ctx.nv12_pool(buf, w2, h2, h2)
+
+
+# ---- host placement + persistent NVDEC sessions ---------------------------------------------------------
+def _parse_cpulist(text: str) -> set[int]:
+    out: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        out.update(range(int(lo), int(hi or lo) + 1))
+    return out
+
+
+def device_numa_cpus(ctx: Context) -> tuple[int | None, list[int]]:
+    """(NUMA node of the context's GPU, host CPUs of that node this process may run on).  ([] when the topology is not
+    visible - e.g. numa_node = -1 on single-socket hosts - in which case nothing is pinned.)"""
+    import os
+
+    buf = C.create_string_buffer(32)
+    try:
+        check(ctx.lib.cb_device_pci_bus_id(ctx.h, buf, 32), "cb_device_pci_bus_id", ctx.h)
+        bus = buf.value.decode().lower()
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None, []
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        return node, sorted(cpus & os.sched_getaffinity(0))
+    except (OSError, ValueError, _lib.CurateB200Error):
+        return None, []
+
+
+class DecoderPool:
+    """Persistent NVDEC sessions behind a thread pool: one `Decoder` per worker thread, created on first use and kept across
+    calls (session creation costs ~10 ms and a context-lock round trip), worker threads pinned to the host CPUs of the GPU's
+    NUMA node (bitstream parsing + H2D staging are host work: on a two-socket 8-GPU box the far socket costs decode rate)."""
+
+    def __init__(self, ctx: Context, sessions: int, pin: bool = True):
+        import threading
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.ctx, self.sessions = ctx, int(sessions)
+        self.numa_node, cpus = device_numa_cpus(ctx) if pin else (None, [])
+        self.cpus = cpus
+        self._tls = threading.local()
+        self._decoders: list[Decoder] = []
+        self._lock = threading.Lock()
+        self._tp = ThreadPoolExecutor(max_workers=self.sessions, thread_name_prefix="cb-nvdec", initializer=self._init_thread)
+
+    def _init_thread(self) -> None:
+        import os
+
+        if self.cpus:
+            try:
+                os.sched_setaffinity(0, self.cpus)  # pid 0 = the calling thread
+            except OSError:
+                pass
+
+    def decoder(self) -> Decoder:
+        d = getattr(self._tls, "dec", None)
+        if d is None or d.h is None:
+            d = self._tls.dec = Decoder(self.ctx)
+            with self._lock:
+                self._decoders.append(d)
+        return d
+
+    def submit(self, fn, *args, **kw):
+        """fn(decoder, *args, **kw) on a pool thread with that thread's own session."""
+        return self._tp.submit(lambda: fn(self.decoder(), *args, **kw))
+
+    def close(self) -> None:
+        self._tp.shutdown(wait=True)
+        with self._lock:
+            for d in self._decoders:
+                d.close()
+            self._decoders.clear()

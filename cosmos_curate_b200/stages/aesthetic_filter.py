@@ -103,46 +103,51 @@ class AestheticFilterStage(CuratorStage):
         return
 
     def process_data(self, tasks):
+        # StageTimer call pattern of the reference (aesthetic_filter_stages.py:161-203): reinit BEFORE the work so that
+        # process_time covers the model calls.  Clips of all tasks of the call share batches, so the window is per call.
+        self._timer.reinit(self, sum(task.get_major_size() for task in tasks))
         work: list[tuple[object, np.ndarray]] = []  # (clip, frames) in task order
-        for task in tasks:
-            for clip in task.video.clips:
-                if not clip.encoded_data:
-                    logger.warning(f"Clip {clip.uuid} has no encoded_data.")
-                    clip.errors["encoded_data"] = "empty"
-                    clip.aesthetic_score = -1.0
-                    continue
-                ef = clip.extracted_frames.resolve()
-                if ef is None or self._frame_extraction_signature not in ef:
-                    clip.errors[f"frames-{self._frame_extraction_signature}"] = "missing"
-                    logger.error(f"Clip {clip.uuid} has buffer but no extracted frames for {self._frame_extraction_signature}")
-                    clip.aesthetic_score = -1.0
-                    continue
-                frames = ef.pop(self._frame_extraction_signature)  # pop: other consumers own the other keys
-                if not ef:
-                    clip.extracted_frames.drop()
-                work.append((clip, frames))
-        if work:
-            per_clip = score_frame_groups(self._model, [f for _, f in work], self._max_batch)
-            for (clip, _), scores in zip(work, per_clip):
-                clip.aesthetic_score = float(self._reduce_fn(scores))
+        n_clips = sum(len(task.video.clips) for task in tasks)
+        with self._timer.time_process(num_samples=max(1, n_clips)):
+            for task in tasks:
+                for clip in task.video.clips:
+                    if not clip.encoded_data:
+                        logger.warning(f"Clip {clip.uuid} has no encoded_data.")
+                        clip.errors["encoded_data"] = "empty"
+                        clip.aesthetic_score = -1.0
+                        continue
+                    ef = clip.extracted_frames.resolve()
+                    if ef is None or self._frame_extraction_signature not in ef:
+                        clip.errors[f"frames-{self._frame_extraction_signature}"] = "missing"
+                        logger.error(f"Clip {clip.uuid} has buffer but no extracted frames for {self._frame_extraction_signature}")
+                        clip.aesthetic_score = -1.0
+                        continue
+                    frames = ef.pop(self._frame_extraction_signature)  # pop: other consumers own the other keys
+                    if not ef:
+                        clip.extracted_frames.drop()
+                    work.append((clip, frames))
+            if work:
+                per_clip = score_frame_groups(self._model, [f for _, f in work], self._max_batch)
+                for (clip, _), scores in zip(work, per_clip):
+                    clip.aesthetic_score = float(self._reduce_fn(scores))
 
-        for task in tasks:
-            self._timer.reinit(self, task.get_major_size())
-            video = task.video
-            passed = []
-            for clip in video.clips:
-                if clip.aesthetic_score < self._score_threshold:
-                    video.filtered_clips.append(clip)
-                    video.clip_stats.num_filtered_by_aesthetic += 1
-                    if self._verbose:
-                        logger.info(f"Clip {clip.uuid} has aesthetic score {clip.aesthetic_score:.3f} below threshold {self._score_threshold}, skipped.")
-                else:
-                    passed.append(clip)
-                    if self._verbose:
-                        logger.info(f"Clip {clip.uuid} has aesthetic score {clip.aesthetic_score:.3f} above threshold {self._score_threshold}, kept.")
-            video.clips = passed
-            if self._log_stats:
-                stage_name, stats = self._timer.log_stats()
+            for task in tasks:
+                video = task.video
+                passed = []
+                for clip in video.clips:
+                    if clip.aesthetic_score < self._score_threshold:
+                        video.filtered_clips.append(clip)
+                        video.clip_stats.num_filtered_by_aesthetic += 1
+                        if self._verbose:
+                            logger.info(f"Clip {clip.uuid} has aesthetic score {clip.aesthetic_score:.3f} below threshold {self._score_threshold}, skipped.")
+                    else:
+                        passed.append(clip)
+                        if self._verbose:
+                            logger.info(f"Clip {clip.uuid} has aesthetic score {clip.aesthetic_score:.3f} above threshold {self._score_threshold}, kept.")
+                video.clips = passed
+        if self._log_stats:
+            stage_name, stats = self._timer.log_stats()
+            for task in tasks:
                 task.stage_perf[stage_name] = stats
         self._process_count += 1
         return tasks

@@ -62,15 +62,29 @@ class ClipFrameExtractionStage(CuratorStage):
         if getattr(self, "_decoder", None):
             self._decoder.close()
 
+    MAX_POOLS = 4  # resolutions kept resident (LRU); a 64-slot 1080p pool is 0.2 GB and the actor may own only 0.25 GPU
+
+    def _surface_pool(self, width: int, height: int, n_frames: int):
+        """One pool per resolution, capacity a power of two >= 64 (grown by replacement), least recently used evicted."""
+        key = (width, height)
+        pool = self._pools.pop(key, None)
+        cap = 64
+        while cap < n_frames:
+            cap *= 2
+        if pool is None or pool.buf.shape[0] < cap:
+            pool = None  # drop the smaller pool before allocating its replacement
+            while len(self._pools) >= self.MAX_POOLS:
+                self._pools.pop(next(iter(self._pools)))
+            pool = alloc_nv12_pool(self._ctx, cap, width, height)
+        self._pools[key] = pool  # most recently used last
+        return pool
+
     def _extract(self, data) -> dict[str, np.ndarray]:
         idx = mp4_index(data)
         ts = sampling.timestamps_from_index(idx["pts"], idx["timescale"])
         plan = sampling.plan_extraction(ts, self._extraction_policies, self._target_fps)
         all_ids = np.unique(np.concatenate(list(plan.values()))).astype(np.int32)
-        key = (idx["width"], idx["height"], max(64, len(all_ids)))
-        pool = self._pools.get(key)
-        if pool is None:
-            pool = self._pools[key] = alloc_nv12_pool(self._ctx, key[2], idx["width"], idx["height"])
+        pool = self._surface_pool(idx["width"], idx["height"], len(all_ids))
         self._decoder.decode(data, all_ids, pool, np.arange(len(all_ids), dtype=np.int32))
         rgb = self._ctx.nv12_to_rgb(pool, slots=np.arange(len(all_ids), dtype=np.int32))[:, : idx["height"], : idx["width"]].cpu().numpy()
         pos = {int(f): i for i, f in enumerate(all_ids)}

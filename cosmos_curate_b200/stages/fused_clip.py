@@ -7,13 +7,18 @@ stage that never materialises RGB frames.  Task mutations and the error conventi
     clip.aesthetic_score, video.filtered_clips, video.clip_stats.num_filtered_by_aesthetic, task.stage_perf,
     no encoded_data            -> clip.errors["encoded_data"] = "empty", score -1.0
     demux / decode failure     -> clip.errors["frame_extraction"] = "video_decode_failed", encoded_data dropped, score -1.0
+    task.stage_perf follows the reference's StageTimer call pattern (reinit BEFORE the work, aesthetic_filter_stages.py:161).
     (optional) clip.openai_embedding = L2-normalised mean of the per-frame embeddings (the reference has
     no pooling rule for frame embeddings; this documented choice fills the existing generic clip-embedding slot).
+
+Inside one `process_data` call the work is pipelined (this IS the product path bench.py times as `e2e`): the clips of
+tower batches k+1 and k+2 are being decoded by the persistent NVDEC sessions (DecoderPool: one session per worker thread,
+kept across calls, pinned to the GPU's NUMA node) while the SMs run preprocess + tower on batch k out of a three-deep ring
+of surface pools; scores / embeddings come back through pinned host buffers with one async copy per batch.
 """
 
 from __future__ import annotations
 
-from concurrent.futures import ThreadPoolExecutor
 from typing import Literal
 
 import numpy as np
@@ -24,7 +29,7 @@ from .._lib import CurateB200Error
 from ..data_model import StageTimer
 from ..interfaces import CuratorStage, CuratorStageResource, ModelInterface
 from ..models.clip_aesthetics import CLIPAestheticScorer
-from ..runtime import Decoder, alloc_nv12_pool, get_context, mp4_index
+from ..runtime import DecoderPool, alloc_nv12_pool, get_context, mp4_index
 
 try:
     from loguru import logger
@@ -44,7 +49,7 @@ class NvdecClipAestheticStage(CuratorStage):
         *,
         write_embedding: bool = False,
         max_batch: int = 256,
-        num_decoders: int = 8,
+        num_decoders: int = 20,
         stage_batch_size: int = 8,
         seek_keyframes: bool = True,
         source: Literal["clip", "video_span"] = "clip",
@@ -68,7 +73,8 @@ class NvdecClipAestheticStage(CuratorStage):
         self._video_index: dict[int, tuple] = {}
         self._model = model if model is not None else CLIPAestheticScorer(max_batch=max_batch)
         self._reduce_fn = np.min
-        self._pools: dict[tuple[int, int], object] = {}
+        self._pools: dict[tuple[int, int], list] = {}
+        self.last_call_stats: dict = {}
 
     @property
     def resources(self) -> CuratorStageResource:
@@ -89,15 +95,13 @@ class NvdecClipAestheticStage(CuratorStage):
         self._reduce_fn = np.mean if self._reduction == "mean" else np.min
         self._model.setup()
         self._ctx = get_context()
-        self._decoders = [Decoder(self._ctx) for _ in range(self._num_decoders)]
-        self._threads = ThreadPoolExecutor(max_workers=self._num_decoders)
+        self._decode_pool = DecoderPool(self._ctx, self._num_decoders)  # 7 NVDEC engines need ~20 sessions in flight
+        self._host: list[tuple[torch.Tensor, torch.Tensor | None]] = []
 
     def destroy(self) -> None:
-        for d in getattr(self, "_decoders", []):
-            d.close()
-        self._decoders = []
-        if getattr(self, "_threads", None):
-            self._threads.shutdown(wait=True)
+        if getattr(self, "_decode_pool", None):
+            self._decode_pool.close()
+            self._decode_pool = None
         self._pools.clear()
 
     # ---- helpers ---------------------------------------------------------------------------------
@@ -149,81 +153,139 @@ class NvdecClipAestheticStage(CuratorStage):
             clip.encoded_data.drop()
         clip.aesthetic_score = -1.0
 
-    def _pool(self, size):
-        p = self._pools.get(size)
-        if p is None:
-            p = self._pools[size] = alloc_nv12_pool(self._ctx, self._max_batch, size[0], size[1])
-        return p
+    RING = 3  # surface pools per resolution: tower on batch k, NVDEC filling k+1 and k+2
 
-    def _run_batch(self, pool, items) -> None:
-        """items: [(clip, data, ids, first_slot)] whose frames fit the pool.  Decode in parallel, embed once."""
+    def _pool(self, size, r: int):
+        ring = self._pools.get(size)
+        if ring is None:
+            if len(self._pools) >= 4:  # mixed-resolution runs: keep the four most recent resolutions (LRU), free the rest
+                self._pools.pop(next(iter(self._pools)))
+            ring = [None] * self.RING
+        else:
+            self._pools.pop(size)
+        self._pools[size] = ring  # most recently used last
+        if ring[r] is None:
+            ring[r] = alloc_nv12_pool(self._ctx, self._max_batch, size[0], size[1])
+        return ring[r]
 
-        def work(arg):
-            j, (clip, data, ids, first) = arg
-            try:
-                self._decoders[j % self._num_decoders].decode(data, ids, pool, np.arange(first, first + len(ids), dtype=np.int32), seek_keyframes=self._seek)
-                return None
-            except CurateB200Error as e:
-                return e
+    def _host_buffers(self, r: int):
+        while len(self._host) <= r:
+            tower = self._model.tower
+            score = torch.empty((self._max_batch,), dtype=torch.float32).pin_memory()
+            emb = torch.empty((self._max_batch, tower.out_dim), dtype=torch.float32).pin_memory() if self._write_embedding else None
+            self._host.append((score, emb))
+        return self._host[r]
 
-        errs = []
-        for wave in range(0, len(items), self._num_decoders):  # a decoder is owned by one thread per wave
-            errs.extend(self._threads.map(work, list(enumerate(items))[wave : wave + self._num_decoders]))
-        n = sum(len(ids) for _, _, ids, _ in items)
-        tower = self._model.tower
-        emb, _, score = tower.embed_pool(pool, slots=np.arange(n, dtype=np.int32))
-        score_h = score.cpu().numpy()
-        emb_h = emb.cpu().numpy() if self._write_embedding else None
-        for (clip, _, ids, first), err in zip(items, errs):
-            if err is not None:
-                self._decode_failed(clip, err)
-                continue
-            clip.aesthetic_score = float(self._reduce_fn(score_h[first : first + len(ids)]))
-            if emb_h is not None:
-                m = emb_h[first : first + len(ids)].mean(axis=0)
-                clip.openai_embedding = (m / np.linalg.norm(m)).astype(np.float32)
-
-    # ---- stage entry -----------------------------------------------------------------------------
-    def process_data(self, tasks):
-        by_size: dict[tuple[int, int], list] = {}
-        for task in tasks:
-            for video in task.videos:
-                for clip in video.clips:
-                    plan = self._plan(clip, video)
-                    if plan is not None:
-                        data, ids, size = plan
-                        by_size.setdefault(size, []).append((clip, data, ids))
+    def _make_batches(self, by_size):
+        """[(size, [(clip, data, ids, first_slot)])]: whole clips, at most max_batch frames, one resolution per batch."""
+        batches = []
         for size, clips in by_size.items():
-            pool = self._pool(size)
             batch, used = [], 0
             for clip, data, ids in clips:
                 if len(ids) > self._max_batch:
                     self._decode_failed(clip, ValueError(f"{len(ids)} sampled frames exceed max_batch={self._max_batch}"))
                     continue
                 if used + len(ids) > self._max_batch:
-                    self._run_batch(pool, batch)
+                    batches.append((size, batch))
                     batch, used = [], 0
                 batch.append((clip, data, ids, used))
                 used += len(ids)
             if batch:
-                self._run_batch(pool, batch)
+                batches.append((size, batch))
+        return batches
 
-        for task in tasks:
-            self._timer.reinit(self, task.get_major_size())
-            for video in task.videos:
-                passed = []
-                for clip in video.clips:
-                    if clip.aesthetic_score is None:
-                        clip.aesthetic_score = -1.0
-                    if clip.aesthetic_score < self._score_threshold:
-                        video.filtered_clips.append(clip)
-                        video.clip_stats.num_filtered_by_aesthetic += 1
-                    else:
-                        passed.append(clip)
-                video.clips = passed
-            if self._log_stats:
-                stage_name, stats = self._timer.log_stats()
+    def _run_batches(self, batches) -> None:
+        """Decode of batches k+1, k+2 (NVDEC + host parsing threads) overlaps preprocess + tower of batch k (SMs)."""
+        seek, tower, stream = self._seek, self._model.tower, torch.cuda.current_stream()
+        ring_pos: dict[tuple[int, int], int] = {}
+        slots_of, futs, inflight = {}, {}, {}
+        decoded = 0
+
+        def decode_one(dec, data, ids, pool, first):
+            return dec.decode(data, ids, pool, np.arange(first, first + len(ids), dtype=np.int32), seek_keyframes=seek)["frames_decoded"]
+
+        def submit(k):
+            size, items = batches[k]
+            r = ring_pos.get(size, 0)
+            ring_pos[size] = (r + 1) % self.RING
+            pool = self._pool(size, r)
+            slots_of[k] = (pool, k % self.RING)
+            futs[k] = [self._decode_pool.submit(decode_one, data, ids, pool, first) for _, data, ids, first in items]
+
+        def finalize(k):
+            """Batch k's results are on the host once its event has fired: write them onto the clips."""
+            ev, errs, n = inflight.pop(k)
+            ev.synchronize()
+            score_h, emb_h = self._host_buffers(k % self.RING)
+            score_h = score_h[:n].numpy()
+            for (clip, _, ids, first), err in zip(batches[k][1], errs):
+                if err is not None:
+                    self._decode_failed(clip, err)
+                    continue
+                clip.aesthetic_score = float(self._reduce_fn(score_h[first : first + len(ids)]))
+                if emb_h is not None:
+                    m = emb_h[first : first + len(ids)].numpy().mean(axis=0)
+                    clip.openai_embedding = (m / np.linalg.norm(m)).astype(np.float32)
+
+        for k in range(min(2, len(batches))):
+            submit(k)
+        for k in range(len(batches)):
+            errs = []
+            for f in futs.pop(k):
+                try:
+                    decoded += f.result()
+                    errs.append(None)
+                except CurateB200Error as e:
+                    errs.append(e)
+            pool, r = slots_of.pop(k)
+            n = sum(len(ids) for _, _, ids, _ in batches[k][1])
+            emb, _, score = tower.embed_pool(pool, slots=np.arange(n, dtype=np.int32))
+            score_h, emb_h = self._host_buffers(r)
+            score_h[:n].copy_(score, non_blocking=True)
+            if emb_h is not None:
+                emb_h[:n].copy_(emb, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            inflight[k] = (ev, errs, n)
+            if k >= 1:
+                finalize(k - 1)  # also frees the surface pool and host buffers batch k+2 is about to reuse
+            if k + 2 < len(batches):
+                submit(k + 2)
+        if batches:
+            finalize(len(batches) - 1)
+        self.last_call_stats = {"frames_decoded": decoded, "batches": len(batches), "nvdec_sessions": self._num_decoders,
+                                "numa_node": self._decode_pool.numa_node, "pinned_cpus": len(self._decode_pool.cpus)}  # fmt: skip
+
+    # ---- stage entry -----------------------------------------------------------------------------
+    def process_data(self, tasks):
+        self._timer.reinit(self, sum(task.get_major_size() for task in tasks))
+        n_clips = sum(len(video.clips) for task in tasks for video in task.videos)
+        with self._timer.time_process(num_samples=max(1, n_clips)):
+            by_size: dict[tuple[int, int], list] = {}
+            for task in tasks:
+                for video in task.videos:
+                    for clip in video.clips:
+                        plan = self._plan(clip, video)
+                        if plan is not None:
+                            data, ids, size = plan
+                            by_size.setdefault(size, []).append((clip, data, ids))
+            self._run_batches(self._make_batches(by_size))
+
+            for task in tasks:
+                for video in task.videos:
+                    passed = []
+                    for clip in video.clips:
+                        if clip.aesthetic_score is None:
+                            clip.aesthetic_score = -1.0
+                        if clip.aesthetic_score < self._score_threshold:
+                            video.filtered_clips.append(clip)
+                            video.clip_stats.num_filtered_by_aesthetic += 1
+                        else:
+                            passed.append(clip)
+                    video.clips = passed
+        if self._log_stats:
+            stage_name, stats = self._timer.log_stats()  # one batched call -> the same window on every task of the call
+            for task in tasks:
                 task.stage_perf[stage_name] = stats
-        torch.cuda.current_stream().synchronize()
         self._video_index.clear()
         return tasks

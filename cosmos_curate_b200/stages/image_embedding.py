@@ -34,21 +34,22 @@ class ImageCLIPEmbeddingStage(CuratorStage):
         self._model.setup()
 
     def process_data(self, tasks):
-        by_shape: dict[tuple, list] = {}
-        for task in tasks:
-            image = task.image
-            if image.image_data is None or len(image.image_data.frames) == 0:
-                image.errors["clip_embedding"] = "no image_data"
-                continue
-            frame = image.image_data.frames[0]
-            by_shape.setdefault(tuple(frame.shape), []).append((image, frame))
-        for items in by_shape.values():
-            emb = self._model(np.stack([f for _, f in items])).cpu().numpy()
-            for (image, _), e in zip(items, emb):
-                image.embeddings["clip"] = e
-        for task in tasks:
-            self._timer.reinit(self, task.get_major_size())
-            if self._log_stats:
-                stage_name, stats = self._timer.log_stats()
+        self._timer.reinit(self, sum(task.get_major_size() for task in tasks))  # before the work (image_embedding_stages.py:262)
+        with self._timer.time_process(num_samples=max(1, len(tasks))):
+            by_shape: dict[tuple, list] = {}
+            for task in tasks:
+                image = task.image
+                if image.image_data is None or len(image.image_data.frames) == 0:
+                    image.errors["clip_embedding"] = "no image_data"
+                    continue
+                frame = image.image_data.frames[0]
+                by_shape.setdefault(tuple(frame.shape), []).append((image, frame))
+            for items in by_shape.values():
+                emb = self._model(np.stack([f for _, f in items])).cpu().numpy()
+                for (image, _), e in zip(items, emb):
+                    image.embeddings["clip"] = e
+        if self._log_stats:
+            stage_name, stats = self._timer.log_stats()
+            for task in tasks:
                 task.stage_perf[stage_name] = stats
         return tasks

@@ -44,6 +44,10 @@ void cb_destroy(cb_ctx* ctx);
 /* Message of the last failing call on `ctx` (or of the last failing cb_init when ctx == NULL). */
 const char* cb_last_error(cb_ctx* ctx);
 int cb_device_info(cb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+/* PCI bus id of the context's device ("0000:1b:00.0") into buf[len]: the host side uses it to find the GPU's NUMA node
+ * (/sys/bus/pci/devices/<id>/numa_node) and pin the NVDEC feeder threads next to it.  The reference leaves placement to
+ * Ray/xenna (cosmos-xenna resources.py); one process per GPU needs it spelled out. */
+int cb_device_pci_bus_id(cb_ctx* ctx, char* buf, int len);
 /* Number of kernels this library has launched on `ctx` since cb_init (bench.py "gpu_launches"). */
 unsigned long long cb_launch_count(cb_ctx* ctx);
 

@@ -213,3 +213,110 @@ def test_model_interfaces_direct_calls(ctx):
     a = AestheticScorer(seed=3, dim=cfg.proj_dim)
     a.setup()
     np.testing.assert_allclose(a(emb).cpu().numpy(), emb @ a.w + a.b, rtol=1e-5, atol=1e-5)
+
+
+def test_image_clip_embedding_stage_on_gpu(ctx):
+    """ImageCLIPEmbeddingStage (image_embedding_stages.py:219-283) with the real CLIPImageEmbeddings model on the GPU:
+    image.embeddings["clip"] per task against the fp32 oracle; the reference's error convention for missing image data."""
+    import types
+
+    from cosmos_curate_b200.models import weights as W
+    from cosmos_curate_b200.models.clip import CLIPImageEmbeddings
+    from cosmos_curate_b200.stages import ImageCLIPEmbeddingStage
+    from oracle import preprocess, vit
+
+    cfg = vit.CLIP_VIT_B32
+
+    class _Seeded(CLIPImageEmbeddings):
+        def setup(self_inner):
+            from cosmos_curate_b200.runtime import VitTower, get_context
+
+            self_inner._tower = VitTower(get_context(), cfg.to_dict(), vit.random_weights(cfg, seed=11), max_batch=8)
+
+    def task(frame):
+        img = types.SimpleNamespace(image_data=None if frame is None else types.SimpleNamespace(frames=[frame]), embeddings={}, errors={})
+        return types.SimpleNamespace(image=img, stage_perf={}, session_id="s", get_major_size=lambda: 0 if frame is None else frame.nbytes)
+
+    rng = np.random.default_rng(4)
+    frames = [rng.integers(0, 256, size=s, dtype=np.uint8) for s in ((360, 640, 3), (360, 640, 3), (500, 375, 3))]
+    tasks = [task(frames[0]), task(None), task(frames[1]), task(frames[2])]
+    stage = ImageCLIPEmbeddingStage(model=_Seeded(), log_stats=True, stage_batch_size=4)
+    stage.stage_setup()
+    out = stage.process_data(tasks)
+    assert out == tasks
+    assert tasks[1].image.errors == {"clip_embedding": "no image_data"} and "clip" not in tasks[1].image.embeddings
+    w = vit.random_weights(cfg, seed=11)
+    for t, f in ((tasks[0], frames[0]), (tasks[2], frames[1]), (tasks[3], frames[2])):
+        e = t.image.embeddings["clip"]
+        assert isinstance(e, np.ndarray) and e.shape == (cfg.proj_dim,) and e.dtype == np.float32
+        want = vit.forward(cfg, w, preprocess.clip_preprocess(f[None]))["embedding"][0]
+        assert np.linalg.norm(e - want) / np.linalg.norm(want) < 1.5e-3  # 1e-3 tower budget + the <=1 LSB u8 resize budget
+        assert "ImageCLIPEmbeddingStage" in t.stage_perf
+    # one image per call (the reference's batch of 1) gives the same vector as the shared batch
+    solo = task(frames[0])
+    stage.process_data([solo])
+    assert np.array_equal(solo.image.embeddings["clip"], tasks[0].image.embeddings["clip"])
+
+
+def test_stage_perf_covers_the_work_and_concurrent_decode_errors(ctx):
+    """a17: process_time of the fused stage is the wall time of the call (StageTimer.reinit before the work, as the reference
+    does); several corrupt clips failing concurrently on different sessions each get their own error (per-thread messages)."""
+    import time
+
+    from cosmos_curate_b200.data_model import Clip
+    from cosmos_curate_b200.stages import NvdecClipAestheticStage
+    from tools import synth_h264
+
+    model, cfg, w, sd = _model()
+    good = synth_h264.make_clip(640, 360, 30, 2.0, seed=9, gop=30)
+    task = _clip_task(good, n_clips=6)
+    for k in range(6):
+        task.video.clips.append(Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0, 2), encoded_data=b"\x00" * (512 + 97 * k)))  # not an mp4
+    stage = NvdecClipAestheticStage(score_threshold=-0.5, reduction="min", max_batch=16, num_decoders=6, log_stats=True, model=model)
+    stage.stage_setup()
+    t0 = time.time()
+    stage.process_data([task])
+    wall = time.time() - t0
+    perf = task.stage_perf["NvdecClipAestheticStage"]
+    assert 0.5 * wall <= perf.process_time <= wall + 0.05, (perf.process_time, wall)
+    assert perf.input_data_size_mb > 0
+    v = task.video
+    assert len(v.clips) == 6 and len(v.filtered_clips) == 6
+    assert all(c.errors == {"frame_extraction": "video_decode_failed"} and c.aesthetic_score == -1.0 for c in v.filtered_clips)
+    assert len({c.aesthetic_score for c in v.clips}) == 1  # six identical clips, identical scores whatever batch they landed in
+    stage.destroy()
+
+
+def test_fused_stage_is_deterministic_at_l14_shape(ctx):
+    """clips near score_threshold must not flip between runs - the L/14 shape (attention_tc2) through the stage,
+    twice, bitwise equal scores and embeddings; identical clips inside one call agree too."""
+    from cosmos_curate_b200.models.clip_aesthetics import CLIPAestheticScorer
+    from cosmos_curate_b200.runtime import VitTower, get_context
+    from cosmos_curate_b200.stages import NvdecClipAestheticStage
+    from oracle import vit
+
+    cfg = vit.CLIP_VIT_L14
+    w = vit.random_weights(cfg, seed=2)
+    aw, ab = vit.collapse_aesthetic_mlp(vit.random_aesthetic_mlp(seed=2, in_dim=cfg.proj_dim))
+
+    class _Seeded(CLIPAestheticScorer):
+        def setup(self_inner):
+            from cosmos_curate_b200.models.clip import CLIPImageEmbeddings
+
+            m = CLIPImageEmbeddings()
+            m._tower = VitTower(get_context(), cfg.to_dict(), w, max_batch=64, aesthetic=(aw, ab))
+            self_inner._clip_model = m
+
+    model = _Seeded()
+    sintel = (GOLDEN / "sintel_clip_10s.mp4").read_bytes()
+    stage = NvdecClipAestheticStage(score_threshold=-100.0, reduction="mean", write_embedding=True, max_batch=64, num_decoders=4, model=model)
+    stage.stage_setup()
+    runs = []
+    for _ in range(2):
+        task = _clip_task(sintel, n_clips=7)  # 77 frames: two tower batches
+        stage.process_data([task])
+        runs.append([(c.aesthetic_score, c.openai_embedding.copy()) for c in task.video.clips])
+    for (s0, e0), (s1, e1) in zip(*runs):
+        assert s0 == s1 and np.array_equal(e0, e1)
+    assert len({s for s, _ in runs[0]}) == 1
+    stage.destroy()

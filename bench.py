@@ -5,19 +5,25 @@
     python bench.py --impl reference --gpus 1 --steps K --warmup W # the reference's CPU path (oracle) on host cores
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): synthetic 1920x1080 30 fps 10 s H.264 clips (tools/synth_h264.py: no encoder
-exists in this image), sampled at 1 fps like AestheticFilterStage (11 frames per clip), CLIP ViT-L/14 image tower
-(seeded random weights) + aesthetic affine head.  One STEP = `--clips-per-step` clips (default 24 -> 264 frames,
-the closest whole-clip count to the 256-frame batch BASELINE.json names).
+Workload (BASELINE.json configs[1]): synthetic 1920x1080 30 fps 10 s H.264 clips at ~4 Mb/s (tools/synth_h264.make_coded_clip:
+residual-coded Intra16x16 IDRs + P pictures, CAVLC, deblocking on - no encoder exists in this image), 64 distinct clips per
+rank, sampled at 1 fps like AestheticFilterStage (11 frames per clip), CLIP ViT-L/14 image tower (seeded random weights) +
+aesthetic affine head.  One STEP = `--clips-per-step` clips (default 24 -> 264 frames, the closest whole-clip count to the
+256-frame batch BASELINE.json names).
 
 Printed JSON line (rank 0):
   value   clips/s, whole job, decoded NV12 surfaces of the step already resident in HBM (preprocess + tower + head),
           timed with CUDA events, max over ranks.
-  e2e     clips/s through the public stage API from HOST mp4 buffers: MP4 index + NVDEC decode + fused preprocess +
-          tower + D2H of embeddings/scores, wall clock between device synchronisations, max over ranks.
+  e2e     clips/s through the PRODUCT stage: NvdecClipAestheticStage.process_data(tasks) on host SplitPipeTasks holding mp4 bytes
+          (one call = `--tasks-per-call` tasks x clips-per-step clips); MP4 index + NVDEC decode of every frame up to the last
+          sampled one (the reference's decode semantics) + fused preprocess + tower + pinned D2H of scores/embeddings, the decode /
+          tower overlap happening inside the stage; wall clock between device synchronisations, max over ranks.
+  e2e_keyframe_seek  the same call with the stage's default seek_keyframes=True (identical frames, only GOPs with sampled frames).
   roofline      the dominant kernel (tcgen05 GEMM): algorithmic FLOPs per launch / CUDA-event time per launch vs the
                 measured sustained bf16 peak (MEASURED_PEAKS.json); roofline_other has preprocess / LayerNorm (HBM).
   cpu_baseline  the oracle's CPU restatement of the reference path timed on the host cores (N=1, rank 0), bounded sample.
+  gpu_library_baseline  the reference's GPU *library* path restated without Ray (torch-CUDA torchvision transforms + HF CLIPModel
+                fp32, one call per clip, clip.py:36-74 / aesthetic_filter_stages.py:181-183), N=1 rank 0, bounded sample.
 """
 
 from __future__ import annotations
@@ -87,10 +93,70 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_clips(n_distinct: int, rank: int) -> list[bytes]:
+BITRATE = 4.0e6  # the reference's transcode default (decoder_utils.py:43)
+
+
+def _gen_clip(args) -> str:
+    seed, path = args
     from tools import synth_h264
 
-    return [synth_h264.make_clip(FRAME_W, FRAME_H, FPS, SECONDS, seed=1000 * rank + i, gop=FPS, pan=(2, 0)) for i in range(n_distinct)]
+    if not os.path.exists(path):
+        data = synth_h264.make_coded_clip(FRAME_W, FRAME_H, FPS, SECONDS, seed=seed, gop=FPS, bitrate=BITRATE)
+        tmp = f"{path}.{os.getpid()}.tmp"
+        with open(tmp, "wb") as f:
+            f.write(data)
+        os.replace(tmp, path)
+    return path
+
+
+def make_clips(n_distinct: int, rank: int, workers: int | None = None) -> list[bytes]:
+    """`n_distinct` residual-coded clips (seed = 1000 * rank + i), generated by a fork pool BEFORE CUDA is initialised and
+    cached under /tmp (both arms of one box reuse them)."""
+    import multiprocessing as mp
+
+    root = os.path.join(os.environ.get("CB_CLIP_CACHE", "/tmp"), f"cb_clips_{FRAME_W}x{FRAME_H}_{FPS}_{int(SECONDS)}s_{int(BITRATE)}")
+    os.makedirs(root, exist_ok=True)
+    jobs = [(1000 * rank + i, os.path.join(root, f"clip_{1000 * rank + i}.mp4")) for i in range(n_distinct)]
+    todo = [j for j in jobs if not os.path.exists(j[1])]
+    if todo:
+        world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+        workers = workers or max(1, min(32, len(os.sched_getaffinity(0)) // max(1, world)))
+        if workers > 1 and len(todo) > 1:
+            with mp.get_context("fork").Pool(min(workers, len(todo))) as pool:
+                pool.map(_gen_clip, todo)
+        else:
+            for j in todo:
+                _gen_clip(j)
+    out = []
+    for _, path in jobs:
+        with open(path, "rb") as f:
+            out.append(f.read())
+    return out
+
+
+def host_cpu_info() -> dict:
+    """Logical CPUs, the CPUs this process may run on, and the cgroup CPU quota (what `cores` really means on this box)."""
+    info = {"logical_cpus": os.cpu_count(), "affinity_cpus": len(os.sched_getaffinity(0)), "cgroup_quota_cpus": None}
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, per = f.read().split()
+        info["cgroup_quota_cpus"] = None if q == "max" else float(q) / float(per)
+    except (OSError, ValueError):
+        try:
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f, open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+                q, per = int(f.read()), int(g.read())
+            info["cgroup_quota_cpus"] = None if q < 0 else q / per
+        except (OSError, ValueError):
+            pass
+    return info
+
+
+def effective_cores() -> int:
+    h = host_cpu_info()
+    n = h["affinity_cpus"] or h["logical_cpus"] or 1
+    if h["cgroup_quota_cpus"]:
+        n = min(n, max(1, int(h["cgroup_quota_cpus"])))
+    return n
 
 
 # ================================================================================================ reference arm
@@ -100,10 +166,10 @@ def run_reference(args) -> None:
         return  # under torchrun only rank 0 measures the CPU path
     from oracle import cpu_path, vit
 
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     procs, threads = cpu_layout(cores)
+    clips = make_clips(8, 0)
     pool = cpu_path.CpuReferencePool(vit.CLIP_VIT_L14, seed=0, procs=procs, threads=threads)
-    clips = make_clips(2, 0)
     sample = max(procs, args.ref_clips)  # at least one clip per worker so every host core is busy
     batch = [clips[i % len(clips)] for i in range(sample)]
     pool.run(batch[:procs], SAMPLE_FPS)  # one warm-up pass (a CPU step takes ~25 s; more warm-up would only burn minutes)
@@ -127,33 +193,36 @@ def run_reference(args) -> None:
                                    "(PyAV stand-in) + torchvision transforms + oracle torch-fp32 tower, one model call per clip",
                          "worker_seconds": phases},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "host_cores": cores,
+        "host_cores": cores, "host": host_cpu_info(),
     }  # fmt: skip
     print(json.dumps(line))
 
 
 # ================================================================================================ this repo's arm
 def run_b200(args) -> None:
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    clips = make_clips(args.distinct_clips, rank)  # fork pool: before torch / CUDA are touched
+
     import torch
     import torch.distributed as dist
 
-    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # its banner goes to stdout: keep stdout to the one JSON line
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from concurrent.futures import ThreadPoolExecutor
+    import uuid
 
     from cosmos_curate_b200 import sampling
+    from cosmos_curate_b200.data_model import Clip, SplitPipeTask, Video
     from cosmos_curate_b200.models import weights as W
-    from cosmos_curate_b200.runtime import Context, Decoder, VitTower, alloc_nv12_pool, mp4_index
+    from cosmos_curate_b200.models.clip_aesthetics import CLIPAestheticScorer
+    from cosmos_curate_b200.runtime import alloc_nv12_pool, decode_discard, get_context, mp4_index
+    from cosmos_curate_b200.stages import NvdecClipAestheticStage
 
-    ctx = Context(local)
     cfg = W.CLIP_VIT_L14
     cps = args.clips_per_step
-    clips = make_clips(args.distinct_clips, rank)
     plans = []
     for c in clips:
         idx = mp4_index(c)
@@ -162,38 +231,29 @@ def run_b200(args) -> None:
         plans.append(np.repeat(ids, counts).astype(np.int32))
     fpc = len(plans[0])
     frames_per_step = cps * fpc
-    tower = VitTower(ctx, cfg.to_dict(), W.seeded_weights(cfg, 0), max_batch=frames_per_step, aesthetic=W.seeded_aesthetic(cfg.proj_dim, 0))
-    pools = [alloc_nv12_pool(ctx, frames_per_step, FRAME_W, FRAME_H) for _ in range(3)]
-    n_dec = args.decoders
-    tp = ThreadPoolExecutor(max_workers=n_dec)       # one NVDEC session per worker thread (thread-local, reused across clips)
-    tls = threading.local()
-    all_decoders = []
-    host_emb = torch.empty((frames_per_step, cfg.proj_dim), dtype=torch.float32).pin_memory()
-    host_score = torch.empty((frames_per_step,), dtype=torch.float32).pin_memory()
-    step_clips = [i % len(clips) for i in range(cps)]
+    clip_arrays = [np.frombuffer(c, dtype=np.uint8) for c in clips]  # host buffers the tasks point at (LazyData holds a view)
 
-    def my_decoder():
-        d = getattr(tls, "dec", None)
-        if d is None:
-            d = tls.dec = Decoder(ctx)
-            all_decoders.append(d)
-        return d
+    # ---- the product stage (what a cosmos-curate actor would run): set up once, process_data per call
+    model = CLIPAestheticScorer(seed=0, max_batch=frames_per_step, config=cfg)
 
-    def decode_clip(j, pool, seek):
-        k = step_clips[j]
-        return my_decoder().decode(clips[k], plans[k], pool, np.arange(j * fpc, (j + 1) * fpc, dtype=np.int32), seek_keyframes=seek)["frames_decoded"]
+    def make_stage(seek: bool):
+        st = NvdecClipAestheticStage(score_threshold=5.0, reduction="min", target_fps=SAMPLE_FPS, write_embedding=True, max_batch=frames_per_step,
+                                     num_decoders=args.decoders, stage_batch_size=args.tasks_per_call, seek_keyframes=seek, log_stats=True, model=model)  # fmt: skip
+        st.stage_setup()
+        return st
 
-    def decode_step(pool, seek=False):
-        return sum(tp.map(lambda j: decode_clip(j, pool, seek), range(cps)))
+    stage = make_stage(seek=False)
+    ctx = get_context()
+    tower = model.tower
 
-    def decode_ceiling(reps: int) -> float:
-        """All NVDEC sessions decoding whole clips, surfaces discarded: frames/s."""
-        from cosmos_curate_b200.runtime import decode_discard
-
-        list(tp.map(lambda j: decode_discard(my_decoder(), clips[step_clips[j]]), range(n_dec)))  # warm-up: sessions created
-        t0 = time.perf_counter()
-        n = sum(tp.map(lambda j: decode_discard(my_decoder(), clips[step_clips[j % cps]]), range(reps)))
-        return n / (time.perf_counter() - t0)
+    def make_tasks(call: int) -> list:
+        """`tasks_per_call` SplitPipeTasks x `cps` clips, walking the distinct clips round-robin; host mp4 bytes in."""
+        tasks = []
+        for t in range(args.tasks_per_call):
+            base = (call * args.tasks_per_call + t) * cps
+            cl = [Clip(uuid=uuid.UUID(int=base + j + 1), source_video="v.mp4", span=(0.0, SECONDS), encoded_data=clip_arrays[(base + j) % len(clips)]) for j in range(cps)]
+            tasks.append(SplitPipeTask(session_id=f"s{call}-{t}", video=Video(input_video="v.mp4", clips=cl)))
+        return tasks
 
     def barrier():
         torch.cuda.synchronize()
@@ -207,11 +267,22 @@ def run_b200(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     # ---- resident-input measurement (value): decoded surfaces of one step already in HBM
-    decode_step(pools[0])
+    pool0 = alloc_nv12_pool(ctx, frames_per_step, FRAME_W, FRAME_H)
+    dp = stage._decode_pool
+    futs = [dp.submit(lambda dec, j=j: dec.decode(clips[j % len(clips)], plans[j % len(clips)], pool0, np.arange(j * fpc, (j + 1) * fpc, dtype=np.int32))) for j in range(cps)]
+    for f in futs:
+        f.result()
     barrier()
     for _ in range(max(args.warmup, 3)):
-        tower.embed_pool(pools[0])
+        tower.embed_pool(pool0)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -221,63 +292,122 @@ def run_b200(args) -> None:
     ctx.profile_begin()
     ev0.record()
     for _ in range(args.steps):
-        emb, _, score = tower.embed_pool(pools[0])
+        emb, _, score = tower.embed_pool(pool0)
     ev1.record()
     prof = ctx.profile_end()
     barrier()
     dev_s = max_over_ranks(ev0.elapsed_time(ev1) / 1e3)
     launches = ctx.launch_count() - l0
     value = world * cps * args.steps / dev_s
+    del pool0
 
-    # ---- end-to-end measurement (e2e): host mp4 bytes -> NVDEC -> preprocess -> tower -> host results.
-    # Decode of steps i+1, i+2 (NVDEC engines + host parsing threads) overlaps the tower of step i (SMs); three surface pools.
-    def e2e_run(n_steps: int, seek: bool):
-        # three surface pools: the clips of steps i+1 and i+2 are queued on the decode threads while the tower works on step i,
-        # so no NVDEC session idles at a step boundary waiting for the slowest clip of the step
-        futs = {}
+    # ---- end-to-end measurement (e2e): the product stage on host tasks
+    cpu_t = lambda: sum(os.times()[:2])  # noqa: E731 - user + system CPU seconds of this process (decode threads included)
 
-        def submit(i):
-            futs[i] = [tp.submit(decode_clip, j, pools[i % 3], seek) for j in range(cps)]
-
-        for i in range(min(2, n_steps)):
-            submit(i)
-        decoded = 0
-        for i in range(n_steps):
-            decoded += sum(f.result() for f in futs.pop(i))
-            if i + 2 < n_steps:
-                submit(i + 2)  # pool (i+2)%3 was last read by the tower of step i-1, synchronised below
-            emb, _, score = tower.embed_pool(pools[i % 3])
-            host_emb.copy_(emb, non_blocking=True)
-            host_score.copy_(score, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        return decoded
-
-    def e2e_measure(seek: bool):
-        e2e_run(max(1, min(args.warmup, 2)), seek)
+    def e2e_measure(st, n_calls: int) -> dict:
+        st.process_data(make_tasks(0))  # warm-up call: sessions created, pools + pinned buffers allocated
         barrier()
+        c0, t0 = cpu_t(), time.perf_counter()
+        decoded = scored = 0
+        perf_s = 0.0
+        for k in range(n_calls):
+            tasks = st.process_data(make_tasks(k + 1))
+            decoded += st.last_call_stats["frames_decoded"]
+            for t in tasks:
+                v = t.video
+                scored += sum(1 for c in v.clips + v.filtered_clips if c.aesthetic_score is not None and c.aesthetic_score > -1.0 and c.openai_embedding is not None)
+            perf_s += tasks[0].stage_perf["NvdecClipAestheticStage"].process_time
+        barrier()
+        wall_local = time.perf_counter() - t0
+        sec = max_over_ranks(wall_local)
+        cpu_used = cpu_t() - c0
+        n_clips = cps * args.tasks_per_call * n_calls
+        assert scored == n_clips, f"{scored} of {n_clips} clips scored"
+        h2d = sum(len(clips[(args.tasks_per_call * cps + j) % len(clips)]) for j in range(cps * args.tasks_per_call))
+        decoded_all = sum_over_ranks(decoded)
+        return {"value": world * n_clips / sec, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": cps * args.tasks_per_call * fpc * (cfg.proj_dim + 1) * 4,
+                "api": "NvdecClipAestheticStage.process_data(list[SplitPipeTask]) on a set-up stage (the call xenna's StageWorker makes)",
+                "clips_per_call": cps * args.tasks_per_call, "calls": n_calls, "ms_per_call": 1e3 * sec / n_calls,
+                "frames_per_sec": world * n_clips * fpc / sec, "decoded_frames_per_sec": decoded_all / sec,
+                "decoded_frames_per_clip": decoded / max(1, n_clips), "nvdec_sessions": args.decoders,
+                "stage_perf_process_time_s": perf_s, "wall_s_this_rank": wall_local,
+                "host_cpu_cores_busy_this_rank": cpu_used / wall_local, "numa_node": st.last_call_stats.get("numa_node"),
+                "pinned_cpus": st.last_call_stats.get("pinned_cpus"), "seek_keyframes": bool(st._seek)}  # fmt: skip
+
+    def gather_per_rank(x: float) -> list:
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
+    def decode_only(dpool, data_list, seconds: float) -> float:
+        """Every session decoding whole clips back to back for `seconds`, surfaces discarded: frames/s of this GPU."""
+        deadline = [0.0]
+
+        def loop(dec, k):
+            n, i = 0, k
+            while time.perf_counter() < deadline[0]:
+                n += decode_discard(dec, data_list[i % len(data_list)])
+                i += dpool.sessions
+            return n
+
+        list(f.result() for f in [dpool.submit(lambda dec, k=k: decode_discard(dec, data_list[k % len(data_list)])) for k in range(dpool.sessions)])  # sessions up
         t0 = time.perf_counter()
-        decoded = e2e_run(args.e2e_steps, seek)
-        barrier()
-        sec = max_over_ranks(time.perf_counter() - t0)
-        h2d = sum(len(clips[k]) for k in step_clips)
-        return {"value": world * cps * args.e2e_steps / sec, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": frames_per_step * (cfg.proj_dim + 1) * 4,
-                "steps": args.e2e_steps, "ms_per_step": 1e3 * sec / args.e2e_steps, "frames_per_sec": world * frames_per_step * args.e2e_steps / sec,
-                "decoded_frames_per_sec": world * decoded / sec, "decoded_frames_per_step": decoded // args.e2e_steps, "nvdec_sessions": n_dec}  # fmt: skip
+        deadline[0] = t0 + seconds
+        n = sum(f.result() for f in [dpool.submit(loop, k) for k in range(dpool.sessions)])
+        return n / (time.perf_counter() - t0)
 
-    e2e = e2e_sparse = ceiling = None
+    e2e = e2e_sparse = ceiling = exchange = None
     e2e_error = None
     if not args.no_e2e:
         try:
-            e2e = e2e_measure(seek=False)
-            e2e["note"] = ("every frame up to the last sampled one is decoded (reference semantics, decoder_utils.py:439-455); synthetic I_PCM + "
-                           "motion-only P pictures; decode of the next two steps overlaps the tower of step i")
-            e2e_sparse = e2e_measure(seek=True)
-            e2e_sparse["note"] = "CB_DECODE_SEEK_SYNC: only GOPs holding sampled frames are decoded (identical frames); closed GOP = 30, 1 fps sampling"
-            ceil_fps = decode_ceiling(2 * n_dec)
-            ceiling = {"decode_only_frames_per_sec_per_gpu": ceil_fps, "sessions": n_dec,
-                       "e2e_fraction_of_decode_ceiling": (e2e["decoded_frames_per_sec"] / world) / ceil_fps if ceil_fps > 0 else None}
+            e2e = e2e_measure(stage, args.e2e_steps)
+            e2e["per_rank_decoded_fps"] = gather_per_rank(e2e["decoded_frames_per_clip"] * cps * args.tasks_per_call * args.e2e_steps / e2e["wall_s_this_rank"])
+            e2e["note"] = ("every frame up to the last sampled one is decoded (reference semantics, decoder_utils.py:439-455); residual-coded ~4 Mb/s "
+                           "synthetic clips; decode of tower batches k+1, k+2 overlaps the tower of batch k INSIDE the stage")
+            ceil_fps = decode_only(stage._decode_pool, clips, args.ceiling_seconds)
+            sintel = ROOT / "tests" / "golden" / "sintel_clip_10s.mp4"
+            real = None
+            if sintel.exists():
+                sd = sintel.read_bytes()
+                fps_real = decode_only(stage._decode_pool, [sd], 3.0)
+                real = {"clip": "tests/golden/sintel_clip_10s.mp4 (854x480, High profile, CABAC, B-frames-free real content)", "frames_per_sec_per_gpu": fps_real,
+                        "macroblocks_per_sec": fps_real * 54 * 30, "as_1080p_frames_per_sec": fps_real * (54 * 30) / (120 * 68)}  # fmt: skip
+            ceiling = {"decode_only_frames_per_sec_per_gpu": ceil_fps, "seconds": args.ceiling_seconds, "sessions": args.decoders,
+                       "e2e_fraction_of_decode_ceiling": (e2e["decoded_frames_per_sec"] / world) / ceil_fps if ceil_fps > 0 else None,
+                       "real_content": real}  # fmt: skip
+            stage.destroy()
+            stage2 = make_stage(seek=True)  # the stage's default
+            e2e_sparse = e2e_measure(stage2, args.e2e_steps)
+            e2e_sparse["note"] = "CB_DECODE_SEEK_SYNC (stage default): only GOPs holding sampled frames are decoded (identical frames); closed GOP = 30, 1 fps sampling"
+            if world > 1:
+                # the one exchange step of the design (BASELINE.json C3/C4): NCCL all-gather of the clip embeddings, then cosine dedup
+                from cosmos_curate_b200.dedup import semdedup_cluster
+                from cosmos_curate_b200.sharding import all_gather_embeddings
+
+                tasks = stage2.process_data(make_tasks(99))
+                local_emb = torch.from_numpy(np.stack([c.openai_embedding for t in tasks for c in t.video.clips + t.video.filtered_clips])).cuda()
+                all_gather_embeddings(local_emb)  # warm-up (communicator creation)
+                barrier()
+                g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                g0.record()
+                allemb, _ = all_gather_embeddings(local_emb)
+                g1.record()
+                res = semdedup_cluster(np.arange(allemb.shape[0]), allemb, torch.zeros(allemb.shape[0]), eps=0.01)
+                g2.record()
+                torch.cuda.synchronize()
+                exchange = {"collective": "NCCL all_gather (padded) of per-rank [n_i, 768] fp32 clip embeddings", "rows_per_rank": int(local_emb.shape[0]),
+                            "rows_total": int(allemb.shape[0]), "allgather_ms": max_over_ranks(g0.elapsed_time(g1)), "semdedup_ms": max_over_ranks(g1.elapsed_time(g2)),
+                            "kept": res["kept"], "total": res["total"]}  # fmt: skip
+            stage2.destroy()
         except Exception as exc:  # noqa: BLE001 - e.g. libnvcuvid missing on the box: report it, keep the device-resident numbers
-            e2e_error = f"{type(exc).__name__}: {exc}"
+            import traceback
+
+            e2e_error = f"{type(exc).__name__}: {exc} | {traceback.format_exc()[-600:]}"
+            if world > 1:
+                raise
     shot = None
     if rank == 0 and not args.no_shots:
         try:
@@ -312,8 +442,10 @@ def run_b200(args) -> None:
         "metric": "clips_per_sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "frames_per_sec": world * frames_per_step * args.steps / dev_s,
-        "config": {"workload": WORKLOAD, "implementation": "one process per B200: NVDEC + fused preprocess kernel + tcgen05 tower",
+        "config": {"workload": WORKLOAD, "implementation": "one process per B200: NVDEC + fused preprocess kernel + tcgen05 tower behind NvdecClipAestheticStage",
                    "clips_per_step": cps, "frames_per_clip": fpc, "frames_per_step": frames_per_step, "sample_fps": SAMPLE_FPS, "distinct_clips": args.distinct_clips,
+                   "clip_bitrate_bps": float(np.mean([8 * len(c) / SECONDS for c in clips])),
+                   "clip_stream": "tools/synth_h264.make_coded_clip: Intra16x16 IDR (DC + sparse AC, chroma DC) + P (P_Skip runs, quarter-pel 16x16 motion, sparse 4x4 residuals), CAVLC, deblocking on, GOP 30",
                    "network": "clip-vit-large-patch14, seeded random weights, fp16 operands / fp32 accumulate+residual", "sharding": f"{world} rank(s), clips sharded per rank, no data-path collective",
                    "l2": "inputs (NV12 pool 0.88 GB + activations > 1 GB) exceed the 126 MB L2", "value_inputs": "decoded NV12 surfaces resident in HBM"},
         "clocks": clocks, "gpu_launches": int(launches),
@@ -322,8 +454,10 @@ def run_b200(args) -> None:
                      "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)", "launches_per_step": gemm_n / args.steps,
                      "ms_per_step": gemm_ms / args.steps, "share_of_step": gemm_ms / args.steps / step_ms},
         "roofline_other": other,
-        "e2e": e2e, "e2e_keyframe_seek": e2e_sparse, "decode_roofline": ceiling,
+        "e2e": e2e, "e2e_keyframe_seek": e2e_sparse, "decode_roofline": ceiling, "host": host_cpu_info(),
     }  # fmt: skip
+    if exchange is not None:
+        line["exchange"] = exchange
     if shot is not None:
         if "tflops_fp32" in shot and clocks:
             peak = ctx.device_info()["sm_count"] * 128 * 2 * clocks["sm_max_mhz"] * 1e6 / 1e12  # FFMA lanes x 2 flop x clock
@@ -332,11 +466,71 @@ def run_b200(args) -> None:
         line["shot_detection"] = shot
     if e2e_error:
         line["e2e_error"] = e2e_error
+    if world == 1 and not args.no_gpu_library:
+        try:
+            line["gpu_library_baseline"] = gpu_library_baseline(clips[:4], torch)
+        except Exception as exc:  # noqa: BLE001
+            line["gpu_library_baseline"] = {"error": f"{type(exc).__name__}: {exc}"}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(clips[:1])
+        line["cpu_baseline"] = cpu_baseline(clips[:4])
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def gpu_library_baseline(clips: list[bytes], torch, n_calls: int = 12) -> dict:
+    """The reference's GPU *library* path restated without Ray: frames decoded on the CPU exactly
+    as ClipFrameExtractionStage does, then per clip ONE call of `_CLIPImageEmbeddings.__call__` semantics - uint8 frames H2D,
+    torchvision Resize(224, bicubic, antialias) / CenterCrop / ConvertImageDtype / Normalize on the GPU, HF `CLIPModel`
+    .get_image_features in fp32, L2 norm (clip.py:48-74), the 5-Linear aesthetic MLP (aesthetics.py:44-53) and `.cpu()`
+    (aesthetic_filter_stages.py:181-183).  Library code only (torchvision + transformers + cuBLAS/cuDNN); none of this repo's
+    kernels.  Weights are random-initialised ViT-L/14 (no checkpoints offline) - the arithmetic is the same."""
+    from torchvision import transforms
+    from transformers import CLIPConfig, CLIPModel
+
+    from oracle import cpu_path
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    tf = transforms.Compose([transforms.Resize(224, interpolation=transforms.InterpolationMode.BICUBIC, antialias=True), transforms.CenterCrop(224),
+                             transforms.ConvertImageDtype(torch.float32),
+                             transforms.Normalize(mean=(0.48145466, 0.4578275, 0.40821073), std=(0.26862954, 0.26130258, 0.27577711))])  # fmt: skip
+    hf_cfg = CLIPConfig(vision_config={"hidden_size": 1024, "intermediate_size": 4096, "num_hidden_layers": 24, "num_attention_heads": 16, "patch_size": 14,
+                                       "image_size": 224, "projection_dim": 768}, projection_dim=768)  # fmt: skip
+    torch.manual_seed(0)
+    model = CLIPModel(hf_cfg).to(dev).eval()
+    mlp = torch.nn.Sequential(torch.nn.Linear(768, 1024), torch.nn.Dropout(0.2), torch.nn.Linear(1024, 128), torch.nn.Dropout(0.2), torch.nn.Linear(128, 64),
+                              torch.nn.Dropout(0.1), torch.nn.Linear(64, 16), torch.nn.Linear(16, 1)).to(dev).eval()  # fmt: skip
+    t0 = time.perf_counter()
+    decoded = [cpu_path.decode_sampled_frames(c, SAMPLE_FPS, 4)[0] for c in clips]
+    decode_s = (time.perf_counter() - t0) / len(clips)
+
+    @torch.no_grad()
+    def call(frames: np.ndarray) -> np.ndarray:
+        x = torch.from_numpy(frames).permute(0, 3, 1, 2).to(dev)
+        feats = model.get_image_features(pixel_values=tf(x))
+        feats = feats.pooler_output if hasattr(feats, "pooler_output") else feats  # transformers >= 5 returns an output object
+        emb = feats / feats.norm(dim=-1, keepdim=True)
+        return mlp(emb).cpu().numpy()
+
+    for k in range(3):
+        call(decoded[k % len(decoded)])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    frames = 0
+    for k in range(n_calls):
+        frames += len(decoded[k % len(decoded)])
+        call(decoded[k % len(decoded)])
+    torch.cuda.synchronize()
+    model_s = (time.perf_counter() - t0) / n_calls
+    del model, mlp
+    torch.cuda.empty_cache()
+    cores = effective_cores()
+    return {"kind": "reference GPU library path restated without Ray (torch-CUDA torchvision + HF CLIPModel fp32, one call per clip); NOT the reference's Ray pipeline",
+            "gpu_model_clips_per_sec": 1.0 / model_s, "gpu_model_frames_per_sec": frames / n_calls / model_s, "gpu_model_ms_per_clip": 1e3 * model_s,
+            "cpu_decode_s_per_clip_4_threads": decode_s,
+            "pipeline_clips_per_sec_estimate": min(1.0 / model_s, (cores / 4.0) / decode_s),
+            "estimate_note": f"min(GPU model stage, CPU decode stage with {cores} usable cores / 4 threads per decode actor) - the reference runs them as separate actors",
+            "sample": f"{n_calls} model calls of 11 frames (1080p); {len(clips)} clips decoded with cv2/libavcodec (PyAV stand-in)"}  # fmt: skip
 
 
 def shot_flops_per_window(frames: int = 100) -> float:
@@ -409,7 +603,7 @@ def cpu_baseline(clips: list[bytes]) -> dict:
     """Bounded CPU sample of the same workload: the oracle's restatement of the reference path (kind 'port')."""
     from oracle import cpu_path, vit
 
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     procs, threads = cpu_layout(cores)
     pool = cpu_path.CpuReferencePool(vit.CLIP_VIT_L14, seed=0, procs=procs, threads=threads)
     try:
@@ -418,7 +612,7 @@ def cpu_baseline(clips: list[bytes]) -> dict:
         r = pool.run([clips[i % len(clips)] for i in range(n)], SAMPLE_FPS)
     finally:
         pool.close()
-    return {"value": r["clips"] / r["seconds"], "unit": "clips/s", "cores": procs * threads, "kind": "port",
+    return {"value": r["clips"] / r["seconds"], "unit": "clips/s", "cores": procs * threads, "kind": "port", "host": host_cpu_info(),
             "sample": f"{n} clips (1080p30 10 s, {r['frames']} sampled frames) over {procs} worker processes x {threads} threads: cv2/libavcodec decode + "
                       "torchvision transforms + oracle torch-fp32 ViT-L/14, one model call per clip",
             "frames_per_sec": r["frames"] / r["seconds"], "worker_seconds": {k: r[k] for k in ("decode_s", "preprocess_s", "model_s")}}  # fmt: skip
@@ -431,9 +625,12 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips-per-step", type=int, default=24)
-    ap.add_argument("--distinct-clips", type=int, default=4)
+    ap.add_argument("--distinct-clips", type=int, default=64)
+    ap.add_argument("--tasks-per-call", type=int, default=10, help="SplitPipeTasks (of clips-per-step clips each) per process_data call of the e2e measurement")
+    ap.add_argument("--ceiling-seconds", type=float, default=5.0, help="duration of the decode-only ceiling measurement")
+    ap.add_argument("--no-gpu-library", action="store_true", help="skip the reference GPU library-path baseline")
     ap.add_argument("--decoders", type=int, default=20, help="concurrent NVDEC sessions per GPU (7 engines on B200)")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=2, help="timed process_data calls of the e2e measurement")
     ap.add_argument("--ref-clips", type=int, default=2, help="clips per step of the reference arm (bounded sample)")
     ap.add_argument("--no-shots", action="store_true", help="skip the shot-detection secondary measurement")
     ap.add_argument("--no-e2e", action="store_true")

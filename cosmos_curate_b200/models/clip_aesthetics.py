@@ -33,6 +33,8 @@ class CLIPAestheticScorer(ModelInterface):
         return [_AESTHETICS_MODEL_ID, _CLIP_MODEL_ID]
 
     def setup(self) -> None:
+        if self._clip_model is not None:  # idempotent: several stages of one actor process may share the model object
+            return
         kw = self._kw
         dim = (kw["config"].proj_dim or kw["config"].hidden) if kw["config"] is not None else 768
         self._aesthetic_model = AestheticScorer(weights_dir=kw["aesthetic_weights_dir"], seed=kw["seed"], dim=dim)

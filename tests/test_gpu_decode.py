@@ -148,3 +148,49 @@ def test_keyframe_seek_is_bit_identical_and_lossless_vs_source(ctx):
     np.testing.assert_array_equal(a[k75, 40 : h - 40, 40 : w - 80], a[k60, 40 + 15 : h - 40 + 15, 40 + 30 : w - 80 + 30])
     assert decode_discard(dec, data) == 120
     dec.close()
+
+
+def test_nvdec_matches_libavcodec_on_residual_coded_clip(ctx, tmp_path):
+    """The 4 Mb/s-class residual-coded synthetic stream (CAVLC coefficients, Intra16x16 IDRs, P_Skip runs, quarter-pel motion,
+    in-loop deblocking): NVDEC luma == libavcodec luma on every sampled frame, sequential and keyframe-seek alike, and the
+    I_PCM sentinel that ends every picture is intact (no entropy-decoding slip anywhere in the slice)."""
+    import cv2
+
+    from cosmos_curate_b200.runtime import Decoder, alloc_nv12_pool, mp4_index
+    from tools import synth_h264
+
+    w, h, fps = 1280, 720, 30
+    mp4, info = synth_h264.make_coded_clip(w, h, fps, 4.0, seed=21, bitrate=2.0e6, return_info=True)
+    path = tmp_path / "coded.mp4"
+    path.write_bytes(mp4)
+    data = np.frombuffer(mp4, dtype=np.uint8)
+    idx = mp4_index(data, ctx)
+    assert idx["n_samples"] == 120 and idx["n_sync"] == 4 and not idx["has_ctts"]
+    assert abs(8 * idx["sample_bytes"] / 4.0 - 2.0e6) / 2.0e6 < 0.15
+    ids = np.array([0, 1, 29, 30, 45, 75, 90, 119], dtype=np.int32)
+    cap = cv2.VideoCapture(str(path))
+    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+    luma, i = {}, 0
+    while True:
+        ok, y = cap.read()
+        if not ok:
+            break
+        if i in set(ids.tolist()):
+            luma[i] = y.copy()
+        i += 1
+    assert i == 120
+    dec = Decoder(ctx)
+    full, sparse = alloc_nv12_pool(ctx, len(ids), w, h), alloc_nv12_pool(ctx, len(ids), w, h)
+    st = dec.decode(data, ids, full, np.arange(len(ids)))
+    st2 = dec.decode(data, ids, sparse, np.arange(len(ids)), seek_keyframes=True)
+    assert st["frames_decoded"] == 120 and st2["frames_decoded"] < 120
+    a, b = full.buf.cpu().numpy(), sparse.buf.cpu().numpy()
+    np.testing.assert_array_equal(a[:, : h + h // 2, :w], b[:, : h + h // 2, :w])
+    pcm = info["pcm"]
+    for k, f in enumerate(ids):
+        np.testing.assert_array_equal(a[k, :h, :w], luma[int(f)].reshape(h, w))
+        np.testing.assert_array_equal(a[k, h - 12 : h, w - 12 : w], pcm[:256].reshape(16, 16)[4:, 4:])  # sentinel interior, luma
+        uv = a[k, h + h // 2 - 6 : h + h // 2, w - 12 : w]
+        np.testing.assert_array_equal(uv[:, 0::2], pcm[256:320].reshape(8, 8)[2:, 2:])  # Cb
+        np.testing.assert_array_equal(uv[:, 1::2], pcm[320:384].reshape(8, 8)[2:, 2:])  # Cr
+    dec.close()

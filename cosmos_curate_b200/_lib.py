@@ -23,6 +23,7 @@ ACT_QUICK_GELU, ACT_GELU_TANH = 0, 1
 ARCH_CLIP, ARCH_SIGLIP = 0, 1
 EPI_NONE, EPI_QUICK_GELU, EPI_GELU_TANH = 0, 1, 2
 DECODE_SEEK_SYNC, DECODE_DISCARD_ALL = 1, 2
+CUBIC_OPENCV, CUBIC_IPP = 0, 1
 
 
 class CurateB200Error(RuntimeError):
@@ -76,6 +77,7 @@ SIGNATURES = {
     "cb_preprocess_clip": (_i, [_vp, C.POINTER(SurfacePool), _pi32, _i, _i, _i, _i, _i, _i, _pf, _pf, _vp, _vp]),
     "cb_preprocess_clip_u8": (_i, [_vp, C.POINTER(SurfacePool), _pi32, _i, _i, _vp, _vp]),
     "cb_preprocess_bilinear_u8": (_i, [_vp, C.POINTER(SurfacePool), _pi32, _i, _i, _i, _vp, _vp]),
+    "cb_resize_cubic_u8": (_i, [_vp, C.POINTER(SurfacePool), _pi32, _i, _i, _i, _i, _vp, _vp]),
     "cb_nv12_to_rgb": (_i, [_vp, C.POINTER(SurfacePool), _pi32, _i, _vp, _vp]),
     "cb_vit_create": (_i, [_vp, C.POINTER(VitCfg), C.POINTER(_vp)]),
     "cb_vit_destroy": (None, [_vp]),

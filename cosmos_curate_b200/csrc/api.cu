@@ -139,6 +139,11 @@ void cb_destroy(cb_ctx* ctx) {
     cudaFree(kv.second.d_size);
     cudaFree(kv.second.d_w);
   }
+  for (auto& kv : ctx->cubic_taps) {
+    cudaFree(kv.second.d_first);
+    cudaFree(kv.second.d_wq);
+    cudaFree(kv.second.d_wf);
+  }
   if (ctx->d_norm_lut) cudaFree(ctx->d_norm_lut);
   if (ctx->d_slots) cudaFree(ctx->d_slots);
   for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);

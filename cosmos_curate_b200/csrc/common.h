@@ -29,6 +29,12 @@ struct TapTable {  // antialiased-bicubic tap table for one axis (device memory)
   std::vector<int> h_min, h_size;
 };
 
+struct CubicTaps {  // cv2.resize(INTER_CUBIC) tap table for one axis (device memory): 4 taps per output
+  int* d_first = nullptr;    // [dst] source index of the first tap (unclamped)
+  short* d_wq = nullptr;     // [dst][4] weights quantised to 2^11 (OpenCV's own fixed-point path)
+  float* d_wf = nullptr;     // [dst][4] float weights (IPP-style float path)
+};
+
 }  // namespace cb
 
 struct cb_ctx {
@@ -40,6 +46,7 @@ struct cb_ctx {
   std::mutex mu;
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
   std::map<std::tuple<int, int, int, int>, cb::TapTable> taps;  // (in, out, crop_off, crop_len)
+  std::map<std::pair<int, int>, cb::CubicTaps> cubic_taps;      // (src, dst)
   float* d_norm_lut = nullptr;                                  // [3*256] fp32, normalise LUT currently loaded
   float lut_mean[3] = {0, 0, 0}, lut_std[3] = {0, 0, 0};
   std::atomic<unsigned long long> launches{0};  // kernels launched by this library (bench.py reports it); decode threads launch too

@@ -513,6 +513,94 @@ __global__ void nv12_to_rgb_kernel(const SimpleArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// cv2.resize(frame, (out_w, out_h), INTER_CUBIC) on the RGB image of a surface: the optional `target_res` resize of
+// extract_frames (decoder_utils.py:666-670).  Keys cubic a = -0.75, 4 taps per axis whatever the scale (no antialiasing),
+// border replicate.  Two arithmetic variants, because opencv-python-headless (the reference's pin) ships two:
+//   CB_CUBIC_OPENCV : OpenCV's own code (aarch64 wheels; x86 wheels with IPP off) - int16 weights at 2^11, exact int32
+//                     horizontal sums, vertical S0*b0 + (S1*b1 + (S2*b2 + S3*b3)) in fp32 without contraction, round half
+//                     even (vector body) or (sum + 2^21) >> 22 (scalar row tail).  Bit-exact.
+//   CB_CUBIC_IPP    : x86 wheels dispatch to Intel IPP, whose result is the correctly rounded real-valued cubic up to fp32
+//                     noise (measured: differs from exact arithmetic on < 3e-5 of the pixels, always at ties): fp32 weights,
+//                     fp32 accumulation, round half even.
+struct CubicArgs {
+  const uint8_t* base;
+  size_t slot_stride;
+  const int* slots;
+  int n, w, h, pitch, luma_rows, format, out_w, out_h, mode, n_vec;
+  const int *x0, *y0;
+  const short *wxq, *wyq;
+  const float *wxf, *wyf;
+  uint8_t* out;
+};
+
+__global__ void resize_cubic_kernel(const CubicArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = a.out_w * a.out_h;
+  if (i >= a.n * per) return;
+  const int f = i / per, p = i - f * per, yo = p / a.out_w, xo = p - yo * a.out_w;
+  const uint8_t* fr = a.base + (size_t)a.slots[f] * a.slot_stride;
+  const int xs = a.x0[xo], ys = a.y0[yo];
+  int hs[4][3];
+  float hf[4][3];
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky) {
+    const int y = min(max(ys + ky, 0), a.h - 1);
+    int acc[3] = {0, 0, 0};
+    float accf[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      const int x = min(max(xs + kx, 0), a.w - 1);
+      int r, g, b;
+      if (a.format == CB_FMT_NV12) {
+        fetch_rgb_nv12(fr, a.pitch, a.luma_rows, x, y, r, g, b);
+      } else {
+        const uint8_t* px = fr + (size_t)y * a.pitch + 3 * x;
+        r = px[0], g = px[1], b = px[2];
+      }
+      if (a.mode == CB_CUBIC_OPENCV) {
+        const int wq = a.wxq[xo * 4 + kx];
+        acc[0] += r * wq, acc[1] += g * wq, acc[2] += b * wq;
+      } else {
+        const float wf = a.wxf[xo * 4 + kx];
+        accf[0] = fmaf((float)r, wf, accf[0]), accf[1] = fmaf((float)g, wf, accf[1]), accf[2] = fmaf((float)b, wf, accf[2]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) hs[ky][c] = acc[c], hf[ky][c] = accf[c];
+  }
+  uint8_t* o = a.out + (size_t)i * 3;
+  if (a.mode == CB_CUBIC_OPENCV) {
+    const float sc = 1.0f / 4194304.0f;  // 2^-22, exact
+    const int b0i = a.wyq[yo * 4 + 0], b1i = a.wyq[yo * 4 + 1], b2i = a.wyq[yo * 4 + 2], b3i = a.wyq[yo * 4 + 3];
+    const float b0 = (float)b0i * sc, b1 = (float)b1i * sc, b2 = (float)b2i * sc, b3 = (float)b3i * sc;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int v;
+      if (xo * 3 + c < a.n_vec) {
+        float t = __fmul_rn((float)hs[3][c], b3);
+        t = __fadd_rn(__fmul_rn((float)hs[2][c], b2), t);
+        t = __fadd_rn(__fmul_rn((float)hs[1][c], b1), t);
+        t = __fadd_rn(__fmul_rn((float)hs[0][c], b0), t);
+        v = __float2int_rn(t);
+      } else {
+        const long long e = (long long)hs[0][c] * b0i + (long long)hs[1][c] * b1i + (long long)hs[2][c] * b2i + (long long)hs[3][c] * b3i;
+        v = (int)((e + (1ll << 21)) >> 22);
+      }
+      o[c] = (uint8_t)min(max(v, 0), 255);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float t = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) t = fmaf(hf[ky][c], a.wyf[yo * 4 + ky], t);
+      o[c] = (uint8_t)min(max(__float2int_rn(t), 0), 255);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 static float cubic_aa(float x) {  // Keys a = -0.5, float32 like ATen's bicubic_filter
   const float a = -0.5f;
@@ -766,6 +854,74 @@ static int run_simple(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* s
   return CB_OK;
 }
 
+// OpenCV resize(): fx = float((dx + 0.5) * scale - 0.5) with scale = 1 / (dst / src) in double; interpolateCubic in float.
+static const CubicTaps* get_cubic_taps(cb_ctx* ctx, int src, int dst) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto key = std::make_pair(src, dst);
+  auto it = ctx->cubic_taps.find(key);
+  if (it != ctx->cubic_taps.end()) return &it->second;
+  std::vector<int> first(dst);
+  std::vector<short> wq(4 * (size_t)dst);
+  std::vector<float> wf(4 * (size_t)dst);
+  const double inv_scale = (double)dst / (double)src, scale = 1.0 / inv_scale;
+  for (int d = 0; d < dst; ++d) {
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    const int sx = (int)std::floor(fx);
+    fx -= (float)sx;
+    first[d] = sx - 1;
+    const float A = -0.75f;
+    float c[4];
+    c[0] = ((A * (fx + 1.f) - 5.f * A) * (fx + 1.f) + 8.f * A) * (fx + 1.f) - 4.f * A;
+    c[1] = ((A + 2.f) * fx - (A + 3.f)) * fx * fx + 1.f;
+    c[2] = ((A + 2.f) * (1.f - fx) - (A + 3.f)) * (1.f - fx) * (1.f - fx) + 1.f;
+    c[3] = 1.f - c[0] - c[1] - c[2];
+    // float path: the same Keys kernel evaluated in double at the double-precision phase (what a correctly rounded result needs)
+    const double pos = (d + 0.5) * scale - 0.5, fr = pos - std::floor(pos), Ad = -0.75;
+    const double cd[4] = {((Ad * (fr + 1) - 5 * Ad) * (fr + 1) + 8 * Ad) * (fr + 1) - 4 * Ad, ((Ad + 2) * fr - (Ad + 3)) * fr * fr + 1,
+                          ((Ad + 2) * (1 - fr) - (Ad + 3)) * (1 - fr) * (1 - fr) + 1, 0.0};
+    for (int k = 0; k < 4; ++k) {
+      const float q = std::nearbyint(c[k] * 2048.f);  // saturate_cast<short>(float) = cvRound: half to even
+      wq[4 * (size_t)d + k] = (short)std::min(32767.f, std::max(-32768.f, q));
+      wf[4 * (size_t)d + k] = (float)(k < 3 ? cd[k] : 1.0 - cd[0] - cd[1] - cd[2]);
+    }
+  }
+  CubicTaps t;
+  if (cudaMalloc(&t.d_first, dst * sizeof(int)) != cudaSuccess || cudaMalloc(&t.d_wq, 4 * (size_t)dst * sizeof(short)) != cudaSuccess ||
+      cudaMalloc(&t.d_wf, 4 * (size_t)dst * sizeof(float)) != cudaSuccess)
+    return nullptr;
+  cudaMemcpy(t.d_first, first.data(), dst * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(t.d_wq, wq.data(), 4 * (size_t)dst * sizeof(short), cudaMemcpyHostToDevice);
+  cudaMemcpy(t.d_wf, wf.data(), 4 * (size_t)dst * sizeof(float), cudaMemcpyHostToDevice);
+  return &(ctx->cubic_taps[key] = t);
+}
+
+static int run_resize_cubic(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int out_w, int out_h, int mode, uint8_t* out,
+                            cudaStream_t stream) {
+  int rc = check_pool(ctx, pool, n, slots);
+  if (rc) return rc;
+  if (n == 0) return CB_OK;
+  if (!out) return fail(ctx, CB_ERR_ARG, "null output");
+  if (out_w <= 0 || out_h <= 0 || out_w > 8192 || out_h > 8192) return fail(ctx, CB_ERR_ARG, "bad output size %dx%d", out_w, out_h);
+  if (mode != CB_CUBIC_OPENCV && mode != CB_CUBIC_IPP) return fail(ctx, CB_ERR_ARG, "unknown cubic mode %d", mode);
+  if (pool->format == CB_FMT_NV12 && ((pool->width | pool->height) & 1)) return fail(ctx, CB_ERR_UNSUPPORTED, "NV12 needs even dimensions");
+  const CubicTaps* tx = get_cubic_taps(ctx, pool->width, out_w);
+  const CubicTaps* ty = get_cubic_taps(ctx, pool->height, out_h);
+  if (!tx || !ty) return fail(ctx, CB_ERR_CUDA, "cubic tap table allocation failed");
+  CubicArgs a{};
+  a.base = (const uint8_t*)pool->base, a.slot_stride = pool->slot_stride;
+  a.n = n, a.w = pool->width, a.h = pool->height, a.pitch = pool->pitch, a.luma_rows = pool->luma_rows, a.format = pool->format;
+  a.out_w = out_w, a.out_h = out_h, a.mode = mode, a.out = out;
+  a.n_vec = (out_w * 3) / 8 * 8;  // elements of a row handled by the 8-lane vector body of VResizeCubicVec_32s8u
+  a.x0 = tx->d_first, a.wxq = tx->d_wq, a.wxf = tx->d_wf, a.y0 = ty->d_first, a.wyq = ty->d_wq, a.wyf = ty->d_wf;
+  rc = upload_slots(ctx, slots, n, stream, &a.slots);
+  if (rc) return rc;
+  mark_launch(ctx, CB_PROF_PREPROCESS, stream);
+  const long long total = (long long)n * out_w * out_h;
+  resize_cubic_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(a);
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
+}
+
 int bilinear_from_surface(cb_ctx* ctx, const void* base, int pitch, int luma_rows, int w, int h, int out_w, int out_h, uint8_t* out,
                           cudaStream_t stream) {
   SimpleArgs a{};
@@ -801,6 +957,12 @@ int cb_preprocess_bilinear_u8(cb_ctx* ctx, const cb_surface_pool* pool, const in
                               void* stream) {
   if (!ctx) return CB_ERR_ARG;
   return cb::run_simple(ctx, pool, slots, n, out_w, out_h, out, true, (cudaStream_t)stream);
+}
+
+int cb_resize_cubic_u8(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int out_w, int out_h, int mode, uint8_t* out,
+                       void* stream) {
+  if (!ctx) return CB_ERR_ARG;
+  return cb::run_resize_cubic(ctx, pool, slots, n, out_w, out_h, mode, out, (cudaStream_t)stream);
 }
 
 int cb_nv12_to_rgb(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, uint8_t* out, void* stream) {

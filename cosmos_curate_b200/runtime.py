@@ -137,6 +137,14 @@ class Context:
               "cb_preprocess_bilinear_u8", self.h)  # fmt: skip
         return out
 
+    def resize_cubic_u8(self, pool: "Pool", out_w: int, out_h: int, slots=None, mode: int = _lib.CUBIC_IPP) -> torch.Tensor:
+        """cv2.resize(frame, (out_w, out_h), INTER_CUBIC) per frame of the pool -> uint8 cuda [n, out_h, out_w, 3]."""
+        arr, ptr = self._slots(pool, slots)
+        out = torch.empty((len(arr), out_h, out_w, 3), dtype=torch.uint8, device=pool.buf.device)
+        check(self.lib.cb_resize_cubic_u8(self.h, C.byref(pool.desc), ptr, len(arr), out_w, out_h, mode, out.data_ptr(), _stream_ptr()),
+              "cb_resize_cubic_u8", self.h)  # fmt: skip
+        return out
+
     def nv12_to_rgb(self, pool: "Pool", slots=None) -> torch.Tensor:
         arr, ptr = self._slots(pool, slots)
         out = torch.empty((len(arr), pool.desc.height, pool.desc.width, 3), dtype=torch.uint8, device=pool.buf.device)

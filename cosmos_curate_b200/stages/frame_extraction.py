@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from .. import sampling
+from .. import _lib
 from .._lib import CurateB200Error
 from ..data_model import LazyData, StageTimer
 from ..interfaces import CuratorStage, CuratorStageResource
@@ -28,6 +29,16 @@ except Exception:  # noqa: BLE001
     logger = logging.getLogger(__name__)
 
 
+CUBIC_MODES = {"opencv": _lib.CUBIC_OPENCV, "ipp": _lib.CUBIC_IPP}
+
+
+def default_cubic_mode() -> str:
+    import os
+    import platform
+
+    return os.environ.get("CURATE_B200_CUBIC_MODE") or ("ipp" if platform.machine() in ("x86_64", "AMD64") else "opencv")
+
+
 class ClipFrameExtractionStage(CuratorStage):
     def __init__(  # noqa: PLR0913
         self,
@@ -38,14 +49,19 @@ class ClipFrameExtractionStage(CuratorStage):
         num_gpus_per_worker: float = 0.25,
         verbose: bool = False,
         log_stats: bool = False,
+        cubic_mode: str | None = None,
     ) -> None:
         self._timer = StageTimer(self)
         self._extraction_policies = extraction_policies
         self._target_fps = [2] if target_fps is None else target_fps
         self._target_res = (-1, -1) if target_res is None else target_res
-        if self._target_res[0] > 0 and self._target_res[1] > 0:
-            msg = "target_res (cv2 INTER_CUBIC square resize, decoder_utils.py:666-670) is not built on the NVDEC path yet"
-            raise NotImplementedError(msg)
+        # target_res = (height, width): cv2.resize(frame, (target_res[1], target_res[0]), INTER_CUBIC), aspect ratio not preserved
+        # (decoder_utils.py:666-670).  opencv-python-headless computes it with Intel IPP on x86-64 and with its own fixed-point
+        # code on aarch64; `cubic_mode` picks the matching arithmetic (default: this host's architecture, like the wheel would).
+        self._cubic_mode = cubic_mode or default_cubic_mode()
+        if self._cubic_mode not in ("ipp", "opencv"):
+            msg = f"cubic_mode={cubic_mode!r} not in ('ipp', 'opencv')"
+            raise ValueError(msg)
         self._num_gpus = num_gpus_per_worker
         self._verbose, self._log_stats = verbose, log_stats
 
@@ -86,7 +102,12 @@ class ClipFrameExtractionStage(CuratorStage):
         all_ids = np.unique(np.concatenate(list(plan.values()))).astype(np.int32)
         pool = self._surface_pool(idx["width"], idx["height"], len(all_ids))
         self._decoder.decode(data, all_ids, pool, np.arange(len(all_ids), dtype=np.int32))
-        rgb = self._ctx.nv12_to_rgb(pool, slots=np.arange(len(all_ids), dtype=np.int32))[:, : idx["height"], : idx["width"]].cpu().numpy()
+        slots = np.arange(len(all_ids), dtype=np.int32)
+        if self._target_res[0] > 0 and self._target_res[1] > 0:  # only 3 * th * tw bytes per frame cross PCIe (150 KB instead of 6 MB)
+            th, tw = self._target_res
+            rgb = self._ctx.resize_cubic_u8(pool, tw, th, slots=slots, mode=CUBIC_MODES[self._cubic_mode]).cpu().numpy()
+        else:
+            rgb = self._ctx.nv12_to_rgb(pool, slots=slots)[:, : idx["height"], : idx["width"]].cpu().numpy()
         pos = {int(f): i for i, f in enumerate(all_ids)}
         return {sig: rgb[[pos[int(f)] for f in ids]] for sig, ids in plan.items()}
 

@@ -53,6 +53,8 @@ class NvdecClipAestheticStage(CuratorStage):
         stage_batch_size: int = 8,
         seek_keyframes: bool = True,
         source: Literal["clip", "video_span"] = "clip",
+        target_res: tuple[int, int] | None = None,
+        cubic_mode: str | None = None,
         verbose: bool = False,
         log_stats: bool = False,
         model: CLIPAestheticScorer | None = None,
@@ -70,6 +72,13 @@ class NvdecClipAestheticStage(CuratorStage):
         # video (video.encoded_data) at clip.span, so ClipTranscodingStage's re-encode + this stage's re-decode disappear for runs
         # that only need scores / embeddings.  Pixels are the source's, not the 4 Mb/s re-encode's: not bit-comparable with "clip".
         self._source = source
+        # clip_extraction_target_res of the reference pipeline (splitting_pipeline -> ClipFrameExtractionStage(target_res=(r, r))):
+        # frames are squashed to (h, w) with cv2 INTER_CUBIC before the CLIP transforms (decoder_utils.py:666-670).  None / (-1, -1)
+        # = native resolution into the antialiased short-side resize (the reference default).
+        from .frame_extraction import CUBIC_MODES, default_cubic_mode
+
+        self._target_res = None if target_res is None or target_res[0] <= 0 or target_res[1] <= 0 else (int(target_res[0]), int(target_res[1]))
+        self._cubic_mode = CUBIC_MODES[cubic_mode or default_cubic_mode()]
         self._video_index: dict[int, tuple] = {}
         self._model = model if model is not None else CLIPAestheticScorer(max_batch=max_batch)
         self._reduce_fn = np.min
@@ -239,7 +248,12 @@ class NvdecClipAestheticStage(CuratorStage):
                     errs.append(e)
             pool, r = slots_of.pop(k)
             n = sum(len(ids) for _, _, ids, _ in batches[k][1])
-            emb, _, score = tower.embed_pool(pool, slots=np.arange(n, dtype=np.int32))
+            if self._target_res is not None:
+                th, tw = self._target_res
+                small = self._ctx.resize_cubic_u8(pool, tw, th, slots=np.arange(n, dtype=np.int32), mode=self._cubic_mode)
+                emb, _, score = tower.embed_pool(self._ctx.rgb_pool(small))
+            else:
+                emb, _, score = tower.embed_pool(pool, slots=np.arange(n, dtype=np.int32))
             score_h, emb_h = self._host_buffers(r)
             score_h[:n].copy_(score, non_blocking=True)
             if emb_h is not None:

@@ -104,6 +104,15 @@ int cb_preprocess_clip_u8(cb_ctx* ctx, const cb_surface_pool* pool, const int32_
 int cb_preprocess_bilinear_u8(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int out_w, int out_h,
                               uint8_t* out, void* stream);
 
+#define CB_CUBIC_OPENCV 0 /* OpenCV's own fixed-point code: aarch64 wheels, x86 wheels with IPP disabled - bit-exact */
+#define CB_CUBIC_IPP 1    /* x86 opencv-python wheels dispatch to Intel IPP: correctly rounded float cubic (<= 1 LSB on ~1e-5 of pixels) */
+/* cv2.resize(frame, (out_w, out_h), interpolation=cv2.INTER_CUBIC) of the RGB image of every selected frame (NV12 surfaces
+ * are colour-converted per tap), u8 HWC out[n][out_h][out_w][3].  The optional `target_res` square resize of extract_frames
+ * (decoder_utils.py:666-670; clip_extraction_target_res = 224 in benchmarks/split_pipeline/invoke.json:38): Keys cubic
+ * a = -0.75, 4 taps per axis at any scale (no antialiasing, aspect ratio not preserved), border replicate. */
+int cb_resize_cubic_u8(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int out_w, int out_h, int mode,
+                       uint8_t* out, void* stream);
+
 /* Full-resolution NV12 -> RGB24 (HWC, tightly packed): what decode_video_cpu_frame_ids returns per
  * frame (decoder_utils.py:439-451) / cvcuda.cvtcolor_into (nvcodec_utils.py:178).  Only for callers that
  * must hand RGB frames to an unmodified downstream stage. */

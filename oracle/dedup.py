@@ -8,11 +8,13 @@
   assign              nearest centroid as KMeans defines it (argmin squared Euclidean distance) and
                       cosine_dist_to_cent = 1 - clip(x . c/|c|) (:244-249)
 
-PARITY UNPINNED against the reference's own execution: its arithmetic is CuPy / cuML (cudf, cupy, cuml are not installed
-and need a GPU), and no reference test exercises dedup_actor.  This file restates the array expressions one to one; the
-reference's 4096-row tiling does not change any result (max / first-argmax are tiling-invariant by the `>` rule above).
-KMeansMG itself (scalable k-means++ seeding with cuML's RNG) is not reproducible outside cuML: only its defining
-properties are tested (labels are nearest centroids, centroids are cluster means, multi-rank == single-rank).
+Pinned (tests/test_dedup_cpu.py, tests/golden/dedup_ref.npz) against the reference's OWN array code for dedup(): the section
+dedup_actor.py:404-466 is executed from its source with numpy standing in for cupy (oracle/ref_import.dedup_core; CuPy mirrors
+numpy for every call in it), tiles of 256 and of the default 4096, exact / scaled / near duplicates and sort-key ties.  What stays
+unpinned is library behaviour outside that section: cudf's `sort_values` tie order (restated as a stable sort) and KMeansMG
+(scalable k-means++ seeding on cuML's RNG is not reproducible outside cuML: only its defining properties are tested - labels are
+nearest centroids, centroids are cluster means, multi-rank == single-rank).  The reference's 4096-row tiling does not change
+any result (max / first-argmax are tiling-invariant by the `>` rule above).
 
 Test infrastructure only (see oracle/__init__.py).
 """

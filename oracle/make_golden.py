@@ -15,6 +15,10 @@ Files written (all small):
   aesthetic_ref.npz       reference aesthetics.MLP (aesthetics.py:30-66) seeded state_dict + outputs
   transnetv2_ref.npz      reference _TransNetV2 on seeded weights (oracle.transnetv2.random_state_dict) + the reference's
                           _get_predictions / _get_scenes / _get_filtered_scenes outputs
+  resize_cubic_ref.npz    cv2.resize(INTER_CUBIC) exactly as extract_frames calls it (decoder_utils.py:666-670), once with Intel IPP
+                          (x86 opencv-python default) and once with cv2.ipp.setUseIPP(False) (OpenCV's own code = aarch64 wheels)
+  dedup_ref.npz           the array section of SemanticDedupActor.dedup (dedup_actor.py:404-466) executed from the reference's source
+                          with numpy standing in for cupy (oracle/ref_import.dedup_core) on clusters with planted duplicates
   siglip_tiny_hf.npz      transformers SiglipVisionModel tiny seeded (stand-in; not in the reference)
 
 Test infrastructure only (see oracle/__init__.py).
@@ -282,6 +286,51 @@ def gen_transnet() -> None:
     print("transnetv2_ref.npz", {k: v.shape for k, v in out.items() if k.startswith("prob")})
 
 
+def gen_resize_cubic() -> None:
+    """target_res resize of extract_frames: frames = np.array([cv2.resize(frame, (target_res[1], target_res[0]), INTER_CUBIC) ...])."""
+    import cv2
+
+    rng = np.random.default_rng(20250923)
+    cases = {"sq224_from_270x480": ((270, 480), (224, 224)), "up_odd": ((37, 53), (77, 51)), "sq224_from_64": ((64, 64), (224, 224)),
+             "thumb_27x48": ((180, 320), (27, 48))}  # name: ((src_h, src_w), target_res = (h, w))
+    out = {}
+    for name, ((h, w), (th, tw)) in cases.items():
+        smooth = cv2.GaussianBlur(rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8), (0, 0), 1.5)
+        img = np.where(rng.random((h, w, 1)) < 0.5, smooth, rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)).astype(np.uint8)
+        out[name + "_in"] = img
+        out[name + "_res"] = np.array([th, tw])
+        cv2.ipp.setUseIPP(True)
+        out[name + "_ipp"] = cv2.resize(img, (tw, th), interpolation=cv2.INTER_CUBIC)
+        cv2.ipp.setUseIPP(False)
+        out[name + "_opencv"] = cv2.resize(img, (tw, th), interpolation=cv2.INTER_CUBIC)
+        cv2.ipp.setUseIPP(True)
+    out["cv2_version"] = np.frombuffer(cv2.__version__.encode(), dtype=np.uint8)
+    out["ipp_version"] = np.frombuffer(str(cv2.ipp.getIppVersion()).encode(), dtype=np.uint8)
+    np.savez_compressed(OUT / "resize_cubic_ref.npz", **out)
+    print("resize_cubic_ref.npz", {k: v.shape for k, v in out.items() if k.endswith("_ipp")})
+
+
+def gen_dedup() -> None:
+    core = ref_import.dedup_core()
+    out = {}
+    for name, (m, d, tile, seed) in {"multi_tile": (700, 64, 256, 1), "default_tile": (4500, 16, 4096, 2), "tiny": (3, 16, 4096, 3)}.items():
+        rng = np.random.default_rng(seed)
+        e = rng.standard_normal((m, d)).astype(np.float32)
+        dup = rng.choice(m, size=max(1, m // 10), replace=False)
+        src = rng.choice(m, size=len(dup))
+        e[dup] = e[src] * rng.choice(np.array([1.0, 2.0, 0.5], dtype=np.float32), size=len(dup))[:, None]  # exact and scaled duplicates
+        near = rng.choice(m, size=max(1, m // 10), replace=False)
+        e[near] = e[rng.choice(m, size=len(near))] + np.float32(0.05) * rng.standard_normal((len(near), d)).astype(np.float32)
+        dist = rng.random(m).astype(np.float32)
+        dist[rng.choice(m, size=m // 5)] = np.float32(0.25)  # ties in the sort key: stable order matters
+        order = np.argsort(-dist, kind="stable")  # cudf sort_values(ascending=False) on ties: pinned separately (not in this section)
+        maxv, argi = core(e[order], tile)
+        out[name + "_emb"], out[name + "_dist"], out[name + "_tile"] = e, dist, np.array(tile)
+        out[name + "_maxv"], out[name + "_argi"] = maxv.astype(np.float32), argi.astype(np.int32)
+    np.savez_compressed(OUT / "dedup_ref.npz", **out)
+    print("dedup_ref.npz", {k: v.shape for k, v in out.items() if k.endswith("_maxv")})
+
+
 def main() -> None:
     assert ref_import.available(), "needs /root/reference (build container)"
     OUT.mkdir(parents=True, exist_ok=True)
@@ -290,6 +339,8 @@ def main() -> None:
     gen_aesthetic()
     gen_siglip()
     gen_transnet()
+    gen_resize_cubic()
+    gen_dedup()
 
 
 if __name__ == "__main__":

@@ -106,3 +106,25 @@ def transnetv2_stage_functions() -> dict:
     ns = {"np": np, "npt": npt, "torch": torch, "math": math, "Callable": Callable, "Generator": Generator, "Literal": Literal}
     exec(compile(ast.Module(body=body, type_ignores=[]), str(path), "exec"), ns)  # noqa: S102 - reference code, build container only
     return {k: ns[k] for k in wanted}
+
+
+def dedup_core():
+    """The array section of SemanticDedupActor.dedup (dedup_actor.py, from `norms = cp.linalg.norm(E ...` to `argi[0] = 0`)
+    executed from the reference's own source with numpy standing in for cupy (CuPy mirrors the numpy API for every call the
+    section makes: linalg.norm, maximum, full, clip, argmax, arange, where, asarray, tril_indices, max).  cudf / cuml / the GPU are
+    not needed for this part.  Returns fn(E float32 [m, d] sorted, tile) -> (maxv float32 [m], argi int32 [m])."""
+    import ast
+    import textwrap
+
+    import numpy as np
+
+    path = REFERENCE_ROOT / "cosmos_curate" / "pipelines" / "video" / "dedup" / "dedup_actor.py"
+    lines = path.read_text().splitlines()
+    start = next(i for i, ln in enumerate(lines) if ln.strip().startswith("norms = cp.linalg.norm(E, axis=1, keepdims=True)"))
+    end = next(i for i, ln in enumerate(lines) if i > start and ln.strip() == "argi[0] = 0")
+    block = textwrap.dedent("\n".join(lines[start : end + 1]))
+    ast.parse(block)  # must be a self-contained statement list
+    src = "def _core(E, TILE, cp):\n    m = E.shape[0]\n" + textwrap.indent(block, "    ") + "\n    return maxv, argi\n"
+    ns: dict = {}
+    exec(compile(src, str(path), "exec"), ns)  # noqa: S102 - reference code, build container only
+    return lambda E, tile=4096: ns["_core"](np.ascontiguousarray(E, dtype=np.float32).copy(), tile, np)

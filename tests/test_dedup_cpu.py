@@ -78,3 +78,36 @@ def test_product_module_imports_without_a_gpu():
     import cosmos_curate_b200.dedup as pd
 
     assert callable(pd.semdedup_cluster) and callable(pd.spherical_kmeans) and callable(pd.rowdot_argmax)
+
+
+def _check_against_reference_golden(name, g, got_maxv, got_arg_pos):
+    """got_* in the sorted order the reference works in; arg-max compared where the decision is not a float near-tie."""
+    maxv, argi = g[name + "_maxv"], g[name + "_argi"]
+    np.testing.assert_allclose(got_maxv, maxv, rtol=0, atol=3e-6)
+    e = od.l2_normalize(g[name + "_emb"][np.argsort(-g[name + "_dist"], kind="stable")])
+    argi0 = np.where(argi < 0, 0, argi)
+    differ = np.flatnonzero(got_arg_pos != argi0)
+    for j in differ:  # a different row may only be chosen if it is an equally good (within fp32 summation noise) earlier row
+        assert got_arg_pos[j] < j and abs(float(e[got_arg_pos[j]] @ e[j]) - float(e[argi0[j]] @ e[j])) < 3e-6, j
+    assert len(differ) <= max(1, len(maxv) // 200)
+
+
+@pytest.mark.parametrize("name", ["multi_tile", "default_tile", "tiny"])
+def test_oracle_pinned_to_reference_executed_dedup(name):
+    """oracle/dedup.pairwise_max against the reference's OWN dedup array code (dedup_actor.py:404-466, run from its source with
+    numpy standing in for cupy, oracle/ref_import.dedup_core -> tests/golden/dedup_ref.npz): start values, strict `>` across
+    tiles, first arg-max inside a tile, the tril mask of the diagonal tile, clip, the legacy row-0 convention."""
+    from conftest import load_golden
+
+    g = load_golden("dedup_ref.npz")
+    emb, dist = g[name + "_emb"], g[name + "_dist"]
+    ids = np.arange(len(emb))
+    r = od.pairwise_max(ids, emb, dist, eps=0.01)
+    order = np.argsort(-dist, kind="stable")
+    pos = {int(i): k for k, i in enumerate(order)}
+    got_arg = np.array([pos[int(i)] for i in r["max_id"]])
+    assert np.array_equal(r["id"], ids[order])
+    _check_against_reference_golden(name, g, r["cosine_sim_score"], got_arg)
+    thr = np.float32(0.99)
+    safe = np.abs(g[name + "_maxv"] - thr) > 1e-5
+    assert np.array_equal((r["cosine_sim_score"] <= thr)[safe], (g[name + "_maxv"] <= thr)[safe])

@@ -150,3 +150,31 @@ def test_kmeans_two_ranks_match_one_rank(ctx):  # noqa: F811
         cnt = torch.bincount(labels.long(), minlength=k).float()
         cent = torch.where(cnt[:, None] > 0, sums / cnt.clamp(min=1)[:, None], cent)
     np.testing.assert_allclose(np.load(out), cent.cpu().numpy(), atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["multi_tile", "default_tile", "tiny"])
+def test_semdedup_cluster_vs_reference_executed_golden(ctx, name):  # noqa: F811
+    """The CUDA path against outputs of the REFERENCE's own dedup array code (dedup_actor.py:404-466 executed from its source with
+    numpy standing in for cupy - tests/golden/dedup_ref.npz, oracle/ref_import.dedup_core)."""
+    from conftest import load_golden
+    from cosmos_curate_b200 import dedup
+    from oracle import dedup as od
+
+    g = load_golden("dedup_ref.npz")
+    emb, dist = g[name + "_emb"], g[name + "_dist"]
+    ids = np.arange(len(emb))
+    r = dedup.semdedup_cluster(ids, emb, dist, eps=0.01, ctx=ctx)
+    order = np.argsort(-dist, kind="stable")
+    assert np.array_equal(r["id"], ids[order])
+    np.testing.assert_allclose(r["cosine_sim_score"], g[name + "_maxv"], rtol=0, atol=3e-6)
+    pos = {int(i): k for k, i in enumerate(order)}
+    got = np.array([pos[int(i)] for i in r["max_id"]])
+    want = np.where(g[name + "_argi"] < 0, 0, g[name + "_argi"])
+    e = od.l2_normalize(emb[order])
+    differ = np.flatnonzero(got != want)
+    for j in differ:
+        assert got[j] < j and abs(float(e[got[j]] @ e[j]) - float(e[want[j]] @ e[j])) < 3e-6
+    assert len(differ) <= max(1, len(want) // 200)
+    thr = np.float32(0.99)
+    safe = np.abs(g[name + "_maxv"] - thr) > 1e-5
+    assert int((r["cosine_sim_score"][safe] <= thr).sum()) == int((g[name + "_maxv"][safe] <= thr).sum())

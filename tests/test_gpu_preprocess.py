@@ -120,3 +120,51 @@ def test_preprocess_edge_cases(ctx):
     _u8_budget(out[:1], preprocess.clip_resize_crop_u8(rgb, 224))
 
 
+
+
+# ------------------------------------------------------------------------------------ mode B: cv2 INTER_CUBIC target_res
+def test_resize_cubic_matches_cv2_goldens(ctx):
+    """cb_resize_cubic_u8 on RGB frames against cv2.resize(INTER_CUBIC) outputs generated by cv2 itself (extract_frames'
+    target_res, decoder_utils.py:666-670): CB_CUBIC_OPENCV bit-exact with OpenCV's own code, CB_CUBIC_IPP within 1 LSB on
+    < 1e-4 of the pixels of the x86 wheels' Intel IPP result."""
+    from conftest import load_golden
+    from cosmos_curate_b200 import _lib
+
+    g = load_golden("resize_cubic_ref.npz")
+    for name in sorted(k[:-3] for k in g.files if k.endswith("_in")):
+        img, (th, tw) = g[name + "_in"], (int(g[name + "_res"][0]), int(g[name + "_res"][1]))
+        pool = ctx.rgb_pool(torch.from_numpy(np.stack([img, img[::-1].copy()])).cuda())
+        got = ctx.resize_cubic_u8(pool, tw, th, mode=_lib.CUBIC_OPENCV).cpu().numpy()
+        assert got.shape == (2, th, tw, 3)
+        np.testing.assert_array_equal(got[0], g[name + "_opencv"], err_msg=name)
+        got_f = ctx.resize_cubic_u8(pool, tw, th, mode=_lib.CUBIC_IPP).cpu().numpy()
+        _u8_budget(got_f[0], g[name + "_ipp"], frac=1e-4)
+
+
+def test_resize_cubic_from_nv12_and_into_the_tower(ctx):
+    """NV12 surfaces (colour-converted per tap) -> 224x224 cubic -> CLIP transforms (Resize(224) is then the identity):
+    u8 frames bit-exact with the oracle chain, embeddings of the mode-B path within 1e-3 of the fp32 oracle."""
+    from cosmos_curate_b200 import _lib
+    from cosmos_curate_b200.runtime import VitTower
+    from oracle import resize_cubic as R
+
+    frames = [color.synthetic_nv12(1080, 1920, seed=80 + s) for s in range(3)]
+    pool = _nv12_pool(ctx, frames, 1920, 1080, 2048, 1088)
+    rgb = np.stack([color.nv12_to_rgb(f, 1080, 1920) for f in frames])
+    got = ctx.resize_cubic_u8(pool, 224, 224, mode=_lib.CUBIC_OPENCV).cpu().numpy()
+    want = np.stack([R.resize_cubic_u8(f, 224, 224) for f in rgb])
+    np.testing.assert_array_equal(got, want)
+    got_f = ctx.resize_cubic_u8(pool, 224, 224, mode=_lib.CUBIC_IPP)
+    want_f = np.stack([R.resize_cubic_real_u8(f, 224, 224) for f in rgb])
+    _u8_budget(got_f.cpu().numpy(), want_f, frac=1e-4)
+    # non-square target, odd source subset through slots
+    got2 = ctx.resize_cubic_u8(pool, 48, 27, slots=np.array([2, 0], dtype=np.int32), mode=_lib.CUBIC_OPENCV).cpu().numpy()
+    np.testing.assert_array_equal(got2[0], R.resize_cubic_u8(rgb[2], 27, 48))
+    np.testing.assert_array_equal(got2[1], R.resize_cubic_u8(rgb[0], 27, 48))
+    cfg = vit.CLIP_VIT_B32
+    w = vit.random_weights(cfg, seed=6)
+    tower = VitTower(ctx, cfg.to_dict(), w, max_batch=4)
+    emb, _, _ = tower.embed_pool(ctx.rgb_pool(got_f))
+    ref = vit.forward(cfg, w, preprocess.clip_preprocess(want_f))["embedding"]  # 224x224 input: torchvision Resize / CenterCrop are no-ops
+    rel = np.linalg.norm(emb.cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel.max() < 1e-3

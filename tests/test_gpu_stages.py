@@ -320,3 +320,40 @@ def test_fused_stage_is_deterministic_at_l14_shape(ctx):
         assert s0 == s1 and np.array_equal(e0, e1)
     assert len({s for s, _ in runs[0]}) == 1
     stage.destroy()
+
+
+def test_clip_frame_extraction_target_res_mode_b(ctx):
+    """ClipFrameExtractionStage(target_res=(224, 224)) - the reference benchmark's clip_extraction_target_res - returns the
+    cv2 INTER_CUBIC squares (decoder_utils.py:666-670) of the NVDEC frames, and the fused stage scores them like the pair does."""
+    from cosmos_curate_b200.interfaces import run_pipeline
+    from cosmos_curate_b200.runtime import Decoder, alloc_nv12_pool
+    from cosmos_curate_b200.stages import AestheticFilterStage, ClipFrameExtractionStage, NvdecClipAestheticStage
+    from oracle import color
+    from oracle import resize_cubic as R
+
+    data = (GOLDEN / "sintel_clip_10s.mp4").read_bytes()
+    ids = [0, 24, 48, 72, 96, 120, 144, 168, 192, 216, 239]
+    pool = alloc_nv12_pool(ctx, len(ids), 854, 480)
+    Decoder(ctx).decode(data, ids, pool, np.arange(len(ids)))
+    rgb = np.stack([color.nv12_to_rgb(np.ascontiguousarray(f[:, :854]), 480, 854) for f in pool.buf.cpu().numpy()])
+    for mode, fn in (("opencv", R.resize_cubic_u8), ("ipp", R.resize_cubic_real_u8)):
+        task = _clip_task(data)
+        st = ClipFrameExtractionStage(target_fps=[1], target_res=(224, 224), cubic_mode=mode)
+        st.stage_setup()
+        st.process_data([task])
+        frames = task.video.clips[0].extracted_frames.resolve()[SIG1]
+        assert frames.shape == (11, 224, 224, 3) and frames.dtype == np.uint8
+        want = np.stack([fn(f, 224, 224) for f in rgb])
+        if mode == "opencv":
+            np.testing.assert_array_equal(frames, want)
+        else:
+            d = np.abs(frames.astype(int) - want.astype(int))
+            assert d.max() <= 1 and (d > 0).mean() < 1e-4
+    model, cfg, w, sd = _model()
+    t_pair = _clip_task(data)
+    run_pipeline([t_pair], [ClipFrameExtractionStage(target_fps=[1], target_res=(224, 224)), AestheticFilterStage(score_threshold=-9.0, reduction="mean", model=model)])
+    t_fused = _clip_task(data)
+    run_pipeline([t_fused], [NvdecClipAestheticStage(score_threshold=-9.0, reduction="mean", target_res=(224, 224), num_decoders=2, max_batch=16, model=model)])
+    assert t_pair.video.clips[0].aesthetic_score == pytest.approx(t_fused.video.clips[0].aesthetic_score, abs=1e-6)
+    _, want_scores = _oracle_scores(cfg, w, sd, want)
+    assert t_fused.video.clips[0].aesthetic_score == pytest.approx(float(want_scores.mean()), abs=3e-3)

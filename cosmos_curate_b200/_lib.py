@@ -16,7 +16,7 @@ LIB_PATH = PKG / "libcurate_b200.so"
 CB_OK = 0
 CB_ERR = {-1: "CB_ERR_CUDA", -2: "CB_ERR_ARG", -3: "CB_ERR_UNSUPPORTED", -4: "CB_ERR_NVDEC", -5: "CB_ERR_DEMUX", -6: "CB_ERR_STATE"}
 ROWDOT_UPPER, ROWDOT_CLIP = 1, 2
-FMT_NV12, FMT_RGB24 = 0, 1
+FMT_NV12, FMT_RGB24, FMT_NV12_SWS = 0, 1, 2
 DT_F16, DT_BF16, DT_F32 = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_PATCH = 0, 1
 ACT_QUICK_GELU, ACT_GELU_TANH = 0, 1

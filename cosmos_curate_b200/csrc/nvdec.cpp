@@ -457,7 +457,7 @@ int cb_decoder_decode_ex(cb_decoder* d, const uint8_t* data, size_t size, const 
   cb_ctx* ctx = d->ctx;
   if (stats) memset(stats, 0, sizeof *stats);
   if (!data || n_ids < 0 || (n_ids > 0 && (!frame_ids || !dst_slots || !dst || !dst->base))) return cb::fail(ctx, CB_ERR_ARG, "decode: null argument");
-  if (dst && n_ids > 0 && dst->format != CB_FMT_NV12) return cb::fail(ctx, CB_ERR_ARG, "decode: destination pool must be NV12");
+  if (dst && n_ids > 0 && dst->format != CB_FMT_NV12 && dst->format != CB_FMT_NV12_SWS) return cb::fail(ctx, CB_ERR_ARG, "decode: destination pool must be NV12");
   for (int i = 1; i < n_ids; ++i)
     if (frame_ids[i] < frame_ids[i - 1]) return cb::fail(ctx, CB_ERR_ARG, "decode: frame ids must be ascending");
   if (n_ids > 0 && frame_ids[0] < 0) return cb::fail(ctx, CB_ERR_ARG, "decode: negative frame id");

@@ -35,6 +35,28 @@ __device__ __forceinline__ void yuv_to_rgb(int y, int u, int v, int& r, int& g, 
   b = min(max(b, 0), 255);
 }
 
+// libswscale's unscaled yuv420p -> rgb24 converter (x86 SIMD path, libswscale/x86/yuv_2_rgb.asm; coefficients from
+// ff_yuv2rgb_c_init_tables for ITU-R BT.601 limited range, the default PyAV / cv2 leave in place): 16-bit fixed point,
+// every product truncated by pmulhw - (8Y - 128) * 9539 >> 16 etc. - nearest chroma.  This is what the reference's CPU decode
+// (decode_video_cpu_frame_ids -> frame.to_ndarray(format="rgb24"), decoder_utils.py:439-451) feeds the CLIP transforms.
+// Pinned bit-exactly against cv2/libswscale over the whole u8 range (oracle/color.py, tests/test_oracle_cpu.py).
+__device__ __forceinline__ void yuv_to_rgb_sws(int y, int u, int v, int& r, int& g, int& b) {
+  const int yy = (((y << 3) - 128) * 9539) >> 16;
+  const int uu = (u << 3) - 1024, vv = (v << 3) - 1024;
+  r = yy + ((vv * 13075) >> 16);
+  g = yy + ((uu * -3209) >> 16) + ((vv * -6660) >> 16);
+  b = yy + ((uu * 16525) >> 16);
+  r = min(max(r, 0), 255);
+  g = min(max(g, 0), 255);
+  b = min(max(b, 0), 255);
+}
+template <int FMT>
+__device__ __forceinline__ void yuv_to_rgb_fmt(int y, int u, int v, int& r, int& g, int& b) {
+  if (FMT == CB_FMT_NV12_SWS) yuv_to_rgb_sws(y, u, v, r, g, b);
+  else yuv_to_rgb(y, u, v, r, g, b);
+}
+__host__ __device__ __forceinline__ constexpr bool is_nv12(int fmt) { return fmt == CB_FMT_NV12 || fmt == CB_FMT_NV12_SWS; }
+
 constexpr int kThreads = 256;
 constexpr int kSR = 32;  // source rows per strip (= lanes of a warp in the horizontal pass)
 
@@ -89,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) clip_preprocess_kernel(const __grid_
   const int slot = a.slots[frame];
 
   // ---- shared memory carve-up
-  const int raw_stage = (FMT == CB_FMT_NV12) ? (a.swa * kSR + a.swa * (kSR / 2)) : (3 * a.swa * kSR);
+  const int raw_stage = is_nv12(FMT) ? (a.swa * kSR + a.swa * (kSR / 2)) : (3 * a.swa * kSR);
   const int swp = a.swa + 1;  // odd pitch: lanes walk rows without bank conflicts
   const int tcp = a.tc | 1;
   uint8_t* raw = smem;                                                  // [2][raw_stage]
@@ -120,7 +142,7 @@ __global__ void __launch_bounds__(kThreads) clip_preprocess_kernel(const __grid_
     uint64_t* bar_ = &bars[s_ & 1];                                                                               \
     const int ys_ = a.y_begin + s_ * kSR;                                                                         \
     mbar_expect_tx(bar_, raw_stage);                                                                              \
-    if (FMT == CB_FMT_NV12) {                                                                                     \
+    if (is_nv12(FMT)) {                                                                                     \
       tma_load_3d(dst_, &map_a, bar_, x_lo, ys_, slot);                                                           \
       tma_load_3d(dst_ + a.swa * kSR, &map_b, bar_, x_lo, ys_ >> 1, slot);                                        \
     } else {                                                                                                      \
@@ -141,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) clip_preprocess_kernel(const __grid_
     mbar_wait(&bars[s & 1], (s >> 1) & 1);
 
     // ---- phase 1: colour convert the strip to planar fp32 RGB (values are exact u8 integers)
-    if (FMT == CB_FMT_NV12) {
+    if (is_nv12(FMT)) {
       const int half_w = a.swa >> 1;
       const uint8_t* ry = rs;
       const uint8_t* ruv = rs + a.swa * kSR;
@@ -151,9 +173,9 @@ __global__ void __launch_bounds__(kThreads) clip_preprocess_kernel(const __grid_
         const uchar2 uv = *(const uchar2*)(ruv + (r >> 1) * a.swa + x);
         int R, G, B;
         float* p = rgbf + r * swp + x;
-        yuv_to_rgb(yy.x, uv.x, uv.y, R, G, B);
+        yuv_to_rgb_fmt<FMT>(yy.x, uv.x, uv.y, R, G, B);
         p[0] = (float)R, p[kSR * swp] = (float)G, p[2 * kSR * swp] = (float)B;
-        yuv_to_rgb(yy.y, uv.x, uv.y, R, G, B);
+        yuv_to_rgb_fmt<FMT>(yy.y, uv.x, uv.y, R, G, B);
         p[1] = (float)R, p[kSR * swp + 1] = (float)G, p[2 * kSR * swp + 1] = (float)B;
       }
     } else {
@@ -250,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 2) clip_preprocess_v2_kernel(const _
   const int slot = a.slots[frame];
   const int ngroups = (ncol + 3) >> 2;
 
-  const int raw_stage = (FMT == CB_FMT_NV12) ? (a.swa * kSR + a.swa * (kSR / 2)) : (3 * a.swa * kSR);
+  const int raw_stage = is_nv12(FMT) ? (a.swa * kSR + a.swa * (kSR / 2)) : (3 * a.swa * kSR);
   const int swp = a.swa + 1;
   const int tcp = a.tc | 1;
   uint8_t* raw = smem;
@@ -297,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 2) clip_preprocess_v2_kernel(const _
     uint64_t* bar_ = &bars[s_ & 1];                                                                               \
     const int ys_ = a.y_begin + s_ * kSR;                                                                         \
     mbar_expect_tx(bar_, raw_stage);                                                                              \
-    if (FMT == CB_FMT_NV12) {                                                                                     \
+    if (is_nv12(FMT)) {                                                                                     \
       tma_load_3d(dst_, &map_a, bar_, x_lo, ys_, slot);                                                           \
       tma_load_3d(dst_ + a.swa * kSR, &map_b, bar_, x_lo, ys_ >> 1, slot);                                        \
     } else {                                                                                                      \
@@ -318,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 2) clip_preprocess_v2_kernel(const _
     mbar_wait(&bars[s & 1], (s >> 1) & 1);
 
     // ---- phase 1: colour conversion; one thread owns a 2-row x 4-pixel block (two chroma samples, three 32-bit loads)
-    if (FMT == CB_FMT_NV12) {
+    if (is_nv12(FMT)) {
       const int q4 = a.swa >> 2;
       const uint8_t* ry = rs;
       const uint8_t* ruv = rs + a.swa * kSR;
@@ -330,6 +352,23 @@ __global__ void __launch_bounds__(kThreads, 2) clip_preprocess_v2_kernel(const _
         float* p = rgbf + r * swp + x;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {  // the two chroma samples of the block
+          if (FMT == CB_FMT_NV12_SWS) {  // swscale arithmetic (see yuv_to_rgb_sws): truncating 16-bit products, clamp 0..255
+            const int uu = ((int)((uv4 >> (16 * h)) & 0xff) << 3) - 1024, vv = ((int)((uv4 >> (16 * h + 8)) & 0xff) << 3) - 1024;
+            const int ruv_ = (vv * 13075) >> 16, guv_ = ((uu * -3209) >> 16) + ((vv * -6660) >> 16), buv_ = (uu * 16525) >> 16;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              const uint32_t yw = rr ? yb : ya;
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int yv = ((((int)((yw >> (16 * h + 8 * k)) & 0xff) << 3) - 128) * 9539) >> 16;
+                float* q = p + rr * swp + 2 * h + k;
+                q[0] = (float)__viaddmin_s32_relu(yv, ruv_, 255);
+                q[kSR * swp] = (float)__viaddmin_s32_relu(yv, guv_, 255);
+                q[2 * kSR * swp] = (float)__viaddmin_s32_relu(yv, buv_, 255);
+              }
+            }
+            continue;
+          }
           const int u = (int)((uv4 >> (16 * h)) & 0xff) - 128, v = (int)((uv4 >> (16 * h + 8)) & 0xff) - 128;
           const int ruv_ = 1673527 * v, guv_ = -852492 * v - 409993 * u, buv_ = 2116026 * u;
 #pragma unroll
@@ -453,14 +492,15 @@ struct SimpleArgs {
   const uint8_t* base;
   size_t slot_stride;
   const int* slots;
-  int n, w, h, pitch, luma_rows, out_w, out_h;
+  int n, w, h, pitch, luma_rows, out_w, out_h, format;
   uint8_t* out;
 };
 
-__device__ __forceinline__ void fetch_rgb_nv12(const uint8_t* f, int pitch, int luma_rows, int x, int y, int& r, int& g, int& b) {
+__device__ __forceinline__ void fetch_rgb_nv12(const uint8_t* f, int pitch, int luma_rows, int x, int y, int& r, int& g, int& b, int format = CB_FMT_NV12) {
   const int Y = f[(size_t)y * pitch + x];
   const uint8_t* uv = f + (size_t)luma_rows * pitch + (size_t)(y >> 1) * pitch + (x & ~1);
-  yuv_to_rgb(Y, uv[0], uv[1], r, g, b);
+  if (format == CB_FMT_NV12_SWS) yuv_to_rgb_sws(Y, uv[0], uv[1], r, g, b);
+  else yuv_to_rgb(Y, uv[0], uv[1], r, g, b);
 }
 
 // cvcuda.resize_into(LINEAR) semantics: half-pixel centres, clamp-to-edge taps, fp32, round-to-nearest-even.
@@ -477,10 +517,10 @@ __global__ void bilinear_u8_kernel(const SimpleArgs a) {
   const int xa = min(max(x0, 0), a.w - 1), xb = min(max(x0 + 1, 0), a.w - 1);
   const int ya = min(max(y0, 0), a.h - 1), yb = min(max(y0 + 1, 0), a.h - 1);
   int p00[3], p01[3], p10[3], p11[3];
-  fetch_rgb_nv12(fr, a.pitch, a.luma_rows, xa, ya, p00[0], p00[1], p00[2]);
-  fetch_rgb_nv12(fr, a.pitch, a.luma_rows, xb, ya, p01[0], p01[1], p01[2]);
-  fetch_rgb_nv12(fr, a.pitch, a.luma_rows, xa, yb, p10[0], p10[1], p10[2]);
-  fetch_rgb_nv12(fr, a.pitch, a.luma_rows, xb, yb, p11[0], p11[1], p11[2]);
+  fetch_rgb_nv12(fr, a.pitch, a.luma_rows, xa, ya, p00[0], p00[1], p00[2], a.format);
+  fetch_rgb_nv12(fr, a.pitch, a.luma_rows, xb, ya, p01[0], p01[1], p01[2], a.format);
+  fetch_rgb_nv12(fr, a.pitch, a.luma_rows, xa, yb, p10[0], p10[1], p10[2], a.format);
+  fetch_rgb_nv12(fr, a.pitch, a.luma_rows, xb, yb, p11[0], p11[1], p11[2], a.format);
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     const float top = __fadd_rn(__fmul_rn((float)p00[ch], 1.f - wx), __fmul_rn((float)p01[ch], wx));
@@ -505,10 +545,13 @@ __global__ void nv12_to_rgb_kernel(const SimpleArgs a) {
   const int U = uv[0], V = uv[1];
   uint8_t* o = a.out + (((size_t)f * a.h + y) * a.w + x) * 3;
   int r, g, b;
-  yuv_to_rgb(fr[(size_t)y * a.pitch + x], U, V, r, g, b);
+  const bool sws = a.format == CB_FMT_NV12_SWS;
+  if (sws) yuv_to_rgb_sws(fr[(size_t)y * a.pitch + x], U, V, r, g, b);
+  else yuv_to_rgb(fr[(size_t)y * a.pitch + x], U, V, r, g, b);
   o[0] = r, o[1] = g, o[2] = b;
   if (x + 1 < a.w) {
-    yuv_to_rgb(fr[(size_t)y * a.pitch + x + 1], U, V, r, g, b);
+    if (sws) yuv_to_rgb_sws(fr[(size_t)y * a.pitch + x + 1], U, V, r, g, b);
+    else yuv_to_rgb(fr[(size_t)y * a.pitch + x + 1], U, V, r, g, b);
     o[3] = r, o[4] = g, o[5] = b;
   }
 }
@@ -553,8 +596,8 @@ __global__ void resize_cubic_kernel(const CubicArgs a) {
     for (int kx = 0; kx < 4; ++kx) {
       const int x = min(max(xs + kx, 0), a.w - 1);
       int r, g, b;
-      if (a.format == CB_FMT_NV12) {
-        fetch_rgb_nv12(fr, a.pitch, a.luma_rows, x, y, r, g, b);
+      if (is_nv12(a.format)) {
+        fetch_rgb_nv12(fr, a.pitch, a.luma_rows, x, y, r, g, b, a.format);
       } else {
         const uint8_t* px = fr + (size_t)y * a.pitch + 3 * x;
         r = px[0], g = px[1], b = px[2];
@@ -697,11 +740,11 @@ static int upload_slots(cb_ctx* ctx, const int32_t* slots, int n, cudaStream_t s
 static int check_pool(cb_ctx* ctx, const cb_surface_pool* pool, int n, const int32_t* slots) {
   if (!ctx) return CB_ERR_ARG;
   if (!pool || !pool->base || n < 0 || (n > 0 && !slots)) return fail(ctx, CB_ERR_ARG, "null pool/slots");
-  if (pool->format != CB_FMT_NV12 && pool->format != CB_FMT_RGB24) return fail(ctx, CB_ERR_ARG, "unknown surface format %d", pool->format);
+  if (!is_nv12(pool->format) && pool->format != CB_FMT_RGB24) return fail(ctx, CB_ERR_ARG, "unknown surface format %d", pool->format);
   if (pool->width <= 0 || pool->height <= 0) return fail(ctx, CB_ERR_ARG, "bad surface size %dx%d", pool->width, pool->height);
-  const int min_pitch = pool->format == CB_FMT_NV12 ? pool->width : 3 * pool->width;
+  const int min_pitch = is_nv12(pool->format) ? pool->width : 3 * pool->width;
   if (pool->pitch < min_pitch) return fail(ctx, CB_ERR_ARG, "pitch %d < row bytes %d", pool->pitch, min_pitch);
-  if (pool->format == CB_FMT_NV12 && pool->luma_rows < pool->height) return fail(ctx, CB_ERR_ARG, "luma_rows < height");
+  if (is_nv12(pool->format) && pool->luma_rows < pool->height) return fail(ctx, CB_ERR_ARG, "luma_rows < height");
   for (int i = 0; i < n; ++i)
     if (slots[i] < 0) return fail(ctx, CB_ERR_ARG, "negative slot index");
   return CB_OK;
@@ -716,7 +759,7 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
   if (res <= 0 || res > 1024) return fail(ctx, CB_ERR_ARG, "bad output resolution %d", res);
   if (((uintptr_t)pool->base & 15) || (pool->pitch & 15) || (pool->slot_stride & 15))
     return fail(ctx, CB_ERR_ARG, "TMA needs base/pitch/slot_stride multiples of 16 bytes");
-  if (pool->format == CB_FMT_NV12 && ((pool->width | pool->height) & 1)) return fail(ctx, CB_ERR_UNSUPPORTED, "NV12 needs even dimensions");
+  if (is_nv12(pool->format) && ((pool->width | pool->height) & 1)) return fail(ctx, CB_ERR_UNSUPPORTED, "NV12 needs even dimensions");
   const int W = pool->width, H = pool->height;
   // torchvision: short side -> res, long side -> int(res * long / short); centre crop res x res
   int new_w, new_h;
@@ -782,7 +825,7 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
   int max_slot = 0;
   for (int i = 0; i < n; ++i) max_slot = std::max(max_slot, (int)slots[i]);
   CUtensorMap map_a, map_b;
-  if (pool->format == CB_FMT_NV12) {
+  if (is_nv12(pool->format)) {
     uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)max_slot + 1};
     uint64_t strides[2] = {(uint64_t)pool->pitch, (uint64_t)pool->slot_stride};
     uint32_t box[3] = {(uint32_t)a.swa, (uint32_t)kSR, 1};
@@ -802,28 +845,28 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
     map_b = map_a;
   }
 
-  const int raw_stage = (pool->format == CB_FMT_NV12) ? (a.swa * kSR * 3 / 2) : (3 * a.swa * kSR);
+  const int raw_stage = is_nv12(pool->format) ? (a.swa * kSR * 3 / 2) : (3 * a.swa * kSR);
   const int npx = out_mode == 2 ? a.tc / a.patch : 0;
   size_t smem = 2 * (size_t)raw_stage + (size_t)3 * kSR * (a.swa + 1) * 4 + (size_t)3 * a.ring * (a.tc | 1) * 4 + (size_t)npx * k_pad * 2 + 32;
   if (use_v2) smem += 48 + (size_t)((a.tc + 3) / 4) * a.gu * 16 + (size_t)2 * ((a.tc + 3) / 4) * 4;
   if (smem > 227 * 1024) return fail(ctx, CB_ERR_UNSUPPORTED, "preprocess tile needs %zu bytes of shared memory", smem);
   dim3 grid(tiles, n);
   mark_launch(ctx, CB_PROF_PREPROCESS, stream);
+#define CB_LAUNCH_PRE(KERNEL, F)                                                                                         \
+  do {                                                                                                                  \
+    CB_CUDA(ctx, cudaFuncSetAttribute(KERNEL<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+    KERNEL<F><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);                                                        \
+  } while (0)
   if (use_v2) {
-    if (pool->format == CB_FMT_NV12) {
-      CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_v2_kernel<CB_FMT_NV12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      clip_preprocess_v2_kernel<CB_FMT_NV12><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
-    } else {
-      CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_v2_kernel<CB_FMT_RGB24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      clip_preprocess_v2_kernel<CB_FMT_RGB24><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
-    }
-  } else if (pool->format == CB_FMT_NV12) {
-    CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_kernel<CB_FMT_NV12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    clip_preprocess_kernel<CB_FMT_NV12><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
+    if (pool->format == CB_FMT_NV12) CB_LAUNCH_PRE(clip_preprocess_v2_kernel, CB_FMT_NV12);
+    else if (pool->format == CB_FMT_NV12_SWS) CB_LAUNCH_PRE(clip_preprocess_v2_kernel, CB_FMT_NV12_SWS);
+    else CB_LAUNCH_PRE(clip_preprocess_v2_kernel, CB_FMT_RGB24);
   } else {
-    CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_kernel<CB_FMT_RGB24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    clip_preprocess_kernel<CB_FMT_RGB24><<<grid, kThreads, smem, stream>>>(map_a, map_b, a);
+    if (pool->format == CB_FMT_NV12) CB_LAUNCH_PRE(clip_preprocess_kernel, CB_FMT_NV12);
+    else if (pool->format == CB_FMT_NV12_SWS) CB_LAUNCH_PRE(clip_preprocess_kernel, CB_FMT_NV12_SWS);
+    else CB_LAUNCH_PRE(clip_preprocess_kernel, CB_FMT_RGB24);
   }
+#undef CB_LAUNCH_PRE
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }
@@ -834,11 +877,11 @@ static int run_simple(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* s
   if (rc) return rc;
   if (n == 0) return CB_OK;
   if (!out) return fail(ctx, CB_ERR_ARG, "null output");
-  if (pool->format != CB_FMT_NV12) return fail(ctx, CB_ERR_UNSUPPORTED, "NV12 surfaces only");
+  if (!is_nv12(pool->format)) return fail(ctx, CB_ERR_UNSUPPORTED, "NV12 surfaces only");
   SimpleArgs a{};
   a.base = (const uint8_t*)pool->base, a.slot_stride = pool->slot_stride;
   a.n = n, a.w = pool->width, a.h = pool->height, a.pitch = pool->pitch, a.luma_rows = pool->luma_rows;
-  a.out_w = out_w, a.out_h = out_h, a.out = out;
+  a.out_w = out_w, a.out_h = out_h, a.out = out, a.format = pool->format;
   rc = upload_slots(ctx, slots, n, stream, &a.slots);
   if (rc) return rc;
   if (bilinear && (out_w <= 0 || out_h <= 0)) return fail(ctx, CB_ERR_ARG, "bad output size");
@@ -903,7 +946,7 @@ static int run_resize_cubic(cb_ctx* ctx, const cb_surface_pool* pool, const int3
   if (!out) return fail(ctx, CB_ERR_ARG, "null output");
   if (out_w <= 0 || out_h <= 0 || out_w > 8192 || out_h > 8192) return fail(ctx, CB_ERR_ARG, "bad output size %dx%d", out_w, out_h);
   if (mode != CB_CUBIC_OPENCV && mode != CB_CUBIC_IPP) return fail(ctx, CB_ERR_ARG, "unknown cubic mode %d", mode);
-  if (pool->format == CB_FMT_NV12 && ((pool->width | pool->height) & 1)) return fail(ctx, CB_ERR_UNSUPPORTED, "NV12 needs even dimensions");
+  if (is_nv12(pool->format) && ((pool->width | pool->height) & 1)) return fail(ctx, CB_ERR_UNSUPPORTED, "NV12 needs even dimensions");
   const CubicTaps* tx = get_cubic_taps(ctx, pool->width, out_w);
   const CubicTaps* ty = get_cubic_taps(ctx, pool->height, out_h);
   if (!tx || !ty) return fail(ctx, CB_ERR_CUDA, "cubic tap table allocation failed");
@@ -926,7 +969,7 @@ int bilinear_from_surface(cb_ctx* ctx, const void* base, int pitch, int luma_row
                           cudaStream_t stream) {
   SimpleArgs a{};
   a.base = (const uint8_t*)base, a.slot_stride = 0, a.slots = nullptr;
-  a.n = 1, a.w = w, a.h = h, a.pitch = pitch, a.luma_rows = luma_rows, a.out_w = out_w, a.out_h = out_h, a.out = out;
+  a.n = 1, a.w = w, a.h = h, a.pitch = pitch, a.luma_rows = luma_rows, a.out_w = out_w, a.out_h = out_h, a.out = out, a.format = CB_FMT_NV12;
   mark_launch(ctx, CB_PROF_PREPROCESS, stream);
   bilinear_u8_kernel<<<(out_w * out_h + 255) / 256, 256, 0, stream>>>(a);
   CB_CUDA(ctx, cudaGetLastError());

@@ -77,12 +77,14 @@ class Context:
         return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
 
     # ---- surfaces -----------------------------------------------------------------------------
-    def nv12_pool(self, buf: torch.Tensor, width: int, height: int, luma_rows: int | None = None) -> "Pool":
-        """buf: uint8 cuda [slots, rows, pitch] with rows >= luma_rows + height/2."""
+    def nv12_pool(self, buf: torch.Tensor, width: int, height: int, luma_rows: int | None = None, colour: str = "opencv") -> "Pool":
+        """buf: uint8 cuda [slots, rows, pitch] with rows >= luma_rows + height/2.  colour: "opencv" (CV-CUDA / cv2.cvtColor
+        semantics, the reference's CUDA branch) or "swscale" (libswscale's yuv420p -> rgb24, the reference's CPU decode branch)."""
         assert buf.is_cuda and buf.dtype == torch.uint8 and buf.dim() == 3 and buf.is_contiguous()
         luma_rows = height if luma_rows is None else luma_rows
         assert buf.shape[1] >= luma_rows + height // 2
-        return Pool(buf, SurfacePool(buf.data_ptr(), buf.shape[1] * buf.shape[2], width, height, buf.shape[2], luma_rows, _lib.FMT_NV12))
+        fmt = {"opencv": _lib.FMT_NV12, "swscale": _lib.FMT_NV12_SWS}[colour]
+        return Pool(buf, SurfacePool(buf.data_ptr(), buf.shape[1] * buf.shape[2], width, height, buf.shape[2], luma_rows, fmt))
 
     def rgb_pool(self, frames: torch.Tensor) -> "Pool":
         """frames: uint8 cuda [n, H, W, 3] (contiguous).  Rows are re-pitched to a 16-byte multiple if needed."""
@@ -395,12 +397,12 @@ def decode_thumbnails(dec: Decoder, data, out_w: int, out_h: int, n_frames: int)
     return out[: st.frames_emitted]
 
 
-def alloc_nv12_pool(ctx: Context, slots: int, width: int, height: int) -> Pool:
-    """Device NV12 surface pool for `slots` frames of width x height (pitch aligned to 256 bytes)."""
+def alloc_nv12_pool(ctx: Context, slots: int, width: int, height: int, colour: str = "opencv") -> Pool:
+    """Device NV12 surface pool for `slots` frames of width x height (pitch aligned to 256 bytes); `colour` as Context.nv12_pool."""
     w2, h2 = (width + 1) & ~1, (height + 1) & ~1
     pitch = (w2 + 255) // 256 * 256
     buf = torch.empty((slots, h2 + h2 // 2, pitch), dtype=torch.uint8, device=f"cuda:{ctx.device}")
-    return ctx.nv12_pool(buf, w2, h2, h2)
+    return ctx.nv12_pool(buf, w2, h2, h2, colour)
 
 
 # ---- host placement + persistent NVDEC sessions ---------------------------------------------------------

@@ -50,8 +50,15 @@ class ClipFrameExtractionStage(CuratorStage):
         verbose: bool = False,
         log_stats: bool = False,
         cubic_mode: str | None = None,
+        colour: str = "swscale",
     ) -> None:
         self._timer = StageTimer(self)
+        # "swscale": RGB frames bit-identical to the reference stage's (PyAV frame.to_ndarray("rgb24") = libswscale's yuv420p
+        # -> rgb24, decoder_utils.py:439-451); "opencv": CV-CUDA / cv2.cvtColor semantics (the reference's nvcodec_utils branch)
+        if colour not in ("swscale", "opencv"):
+            msg = f"colour={colour!r} not in ('swscale', 'opencv')"
+            raise ValueError(msg)
+        self._colour = colour
         self._extraction_policies = extraction_policies
         self._target_fps = [2] if target_fps is None else target_fps
         self._target_res = (-1, -1) if target_res is None else target_res
@@ -91,7 +98,7 @@ class ClipFrameExtractionStage(CuratorStage):
             pool = None  # drop the smaller pool before allocating its replacement
             while len(self._pools) >= self.MAX_POOLS:
                 self._pools.pop(next(iter(self._pools)))
-            pool = alloc_nv12_pool(self._ctx, cap, width, height)
+            pool = alloc_nv12_pool(self._ctx, cap, width, height, self._colour)
         self._pools[key] = pool  # most recently used last
         return pool
 

@@ -55,6 +55,7 @@ class NvdecClipAestheticStage(CuratorStage):
         source: Literal["clip", "video_span"] = "clip",
         target_res: tuple[int, int] | None = None,
         cubic_mode: str | None = None,
+        colour: str = "swscale",
         verbose: bool = False,
         log_stats: bool = False,
         model: CLIPAestheticScorer | None = None,
@@ -72,6 +73,12 @@ class NvdecClipAestheticStage(CuratorStage):
         # video (video.encoded_data) at clip.span, so ClipTranscodingStage's re-encode + this stage's re-decode disappear for runs
         # that only need scores / embeddings.  Pixels are the source's, not the 4 Mb/s re-encode's: not bit-comparable with "clip".
         self._source = source
+        # colour conversion of the decoded NV12 surfaces inside the fused kernel: "swscale" = bit-identical to the RGB frames the
+        # reference's CPU decode hands to CLIP (libswscale yuv420p -> rgb24, decoder_utils.py:439-451), "opencv" = CV-CUDA semantics
+        if colour not in ("swscale", "opencv"):
+            error_msg = f"colour={colour!r} not in ('swscale', 'opencv')"
+            raise ValueError(error_msg)
+        self._colour = colour
         # clip_extraction_target_res of the reference pipeline (splitting_pipeline -> ClipFrameExtractionStage(target_res=(r, r))):
         # frames are squashed to (h, w) with cv2 INTER_CUBIC before the CLIP transforms (decoder_utils.py:666-670).  None / (-1, -1)
         # = native resolution into the antialiased short-side resize (the reference default).
@@ -174,7 +181,7 @@ class NvdecClipAestheticStage(CuratorStage):
             self._pools.pop(size)
         self._pools[size] = ring  # most recently used last
         if ring[r] is None:
-            ring[r] = alloc_nv12_pool(self._ctx, self._max_batch, size[0], size[1])
+            ring[r] = alloc_nv12_pool(self._ctx, self._max_batch, size[0], size[1], self._colour)
         return ring[r]
 
     def _host_buffers(self, r: int):

@@ -66,6 +66,11 @@ int cb_profile_end(cb_ctx* ctx, void* stream, float* ms_by_category, int* launch
 /* ---- surfaces ----------------------------------------------------------------------------------- */
 #define CB_FMT_NV12 0  /* Y plane [luma_rows x pitch] then interleaved UV plane [height/2 x pitch] */
 #define CB_FMT_RGB24 1 /* interleaved RGB u8, pitch >= 3*width */
+/* NV12 surfaces (same layout as CB_FMT_NV12) whose colour conversion follows libswscale's unscaled yuv420p -> rgb24 converter
+ * bit for bit - what the reference's CPU decode hands to CLIP (frame.to_ndarray(format="rgb24"), decoder_utils.py:439-451).
+ * CB_FMT_NV12 converts with OpenCV / CV-CUDA semantics (cvcuda.cvtcolor_into, nvcodec_utils.py:35-38,178), the reference's
+ * CUDA branch (27x48 shot-detection frames).  Both: ITU-R BT.601 limited range, nearest chroma. */
+#define CB_FMT_NV12_SWS 2
 
 /* A pool of equally shaped frames in device memory: frame i starts at base + i*slot_stride.
  * NV12: UV plane of a frame starts `luma_rows * pitch` bytes after its Y plane (NVDEC aligns the coded

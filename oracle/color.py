@@ -11,6 +11,16 @@ the 2x2 luma block (no interpolation), result clamped to u8.  tests/test_oracle_
 this bit-exactly against cv2.cvtColor on random surfaces; parity against CV-CUDA itself is
 UNPINNED (stated in DESIGN.md).
 
+nv12_to_rgb_swscale restates what the reference's CPU decode path - the one that feeds CLIP - does with every decoded
+frame: ``frame.to_ndarray(format="rgb24")`` (decoder_utils.py:439-451) = libswscale's unscaled yuv420p -> rgb24 converter
+(third-party: FFmpeg libswscale, conda-forge build pinned by pixi.lock; cv2 bundles libswscale 9.1 here).  Restated from
+libswscale's published code (yuv2rgb.c ff_yuv2rgb_c_init_tables for the coefficients, x86/yuv_2_rgb.asm for the arithmetic):
+ITU-R BT.601 limited range whatever the stream says (neither PyAV nor cv2 calls sws_setColorspaceDetails), chroma replicated
+to the 2x2 block, 16-bit fixed point with every product TRUNCATED (pmulhw): y' = ((8Y - 128) * 9539) >> 16, r = y' +
+((8V - 1024) * 13075 >> 16), ... clamp.  Pinned bit-exactly against cv2.VideoCapture's BGR output over the whole u8 range
+(tests/test_oracle_cpu.py decodes lossless I_PCM pictures of known YUV).  aarch64 builds use a NEON converter with other
+rounding: this restates the x86 path the reference's deployment runs.
+
 rgb_to_nv12 is only a generator of plausible synthetic surfaces for tests/bench (not on the
 reference path).
 
@@ -40,6 +50,26 @@ def nv12_to_rgb(nv12: np.ndarray, height: int, width: int) -> np.ndarray:
     r = (yy + half + CVR * v) >> SHIFT
     g = (yy + half + CVG * v + CUG * u) >> SHIFT
     b = (yy + half + CUB * u) >> SHIFT
+    return np.clip(np.stack([r, g, b], axis=-1), 0, 255).astype(np.uint8)
+
+
+# libswscale ff_yuv2rgb_c_init_tables, ITU601 (SWS_CS_DEFAULT), limited range, brightness 0 / contrast 1 / saturation 1:
+# roundToInt16(c * 2^13): cy = 65536 * 255 / 219, crv = 104597, cbu = 132201, cgu = -25675, cgv = -53279
+SWS_Y, SWS_VR, SWS_UB, SWS_VG, SWS_UG, SWS_YOFF, SWS_COFF = 9539, 13075, 16525, -6660, -3209, 128, 1024
+
+
+def nv12_to_rgb_swscale(nv12: np.ndarray, height: int, width: int) -> np.ndarray:
+    """Same layout contract as nv12_to_rgb; libswscale (x86) yuv420p -> rgb24 arithmetic."""
+    assert nv12.dtype == np.uint8 and nv12.shape[0] >= height * 3 // 2
+    y = nv12[:height, :width].astype(np.int64)
+    uv = nv12[height : height + height // 2, :width]
+    u = np.repeat(np.repeat(uv[:, 0::2].astype(np.int64), 2, axis=0), 2, axis=1)[:height, :width]
+    v = np.repeat(np.repeat(uv[:, 1::2].astype(np.int64), 2, axis=0), 2, axis=1)[:height, :width]
+    yy = (((y << 3) - SWS_YOFF) * SWS_Y) >> 16  # numpy >> on negative ints floors, like pmulhw
+    uu, vv = (u << 3) - SWS_COFF, (v << 3) - SWS_COFF
+    r = yy + ((vv * SWS_VR) >> 16)
+    g = yy + ((uu * SWS_UG) >> 16) + ((vv * SWS_VG) >> 16)
+    b = yy + ((uu * SWS_UB) >> 16)
     return np.clip(np.stack([r, g, b], axis=-1), 0, 255).astype(np.uint8)
 
 

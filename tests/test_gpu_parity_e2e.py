@@ -2,8 +2,9 @@
 
 * swscale RGB (what the reference feeds CLIP: PyAV `to_ndarray("rgb24")`, decoder_utils.py:439-451; cv2/libavcodec+swscale
   is the stand-in, PyAV is not installable here) -> fp32 oracle embeddings, against NVDEC -> fused NV12 kernel -> fp16 tower,
-  on CLIP ViT-L/14.  The two decoders agree bit-exactly on luma; the colour conversions differ (OpenCV/CV-CUDA fixed point with
-  nearest chroma on our side - the reference's own CUDA semantics, nvcodec_utils.py:178 - versus swscale on the CPU side).
+  on CLIP ViT-L/14.  Round 1 converted with OpenCV / CV-CUDA semantics and claimed the difference to swscale was "absorbed by the
+  1e-3 tolerance"; measured here it is NOT (1.2e-2 on the dark title frames), so the fused kernel now has libswscale's own
+  arithmetic (CB_FMT_NV12_SWS) and the stages default to it: the RGB is byte-identical, the embeddings within 1e-3.
 * batch invariance at the bench shape: 264 frames through the 2-CTA GEMM + attention_tc2 + chunking vs the same frames at n=3.
 * activation outliers: real CLIP-L/14 has a few residual-stream channels two orders of magnitude above the rest; seeded
   Gaussian weights do not.  A stress configuration plants such channels and checks the fp16 qkv / mlp activations survive.
@@ -67,26 +68,28 @@ def test_real_input_path_embeddings_swscale_vs_nvdec_l14(ctx):
     tower = VitTower(ctx, cfg.to_dict(), w, max_batch=16, aesthetic=(aw, ab))
     # (b) our tower on the SAME swscale RGB frames: isolates fp16-tower + resize error from the colour path
     emb_b, _, score_b = tower.embed_pool(ctx.rgb_pool(torch.from_numpy(rgb_sws).cuda()))
-    # (c) the product path: NVDEC surfaces -> fused NV12 preprocess -> tower
-    pool = alloc_nv12_pool(ctx, len(SINTEL_IDS), 854, 480)
+    # (c) the product path: NVDEC surfaces -> fused NV12 kernel with libswscale's colour arithmetic -> tower
+    pool = alloc_nv12_pool(ctx, len(SINTEL_IDS), 854, 480, colour="swscale")
     Decoder(ctx).decode(path.read_bytes(), SINTEL_IDS, pool, np.arange(len(SINTEL_IDS)))
+    rgb_gpu = ctx.nv12_to_rgb(pool).cpu().numpy()
+    assert np.array_equal(rgb_gpu, rgb_sws)  # NVDEC + our conversion == libavcodec + libswscale, every byte of every sampled frame
     emb_c, _, score_c = tower.embed_pool(pool)
-    # (d) fp32 oracle on OUR colour conversion: what remains of (c) - (a) once tower precision is taken out
-    nv12 = pool.buf.cpu().numpy()
-    rgb_cv = np.stack([color.nv12_to_rgb(np.ascontiguousarray(f[:, :854]), 480, 854) for f in nv12])
-    ref_d = vit.forward(cfg, w, preprocess.clip_preprocess(rgb_cv))
+    # (d) for the record: the same surfaces through the OpenCV / CV-CUDA conversion (the reference's nvcodec_utils branch)
+    pool_cv = ctx.nv12_pool(pool.buf, 854, 480, 480, colour="opencv")
+    emb_d, _, _ = tower.embed_pool(pool_cv)
+    rgb_cv = ctx.nv12_to_rgb(pool_cv).cpu().numpy()
 
     rel_b = _rel_rows(emb_b.cpu().numpy(), ref["embedding"])
     rel_c = _rel_rows(emb_c.cpu().numpy(), ref["embedding"])
-    rel_colour = _rel_rows(ref_d["embedding"], ref["embedding"])
+    rel_d = _rel_rows(emb_d.cpu().numpy(), ref["embedding"])
     px = np.abs(rgb_cv.astype(int) - rgb_sws.astype(int))
-    print(f"\n[real-input parity, ViT-L/14 seeded] pixels: mean |d| {px.mean():.3f} max {px.max()} | embedding rel err: tower-only(b) max {rel_b.max():.2e}, "
-          f"colour-only(fp32 oracle) max {rel_colour.max():.2e}, product path(c) max {rel_c.max():.2e} mean {rel_c.mean():.2e} | "
-          f"score |d| max {np.abs(score_c.cpu().numpy() - ref_score).max():.2e}")  # fmt: skip
+    print(f"\n[real-input parity, ViT-L/14 seeded] embedding rel err vs fp32 oracle on swscale RGB: tower on uploaded RGB max {rel_b.max():.2e}, "
+          f"product path (NVDEC + swscale-exact fused kernel) max {rel_c.max():.2e} mean {rel_c.mean():.2e}, score |d| max "
+          f"{np.abs(score_c.cpu().numpy() - ref_score).max():.2e} | with the OpenCV/CV-CUDA colour instead: pixels mean |d| {px.mean():.3f} max {px.max()}, "
+          f"embedding rel err max {rel_d.max():.2e} (dark title frames dominate)")  # fmt: skip
     assert rel_b.max() < 1e-3  # BASELINE.json: fp embeddings within 1e-3 relative, same input frames
-    # The product path adds the colour-conversion difference between the reference's CPU (swscale) and CUDA (CV-CUDA/OpenCV
-    # semantics, ours) decode branches; it must stay inside the same budget for the drop-in claim to hold on the CPU-decoded branch.
-    assert rel_c.max() < 1e-3, (rel_c, rel_colour)
+    assert rel_c.max() < 1e-3  # ... and on the product path from the compressed clip
+    assert _rel_rows(emb_c.cpu().numpy(), emb_b.cpu().numpy()).max() < 1e-5  # identical pixels in, same embeddings out, whichever way the RGB got there
     np.testing.assert_allclose(score_c.cpu().numpy(), ref_score, atol=2e-3)  # the reference's own test tolerance
 
 

@@ -118,7 +118,7 @@ def test_fused_nvdec_stage_matches_oracle_and_error_convention(ctx):
         pool = alloc_nv12_pool(ctx, len(ids), wd, h)
         dec.decode(data, ids, pool, np.arange(len(ids)))
         nv12 = pool.buf.cpu().numpy()
-        rgb = np.stack([color.nv12_to_rgb(np.ascontiguousarray(f[:, :wd]), h, wd) for f in nv12])
+        rgb = np.stack([color.nv12_to_rgb_swscale(np.ascontiguousarray(f[:, :wd]), h, wd) for f in nv12])  # the stages convert like the reference CPU decode
         emb, scores = _oracle_scores(cfg, w, sd, rgb)
         assert clip.aesthetic_score == pytest.approx(float(scores.min()), abs=3e-3)
         m = emb.mean(axis=0)
@@ -159,7 +159,7 @@ def test_fused_stage_on_source_video_spans(ctx):
         ids = sampling.span_frame_ids(ts, clip.span, 1.0)
         pool = alloc_nv12_pool(ctx, len(ids), 854, 480)
         dec.decode(sintel, ids, pool, np.arange(len(ids)))
-        rgb = np.stack([color.nv12_to_rgb(np.ascontiguousarray(f[:, :854]), 480, 854) for f in pool.buf.cpu().numpy()])
+        rgb = np.stack([color.nv12_to_rgb_swscale(np.ascontiguousarray(f[:, :854]), 480, 854) for f in pool.buf.cpu().numpy()])
         _, scores = _oracle_scores(cfg, w, sd, rgb)
         assert clip.aesthetic_score == pytest.approx(float(scores.mean()), abs=3e-3)
 
@@ -335,7 +335,7 @@ def test_clip_frame_extraction_target_res_mode_b(ctx):
     ids = [0, 24, 48, 72, 96, 120, 144, 168, 192, 216, 239]
     pool = alloc_nv12_pool(ctx, len(ids), 854, 480)
     Decoder(ctx).decode(data, ids, pool, np.arange(len(ids)))
-    rgb = np.stack([color.nv12_to_rgb(np.ascontiguousarray(f[:, :854]), 480, 854) for f in pool.buf.cpu().numpy()])
+    rgb = np.stack([color.nv12_to_rgb_swscale(np.ascontiguousarray(f[:, :854]), 480, 854) for f in pool.buf.cpu().numpy()])
     for mode, fn in (("opencv", R.resize_cubic_u8), ("ipp", R.resize_cubic_real_u8)):
         task = _clip_task(data)
         st = ClipFrameExtractionStage(target_fps=[1], target_res=(224, 224), cubic_mode=mode)

@@ -275,7 +275,7 @@ def run_b200(args) -> None:
         return float(t.item())
 
     # ---- resident-input measurement (value): decoded surfaces of one step already in HBM
-    pool0 = alloc_nv12_pool(ctx, frames_per_step, FRAME_W, FRAME_H)
+    pool0 = alloc_nv12_pool(ctx, frames_per_step, FRAME_W, FRAME_H, colour="swscale")  # the conversion the product stage uses
     dp = stage._decode_pool
     futs = [dp.submit(lambda dec, j=j: dec.decode(clips[j % len(clips)], plans[j % len(clips)], pool0, np.arange(j * fpc, (j + 1) * fpc, dtype=np.int32))) for j in range(cps)]
     for f in futs:

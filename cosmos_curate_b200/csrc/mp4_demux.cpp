@@ -3,6 +3,9 @@
 // (clip_frame_extraction_stages.py:160-165).
 #include "mp4_demux.h"
 
+#include <climits>
+#include <cstdint>
+
 #include <string.h>
 
 #include <algorithm>
@@ -134,6 +137,8 @@ std::string parse_trak(const Reader& r, const Box& trak, uint32_t movie_timescal
   // ---- stsd: first sample entry
   Box stsd;
   if (!find_box(r, stbl.body, stbl.end, fourcc("stsd"), &stsd) || stsd.end - stsd.body < 16) return "no stsd";
+  t->stsd_off = stsd.body - 8, t->stsd_size = stsd.end - (stsd.body - 8);
+  if (r.u32(stsd.body - 8) == 1) return "64-bit stsd box";  // never written by any muxer; keeps the verbatim copy simple
   {
     const size_t e = stsd.body + 8;  // first entry: size, format
     const uint32_t esz = r.u32(e), fmt = r.u32(e + 4);
@@ -318,6 +323,156 @@ std::string mp4_parse(const uint8_t* data, size_t size, Mp4Track* out) {
     return false;  // first video track only (stream_idx 0 in the reference)
   });
   return done ? "" : err;
+}
+
+namespace {
+
+struct Out {
+  std::vector<uint8_t>* v;
+  void u8(uint32_t x) { v->push_back((uint8_t)x); }
+  void u16(uint32_t x) { u8(x >> 8), u8(x); }
+  void u32(uint32_t x) { u16(x >> 16), u16(x); }
+  void u64(uint64_t x) { u32((uint32_t)(x >> 32)), u32((uint32_t)x); }
+  void zeros(size_t n) { v->insert(v->end(), n, 0); }
+  void bytes(const uint8_t* p, size_t n) { v->insert(v->end(), p, p + n); }
+  size_t begin(const char* type, int full_version = -1, uint32_t flags = 0) {  // returns the box start for end()
+    const size_t at = v->size();
+    u32(0);
+    bytes((const uint8_t*)type, 4);
+    if (full_version >= 0) u32(((uint32_t)full_version << 24) | flags);
+    return at;
+  }
+  void end(size_t at) {
+    const uint32_t n = (uint32_t)(v->size() - at);
+    (*v)[at] = n >> 24, (*v)[at + 1] = n >> 16, (*v)[at + 2] = n >> 8, (*v)[at + 3] = n;
+  }
+};
+
+}  // namespace
+
+std::string mp4_cut(const uint8_t* data, size_t size, const Mp4Track& t, size_t first, size_t count, std::vector<uint8_t>* out) {
+  const size_t n = t.size.size();
+  if (count == 0 || first >= n || count > n - first) return "cut range outside the track";
+  if (!t.sync[first]) return "a stream-copied clip must start on a sync sample";
+  if (t.stsd_size < 16 || t.stsd_off + t.stsd_size > size) return "no sample description to copy";
+  std::vector<int64_t> delta(count), cts(count);
+  bool any_cts = false, neg_cts = false;
+  int64_t min_pts = INT64_MAX, max_end = 0;
+  for (size_t i = 0; i < count; ++i) {
+    const size_t s = first + i;
+    delta[i] = s + 1 < n ? t.dts[s + 1] - t.dts[s] : (i > 0 ? delta[i - 1] : 1);
+    if (delta[i] <= 0) return "non-increasing decode timestamps";
+    cts[i] = t.pts[s] - t.dts[s];
+    any_cts |= cts[i] != 0, neg_cts |= cts[i] < 0;
+    const int64_t p = (t.dts[s] - t.dts[first]) + cts[i];
+    min_pts = std::min(min_pts, p), max_end = std::max(max_end, p + delta[i]);
+  }
+  int64_t media_dur = 0;
+  uint64_t payload = 0;
+  for (size_t i = 0; i < count; ++i) media_dur += delta[i], payload += t.size[first + i];
+  const uint32_t movie_ts = 1000;
+  const uint64_t pres_dur = (uint64_t)(max_end - min_pts);
+  const uint64_t movie_dur = pres_dur * movie_ts / t.timescale;
+
+  out->clear();
+  out->reserve((size_t)payload + 1024 + 16 * count);
+  Out o{out};
+  size_t b = o.begin("ftyp");
+  o.bytes((const uint8_t*)"isom", 4), o.u32(0x200), o.bytes((const uint8_t*)"isomiso2avc1mp41", 16);
+  o.end(b);
+  const size_t moov = o.begin("moov");
+  static const uint32_t kMatrix[9] = {0x10000, 0, 0, 0, 0x10000, 0, 0, 0, 0x40000000};
+  b = o.begin("mvhd", 0);
+  o.u32(0), o.u32(0), o.u32(movie_ts), o.u32((uint32_t)movie_dur), o.u32(0x10000), o.u16(0x100), o.zeros(10);
+  for (uint32_t m : kMatrix) o.u32(m);
+  o.zeros(24), o.u32(2);
+  o.end(b);
+  const size_t trak = o.begin("trak");
+  b = o.begin("tkhd", 0, 3);
+  o.u32(0), o.u32(0), o.u32(1), o.u32(0), o.u32((uint32_t)movie_dur), o.zeros(8), o.u16(0), o.u16(0), o.u16(0), o.u16(0);
+  for (uint32_t m : kMatrix) o.u32(m);
+  o.u32((uint32_t)t.width << 16), o.u32((uint32_t)t.height << 16);
+  o.end(b);
+  if (min_pts != 0) {  // composition offsets: presentation starts at the earliest composition time of the range
+    const size_t edts = o.begin("edts");
+    b = o.begin("elst", 1);
+    o.u32(1), o.u64(movie_dur), o.u64((uint64_t)min_pts), o.u16(1), o.u16(0);
+    o.end(b), o.end(edts);
+  }
+  const size_t mdia = o.begin("mdia");
+  b = o.begin("mdhd", 1);
+  o.u64(0), o.u64(0), o.u32(t.timescale), o.u64((uint64_t)media_dur), o.u16(0x55C4), o.u16(0);
+  o.end(b);
+  b = o.begin("hdlr", 0);
+  o.u32(0), o.bytes((const uint8_t*)"vide", 4), o.zeros(12), o.bytes((const uint8_t*)"VideoHandler", 13);
+  o.end(b);
+  const size_t minf = o.begin("minf");
+  b = o.begin("vmhd", 0, 1);
+  o.zeros(8);
+  o.end(b);
+  const size_t dinf = o.begin("dinf");
+  b = o.begin("dref", 0);
+  o.u32(1);
+  const size_t url = o.begin("url ", 0, 1);
+  o.end(url), o.end(b), o.end(dinf);
+  const size_t stbl = o.begin("stbl");
+  o.bytes(data + t.stsd_off, t.stsd_size);
+  b = o.begin("stts", 0);
+  {
+    const size_t cnt_at = out->size();
+    o.u32(0);
+    uint32_t entries = 0;
+    for (size_t i = 0; i < count;) {
+      size_t j = i;
+      while (j < count && delta[j] == delta[i]) ++j;
+      o.u32((uint32_t)(j - i)), o.u32((uint32_t)delta[i]);
+      ++entries, i = j;
+    }
+    (*out)[cnt_at] = entries >> 24, (*out)[cnt_at + 1] = entries >> 16, (*out)[cnt_at + 2] = entries >> 8, (*out)[cnt_at + 3] = entries;
+  }
+  o.end(b);
+  if (any_cts) {
+    b = o.begin("ctts", neg_cts ? 1 : 0);
+    const size_t cnt_at = out->size();
+    o.u32(0);
+    uint32_t entries = 0;
+    for (size_t i = 0; i < count;) {
+      size_t j = i;
+      while (j < count && cts[j] == cts[i]) ++j;
+      o.u32((uint32_t)(j - i)), o.u32((uint32_t)(int32_t)cts[i]);
+      ++entries, i = j;
+    }
+    (*out)[cnt_at] = entries >> 24, (*out)[cnt_at + 1] = entries >> 16, (*out)[cnt_at + 2] = entries >> 8, (*out)[cnt_at + 3] = entries;
+    o.end(b);
+  }
+  b = o.begin("stss", 0);
+  {
+    uint32_t ns = 0;
+    for (size_t i = 0; i < count; ++i) ns += t.sync[first + i];
+    o.u32(ns);
+    for (size_t i = 0; i < count; ++i)
+      if (t.sync[first + i]) o.u32((uint32_t)i + 1);
+  }
+  o.end(b);
+  b = o.begin("stsc", 0);
+  o.u32(1), o.u32(1), o.u32((uint32_t)count), o.u32(1);
+  o.end(b);
+  b = o.begin("stsz", 0);
+  o.u32(0), o.u32((uint32_t)count);
+  for (size_t i = 0; i < count; ++i) o.u32(t.size[first + i]);
+  o.end(b);
+  b = o.begin("co64", 0);
+  o.u32(1);
+  const size_t co_at = out->size();
+  o.u64(0);
+  o.end(b);
+  o.end(stbl), o.end(minf), o.end(mdia), o.end(trak), o.end(moov);
+  const uint64_t mdat_at = out->size();
+  o.u32(1), o.bytes((const uint8_t*)"mdat", 4), o.u64(16 + payload);
+  const uint64_t chunk = mdat_at + 16;
+  for (int k = 0; k < 8; ++k) (*out)[co_at + k] = (uint8_t)(chunk >> (56 - 8 * k));
+  for (size_t i = 0; i < count; ++i) o.bytes(data + t.offset[first + i], t.size[first + i]);
+  return "";
 }
 
 bool mp4_sample_annexb(const uint8_t* data, size_t size, const Mp4Track& t, size_t i, std::vector<uint8_t>* dst) {

@@ -392,6 +392,22 @@ int cb_mp4_index(cb_ctx* ctx, const uint8_t* data, size_t size, cb_mp4_info* inf
   return CB_OK;
 }
 
+int cb_mp4_cut(cb_ctx* ctx, const uint8_t* data, size_t size, int first_sample, int n_samples, uint8_t* out, size_t out_cap, size_t* out_size) {
+  // pure host work like cb_mp4_index: ctx may be NULL
+  if (!data || !out_size || first_sample < 0 || n_samples <= 0) return cb::fail(ctx, CB_ERR_ARG, "mp4_cut: bad argument");
+  cb::Mp4Track t;
+  std::string err = cb::mp4_parse(data, size, &t);
+  if (!err.empty()) return cb::fail(ctx, CB_ERR_DEMUX, "mp4: %s", err.c_str());
+  std::vector<uint8_t> buf;
+  err = cb::mp4_cut(data, size, t, (size_t)first_sample, (size_t)n_samples, &buf);
+  if (!err.empty()) return cb::fail(ctx, CB_ERR_ARG, "mp4_cut: %s", err.c_str());
+  *out_size = buf.size();
+  if (!out) return CB_OK;  // size query
+  if (out_cap < buf.size()) return cb::fail(ctx, CB_ERR_ARG, "mp4_cut: output buffer of %zu bytes needed, %zu given", buf.size(), out_cap);
+  memcpy(out, buf.data(), buf.size());
+  return CB_OK;
+}
+
 int cb_decoder_create(cb_ctx* ctx, cb_decoder** out) {
   if (!ctx) return CB_ERR_ARG;
   if (!out) return cb::fail(ctx, CB_ERR_ARG, "decoder_create: null argument");

@@ -9,9 +9,11 @@ Same-name drop-ins (constructor arguments, task mutations and error convention o
 New fused stage (replaces ClipFrameExtractionStage -> AestheticFilterStage [-> clip embedding] in one GPU pass):
     NvdecClipAestheticStage
     NvdecShotDetectionStage      (VideoFrameExtractionStage -> TransNetV2ClipExtractionStage, frames stay in HBM)
+    ClipStreamCopyStage          (ClipTranscodingStage without the transcode: clip mp4s by stream copy, clip_extraction_stages.py:167-442)
 """
 
 from .aesthetic_filter import AestheticFilterStage  # noqa: F401
+from .clip_stream_copy import ClipStreamCopyStage  # noqa: F401
 from .fused_clip import NvdecClipAestheticStage  # noqa: F401
 from .frame_extraction import ClipFrameExtractionStage, VideoFrameExtractionStage  # noqa: F401
 from .image_embedding import ImageCLIPEmbeddingStage  # noqa: F401

@@ -188,6 +188,14 @@ typedef struct cb_decode_stats {
  * be NULL. */
 int cb_mp4_index(cb_ctx* ctx, const uint8_t* data, size_t size, cb_mp4_info* info, int64_t* pts_out, uint8_t* sync_out, int cap);
 
+/* Stream-copy cut (no transcode): samples [first_sample, first_sample + n_samples) of the first video track, decode order,
+ * starting on a sync sample, as a standalone MP4 in out[0..*out_size) - sample description copied verbatim, timestamps
+ * re-based to 0, coded pictures untouched.  With out == NULL only *out_size is set.  Replaces, for analysis-only runs, the
+ * per-clip `ffmpeg -ss/-to ... -c:v libopenh264 -b:v 4M` re-encode of ClipTranscodingStage (clip_extraction_stages.py:318-442;
+ * B200 has no NVENC, so that stage is CPU-bound there) with a memcpy of the clip's GOPs.  Host-only: ctx may be NULL. */
+int cb_mp4_cut(cb_ctx* ctx, const uint8_t* data, size_t size, int first_sample, int n_samples, uint8_t* out, size_t out_cap,
+               size_t* out_size);
+
 /* One NVDEC session (parser + decoder + copy stream); use one per host thread, reuse it across clips. */
 int cb_decoder_create(cb_ctx* ctx, cb_decoder** out);
 void cb_decoder_destroy(cb_decoder* dec);

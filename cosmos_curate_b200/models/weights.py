@@ -85,6 +85,10 @@ def seeded_weights(cfg: VitConfig, seed: int = 0) -> dict[str, np.ndarray]:
     w["post_ln_w"], w["post_ln_b"] = 1 + rn(d, std=0.05), rn(d, std=0.02)
     if cfg.proj_dim:
         w["proj_w"] = rn(cfg.proj_dim, d, std=d**-0.5)
+    if cfg.arch == "siglip":  # MAP pooling head (HF SiglipMultiheadAttentionPoolingHead)
+        w.update(map_probe=rn(d, std=0.02), map_in_w=rn(3 * d, d, std=d**-0.5), map_in_b=rn(3 * d, std=0.02), map_out_w=rn(d, d, std=d**-0.5),
+                 map_out_b=rn(d, std=0.02), map_ln_w=1 + rn(d, std=0.05), map_ln_b=rn(d, std=0.02), map_fc1_w=rn(m, d, std=d**-0.5),
+                 map_fc1_b=rn(m, std=0.02), map_fc2_w=rn(d, m, std=m**-0.5), map_fc2_b=rn(d, std=0.02))  # fmt: skip
     return w
 
 
@@ -156,3 +160,43 @@ def load_hf_clip_dir(model_dir: str | Path) -> tuple[VitConfig, dict[str, np.nda
         ln_eps=vc.get("layer_norm_eps", 1e-5), arch="clip",
     )  # fmt: skip
     return cfg, weights_from_hf_clip_state(_hf_state(model_dir), cfg)
+
+
+def weights_from_hf_siglip_state(sd: dict[str, np.ndarray], cfg: VitConfig) -> dict[str, np.ndarray]:
+    """transformers SiglipVisionModel / SiglipModel state dict (vision side) -> tower tensor names."""
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)  # noqa: E731
+    v = "vision_model."
+    w = {
+        "patch_w": f32(sd[v + "embeddings.patch_embedding.weight"]).reshape(cfg.hidden, -1), "patch_b": f32(sd[v + "embeddings.patch_embedding.bias"]),
+        "pos": f32(sd[v + "embeddings.position_embedding.weight"]),
+        "post_ln_w": f32(sd[v + "post_layernorm.weight"]), "post_ln_b": f32(sd[v + "post_layernorm.bias"]),
+        "map_probe": f32(sd[v + "head.probe"]).reshape(-1),
+        "map_in_w": f32(sd[v + "head.attention.in_proj_weight"]), "map_in_b": f32(sd[v + "head.attention.in_proj_bias"]),
+        "map_out_w": f32(sd[v + "head.attention.out_proj.weight"]), "map_out_b": f32(sd[v + "head.attention.out_proj.bias"]),
+        "map_ln_w": f32(sd[v + "head.layernorm.weight"]), "map_ln_b": f32(sd[v + "head.layernorm.bias"]),
+        "map_fc1_w": f32(sd[v + "head.mlp.fc1.weight"]), "map_fc1_b": f32(sd[v + "head.mlp.fc1.bias"]),
+        "map_fc2_w": f32(sd[v + "head.mlp.fc2.weight"]), "map_fc2_b": f32(sd[v + "head.mlp.fc2.bias"]),
+    }  # fmt: skip
+    for i in range(cfg.layers):
+        s, p = f"{v}encoder.layers.{i}.", f"L{i}."
+        w[p + "ln1_w"], w[p + "ln1_b"] = f32(sd[s + "layer_norm1.weight"]), f32(sd[s + "layer_norm1.bias"])
+        w[p + "ln2_w"], w[p + "ln2_b"] = f32(sd[s + "layer_norm2.weight"]), f32(sd[s + "layer_norm2.bias"])
+        w[p + "qkv_w"] = np.concatenate([f32(sd[s + f"self_attn.{n}_proj.weight"]) for n in "qkv"], axis=0)
+        w[p + "qkv_b"] = np.concatenate([f32(sd[s + f"self_attn.{n}_proj.bias"]) for n in "qkv"], axis=0)
+        w[p + "out_w"], w[p + "out_b"] = f32(sd[s + "self_attn.out_proj.weight"]), f32(sd[s + "self_attn.out_proj.bias"])
+        w[p + "fc1_w"], w[p + "fc1_b"] = f32(sd[s + "mlp.fc1.weight"]), f32(sd[s + "mlp.fc1.bias"])
+        w[p + "fc2_w"], w[p + "fc2_b"] = f32(sd[s + "mlp.fc2.weight"]), f32(sd[s + "mlp.fc2.bias"])
+    return w
+
+
+def load_hf_siglip_dir(model_dir: str | Path) -> tuple[VitConfig, dict[str, np.ndarray]]:
+    """A Hugging Face SigLIP checkpoint directory (google/siglip-so400m-patch14-384 layout) without instantiating the torch model."""
+    model_dir = Path(model_dir)
+    c = json.loads((model_dir / "config.json").read_text())
+    vc = c.get("vision_config", c)
+    cfg = VitConfig(
+        image_size=vc.get("image_size", 224), patch=vc.get("patch_size", 16), hidden=vc.get("hidden_size", 768),
+        layers=vc.get("num_hidden_layers", 12), heads=vc.get("num_attention_heads", 12), mlp=vc.get("intermediate_size", 3072),
+        proj_dim=0, act="gelu_tanh", ln_eps=vc.get("layer_norm_eps", 1e-6), arch="siglip",
+    )  # fmt: skip
+    return cfg, weights_from_hf_siglip_state(_hf_state(model_dir), cfg)

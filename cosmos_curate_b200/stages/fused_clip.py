@@ -42,7 +42,7 @@ except Exception:  # noqa: BLE001
 class NvdecClipAestheticStage(CuratorStage):
     def __init__(  # noqa: PLR0913
         self,
-        score_threshold: float,
+        score_threshold: float | None,
         reduction: Literal["mean", "min"] = "min",
         target_fps: float = 1.0,
         num_gpus_per_worker: float = 1.0,
@@ -87,6 +87,8 @@ class NvdecClipAestheticStage(CuratorStage):
         self._target_res = None if target_res is None or target_res[0] <= 0 or target_res[1] <= 0 else (int(target_res[0]), int(target_res[1]))
         self._cubic_mode = CUBIC_MODES[cubic_mode or default_cubic_mode()]
         self._video_index: dict[int, tuple] = {}
+        # Any ModelInterface with a `.tower` works: CLIPAestheticScorer (score + embedding) or an embedding-only tower such as
+        # SigLIPImageEmbeddings (score_threshold=None: nothing is filtered, clip.openai_embedding is the output).
         self._model = model if model is not None else CLIPAestheticScorer(max_batch=max_batch)
         self._reduce_fn = np.min
         self._pools: dict[tuple[int, int], list] = {}
@@ -111,6 +113,13 @@ class NvdecClipAestheticStage(CuratorStage):
         self._reduce_fn = np.mean if self._reduction == "mean" else np.min
         self._model.setup()
         self._ctx = get_context()
+        self._norm = (getattr(self._model, "mean", None), getattr(self._model, "std", None))
+        if self._score_threshold is not None and not self._model.tower.has_aesthetic:
+            error_msg = "score_threshold given but the model has no aesthetic head (pass score_threshold=None for embedding-only towers)"
+            raise ValueError(error_msg)
+        if self._score_threshold is None and not self._write_embedding:
+            error_msg = "embedding-only mode (score_threshold=None) needs write_embedding=True"
+            raise ValueError(error_msg)
         self._decode_pool = DecoderPool(self._ctx, self._num_decoders)  # 7 NVDEC engines need ~20 sessions in flight
         self._host: list[tuple[torch.Tensor, torch.Tensor | None]] = []
 
@@ -187,7 +196,7 @@ class NvdecClipAestheticStage(CuratorStage):
     def _host_buffers(self, r: int):
         while len(self._host) <= r:
             tower = self._model.tower
-            score = torch.empty((self._max_batch,), dtype=torch.float32).pin_memory()
+            score = torch.empty((self._max_batch,), dtype=torch.float32).pin_memory() if tower.has_aesthetic else None
             emb = torch.empty((self._max_batch, tower.out_dim), dtype=torch.float32).pin_memory() if self._write_embedding else None
             self._host.append((score, emb))
         return self._host[r]
@@ -233,12 +242,13 @@ class NvdecClipAestheticStage(CuratorStage):
             ev, errs, n = inflight.pop(k)
             ev.synchronize()
             score_h, emb_h = self._host_buffers(k % self.RING)
-            score_h = score_h[:n].numpy()
+            score_h = score_h[:n].numpy() if score_h is not None else None
             for (clip, _, ids, first), err in zip(batches[k][1], errs):
                 if err is not None:
                     self._decode_failed(clip, err)
                     continue
-                clip.aesthetic_score = float(self._reduce_fn(score_h[first : first + len(ids)]))
+                if score_h is not None:
+                    clip.aesthetic_score = float(self._reduce_fn(score_h[first : first + len(ids)]))
                 if emb_h is not None:
                     m = emb_h[first : first + len(ids)].numpy().mean(axis=0)
                     clip.openai_embedding = (m / np.linalg.norm(m)).astype(np.float32)
@@ -255,14 +265,16 @@ class NvdecClipAestheticStage(CuratorStage):
                     errs.append(e)
             pool, r = slots_of.pop(k)
             n = sum(len(ids) for _, _, ids, _ in batches[k][1])
+            norm = {} if self._norm[0] is None else {"mean": self._norm[0], "std": self._norm[1]}
             if self._target_res is not None:
                 th, tw = self._target_res
                 small = self._ctx.resize_cubic_u8(pool, tw, th, slots=np.arange(n, dtype=np.int32), mode=self._cubic_mode)
-                emb, _, score = tower.embed_pool(self._ctx.rgb_pool(small))
+                emb, _, score = tower.embed_pool(self._ctx.rgb_pool(small), **norm)
             else:
-                emb, _, score = tower.embed_pool(pool, slots=np.arange(n, dtype=np.int32))
+                emb, _, score = tower.embed_pool(pool, slots=np.arange(n, dtype=np.int32), **norm)
             score_h, emb_h = self._host_buffers(r)
-            score_h[:n].copy_(score, non_blocking=True)
+            if score_h is not None:
+                score_h[:n].copy_(score, non_blocking=True)
             if emb_h is not None:
                 emb_h[:n].copy_(emb, non_blocking=True)
             ev = torch.cuda.Event()
@@ -295,6 +307,8 @@ class NvdecClipAestheticStage(CuratorStage):
             for task in tasks:
                 for video in task.videos:
                     passed = []
+                    if self._score_threshold is None:  # embedding-only tower: nothing to filter on
+                        continue
                     for clip in video.clips:
                         if clip.aesthetic_score is None:
                             clip.aesthetic_score = -1.0

@@ -357,3 +357,35 @@ def test_clip_frame_extraction_target_res_mode_b(ctx):
     assert t_pair.video.clips[0].aesthetic_score == pytest.approx(t_fused.video.clips[0].aesthetic_score, abs=1e-6)
     _, want_scores = _oracle_scores(cfg, w, sd, want)
     assert t_fused.video.clips[0].aesthetic_score == pytest.approx(float(want_scores.mean()), abs=3e-3)
+
+
+def test_fused_stage_embedding_only_with_siglip_tower(ctx):
+    """score_threshold=None: an embedding-only tower (SigLIP geometry: no CLS, MAP head, mean = std = 0.5) behind the same fused
+    stage - clip.openai_embedding is the output, nothing is filtered (BASELINE.json configs[3]'s embed step)."""
+    from cosmos_curate_b200.interfaces import run_pipeline
+    from cosmos_curate_b200.models import weights as W
+    from cosmos_curate_b200.models.siglip import SigLIPImageEmbeddings
+    from cosmos_curate_b200.runtime import Decoder, alloc_nv12_pool
+    from cosmos_curate_b200.stages import NvdecClipAestheticStage
+    from oracle import color, preprocess, vit
+
+    cfg = W.VitConfig(image_size=224, patch=16, hidden=256, layers=2, heads=4, mlp=512, proj_dim=0, act="gelu_tanh", ln_eps=1e-6, arch="siglip")
+    model = SigLIPImageEmbeddings(seed=5, max_batch=32, config=cfg)
+    data = (GOLDEN / "sintel_clip_10s.mp4").read_bytes()
+    task = _clip_task(data, n_clips=2)
+    stage = NvdecClipAestheticStage(score_threshold=None, write_embedding=True, max_batch=32, num_decoders=2, model=model)
+    assert run_pipeline([task], [stage]) is not None
+    assert len(task.video.clips) == 2 and not task.video.filtered_clips and task.video.clips[0].aesthetic_score is None
+    ids = [0, 24, 48, 72, 96, 120, 144, 168, 192, 216, 239]
+    pool = alloc_nv12_pool(ctx, len(ids), 854, 480)
+    Decoder(ctx).decode(data, ids, pool, np.arange(len(ids)))
+    rgb = np.stack([color.nv12_to_rgb_swscale(np.ascontiguousarray(f[:, :854]), 480, 854) for f in pool.buf.cpu().numpy()])
+    ocfg = vit.VitConfig(**cfg.to_dict())
+    ref = vit.forward(ocfg, W.seeded_weights(cfg, 5), preprocess.clip_preprocess(rgb, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)))["embedding"]
+    m = ref.mean(axis=0)
+    m /= np.linalg.norm(m)
+    e = task.video.clips[0].openai_embedding
+    assert e.shape == (256,) and np.linalg.norm(e - m) / np.linalg.norm(m) < 2e-3
+    assert np.array_equal(e, task.video.clips[1].openai_embedding)
+    with pytest.raises(ValueError):
+        NvdecClipAestheticStage(score_threshold=0.5, write_embedding=True, model=SigLIPImageEmbeddings(seed=5, config=cfg)).stage_setup()

@@ -96,3 +96,29 @@ def test_siglip_so400m_shape_two_layers(ctx):
     x = np.stack([lut[c][u8[:, c]] for c in range(3)], axis=1)
     ref = vit.forward(cfg, w, x)
     assert _rel(emb.cpu().numpy(), ref["embedding"]) < 2e-3
+
+
+def test_siglip_so400m_full_depth_vs_oracle(ctx):
+    """The full SoViT-400m/14 @384 tower (27 layers, 1152 hidden, 16 x 72 heads, MLP 4304, 729 tokens, MAP head) - BASELINE.json
+    configs[3]'s network - against the fp32 oracle at n = 2, from NV12 surfaces (384 = 27 * 14 + 6 geometry included)."""
+    from cosmos_curate_b200.models import weights as W
+
+    cfg = vit.SIGLIP_SO400M_384
+    assert (cfg.layers, cfg.hidden, cfg.heads, cfg.mlp, cfg.tokens) == (27, 1152, 16, 4304, 729)
+    w = vit.random_weights(cfg, seed=8)
+    frames = [color.synthetic_nv12(1080, 1920, seed=90 + s) for s in range(2)]
+    pool = _nv12_pool(ctx, frames, 1920, 1080, 2048, 1088)
+    tower = _tower(ctx, cfg, w, max_batch=2)
+    mean = std = (0.5, 0.5, 0.5)
+    emb, feat, _ = tower.embed_pool(pool, mean=mean, std=std, want_features=True)
+    u8 = ctx.preprocess_clip_u8(pool, res=384).cpu().numpy()
+    lut = preprocess.normalize_lut(mean, std)
+    x = np.stack([lut[c][u8[:, c]] for c in range(3)], axis=1)
+    ref = vit.forward(cfg, w, x)
+    rel = _rel(emb.cpu().numpy(), ref["embedding"])
+    print(f"\n[SoViT-400m/14@384, 27 layers] embedding rel err {rel:.2e}")
+    assert rel < 1e-3
+    assert abs(W.SIGLIP_SO400M_384.flops_per_image() / 1e9 - 666.5) < 15  # SURVEY.md 8d: ~666.5 GFLOP per image
+    # the product's own seeded weights carry the MAP head too (bench.py's secondary line uses them)
+    w2 = W.seeded_weights(W.SIGLIP_SO400M_384.__class__(**{**W.SIGLIP_SO400M_384.to_dict(), "layers": 1}), seed=1)
+    assert {"map_probe", "map_in_w", "map_fc2_b", "patch_b"} <= set(w2)

@@ -32,7 +32,7 @@ struct TapTable {  // antialiased-bicubic tap table for one axis (device memory)
 struct CubicTaps {  // cv2.resize(INTER_CUBIC) tap table for one axis (device memory): 4 taps per output
   int* d_first = nullptr;    // [dst] source index of the first tap (unclamped)
   short* d_wq = nullptr;     // [dst][4] weights quantised to 2^11 (OpenCV's own fixed-point path)
-  float* d_wf = nullptr;     // [dst][4] float weights (IPP-style float path)
+  double* d_wf = nullptr;    // [dst][4] unquantised weights (IPP-style path, evaluated in double)
 };
 
 }  // namespace cb

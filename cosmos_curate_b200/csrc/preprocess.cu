@@ -565,8 +565,8 @@ __global__ void nv12_to_rgb_kernel(const SimpleArgs a) {
 //                     horizontal sums, vertical S0*b0 + (S1*b1 + (S2*b2 + S3*b3)) in fp32 without contraction, round half
 //                     even (vector body) or (sum + 2^21) >> 22 (scalar row tail).  Bit-exact.
 //   CB_CUBIC_IPP    : x86 wheels dispatch to Intel IPP, whose result is the correctly rounded real-valued cubic up to fp32
-//                     noise (measured: differs from exact arithmetic on < 3e-5 of the pixels, always at ties): fp32 weights,
-//                     fp32 accumulation, round half even.
+//                     noise (measured: differs from exact arithmetic on < 3e-5 of the pixels, always at ties): unquantised
+//                     weights and accumulation in double (fp32 accumulation alone flips ~3e-4 of the pixels), round half even.
 struct CubicArgs {
   const uint8_t* base;
   size_t slot_stride;
@@ -574,7 +574,7 @@ struct CubicArgs {
   int n, w, h, pitch, luma_rows, format, out_w, out_h, mode, n_vec;
   const int *x0, *y0;
   const short *wxq, *wyq;
-  const float *wxf, *wyf;
+  const double *wxf, *wyf;
   uint8_t* out;
 };
 
@@ -586,12 +586,12 @@ __global__ void resize_cubic_kernel(const CubicArgs a) {
   const uint8_t* fr = a.base + (size_t)a.slots[f] * a.slot_stride;
   const int xs = a.x0[xo], ys = a.y0[yo];
   int hs[4][3];
-  float hf[4][3];
+  double hf[4][3];  // IPP variant in double: fp32 accumulation alone moves ~3e-4 of the pixels across a rounding tie (measured)
 #pragma unroll
   for (int ky = 0; ky < 4; ++ky) {
     const int y = min(max(ys + ky, 0), a.h - 1);
     int acc[3] = {0, 0, 0};
-    float accf[3] = {0.f, 0.f, 0.f};
+    double accf[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int kx = 0; kx < 4; ++kx) {
       const int x = min(max(xs + kx, 0), a.w - 1);
@@ -606,8 +606,8 @@ __global__ void resize_cubic_kernel(const CubicArgs a) {
         const int wq = a.wxq[xo * 4 + kx];
         acc[0] += r * wq, acc[1] += g * wq, acc[2] += b * wq;
       } else {
-        const float wf = a.wxf[xo * 4 + kx];
-        accf[0] = fmaf((float)r, wf, accf[0]), accf[1] = fmaf((float)g, wf, accf[1]), accf[2] = fmaf((float)b, wf, accf[2]);
+        const double wf = a.wxf[xo * 4 + kx];
+        accf[0] = fma((double)r, wf, accf[0]), accf[1] = fma((double)g, wf, accf[1]), accf[2] = fma((double)b, wf, accf[2]);
       }
     }
 #pragma unroll
@@ -636,10 +636,10 @@ __global__ void resize_cubic_kernel(const CubicArgs a) {
   } else {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float t = 0.f;
+      double t = 0.0;
 #pragma unroll
-      for (int ky = 0; ky < 4; ++ky) t = fmaf(hf[ky][c], a.wyf[yo * 4 + ky], t);
-      o[c] = (uint8_t)min(max(__float2int_rn(t), 0), 255);
+      for (int ky = 0; ky < 4; ++ky) t = fma(hf[ky][c], a.wyf[yo * 4 + ky], t);
+      o[c] = (uint8_t)min(max(__double2int_rn(t), 0), 255);
     }
   }
 }
@@ -905,7 +905,7 @@ static const CubicTaps* get_cubic_taps(cb_ctx* ctx, int src, int dst) {
   if (it != ctx->cubic_taps.end()) return &it->second;
   std::vector<int> first(dst);
   std::vector<short> wq(4 * (size_t)dst);
-  std::vector<float> wf(4 * (size_t)dst);
+  std::vector<double> wf(4 * (size_t)dst);
   const double inv_scale = (double)dst / (double)src, scale = 1.0 / inv_scale;
   for (int d = 0; d < dst; ++d) {
     float fx = (float)((d + 0.5) * scale - 0.5);
@@ -925,16 +925,16 @@ static const CubicTaps* get_cubic_taps(cb_ctx* ctx, int src, int dst) {
     for (int k = 0; k < 4; ++k) {
       const float q = std::nearbyint(c[k] * 2048.f);  // saturate_cast<short>(float) = cvRound: half to even
       wq[4 * (size_t)d + k] = (short)std::min(32767.f, std::max(-32768.f, q));
-      wf[4 * (size_t)d + k] = (float)(k < 3 ? cd[k] : 1.0 - cd[0] - cd[1] - cd[2]);
+      wf[4 * (size_t)d + k] = k < 3 ? cd[k] : 1.0 - cd[0] - cd[1] - cd[2];
     }
   }
   CubicTaps t;
   if (cudaMalloc(&t.d_first, dst * sizeof(int)) != cudaSuccess || cudaMalloc(&t.d_wq, 4 * (size_t)dst * sizeof(short)) != cudaSuccess ||
-      cudaMalloc(&t.d_wf, 4 * (size_t)dst * sizeof(float)) != cudaSuccess)
+      cudaMalloc(&t.d_wf, 4 * (size_t)dst * sizeof(double)) != cudaSuccess)
     return nullptr;
   cudaMemcpy(t.d_first, first.data(), dst * sizeof(int), cudaMemcpyHostToDevice);
   cudaMemcpy(t.d_wq, wq.data(), 4 * (size_t)dst * sizeof(short), cudaMemcpyHostToDevice);
-  cudaMemcpy(t.d_wf, wf.data(), 4 * (size_t)dst * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(t.d_wf, wf.data(), 4 * (size_t)dst * sizeof(double), cudaMemcpyHostToDevice);
   return &(ctx->cubic_taps[key] = t);
 }
 

@@ -97,11 +97,12 @@ BITRATE = 4.0e6  # the reference's transcode default (decoder_utils.py:43)
 
 
 def _gen_clip(args) -> str:
-    seed, path = args
+    seed, path = args[:2]
+    w, h, bitrate = args[2:] if len(args) > 2 else (FRAME_W, FRAME_H, BITRATE)
     from tools import synth_h264
 
     if not os.path.exists(path):
-        data = synth_h264.make_coded_clip(FRAME_W, FRAME_H, FPS, SECONDS, seed=seed, gop=FPS, bitrate=BITRATE)
+        data = synth_h264.make_coded_clip(w, h, FPS, SECONDS, seed=seed, gop=FPS, bitrate=bitrate)
         tmp = f"{path}.{os.getpid()}.tmp"
         with open(tmp, "wb") as f:
             f.write(data)
@@ -109,14 +110,14 @@ def _gen_clip(args) -> str:
     return path
 
 
-def make_clips(n_distinct: int, rank: int, workers: int | None = None) -> list[bytes]:
+def make_clips(n_distinct: int, rank: int, workers: int | None = None, size: tuple[int, int] = (FRAME_W, FRAME_H), bitrate: float = BITRATE) -> list[bytes]:
     """`n_distinct` residual-coded clips (seed = 1000 * rank + i), generated by a fork pool BEFORE CUDA is initialised and
     cached under /tmp (both arms of one box reuse them)."""
     import multiprocessing as mp
 
-    root = os.path.join(os.environ.get("CB_CLIP_CACHE", "/tmp"), f"cb_clips_{FRAME_W}x{FRAME_H}_{FPS}_{int(SECONDS)}s_{int(BITRATE)}")
+    root = os.path.join(os.environ.get("CB_CLIP_CACHE", "/tmp"), f"cb_clips_{size[0]}x{size[1]}_{FPS}_{int(SECONDS)}s_{int(bitrate)}")
     os.makedirs(root, exist_ok=True)
-    jobs = [(1000 * rank + i, os.path.join(root, f"clip_{1000 * rank + i}.mp4")) for i in range(n_distinct)]
+    jobs = [(1000 * rank + i, os.path.join(root, f"clip_{1000 * rank + i}.mp4"), size[0], size[1], bitrate) for i in range(n_distinct)]
     todo = [j for j in jobs if not os.path.exists(j[1])]
     if todo:
         world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
@@ -128,8 +129,8 @@ def make_clips(n_distinct: int, rank: int, workers: int | None = None) -> list[b
             for j in todo:
                 _gen_clip(j)
     out = []
-    for _, path in jobs:
-        with open(path, "rb") as f:
+    for job in jobs:
+        with open(job[1], "rb") as f:
             out.append(f.read())
     return out
 
@@ -202,6 +203,7 @@ def run_reference(args) -> None:
 def run_b200(args) -> None:
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     clips = make_clips(args.distinct_clips, rank)  # fork pool: before torch / CUDA are touched
+    clips_4k = make_clips(4, 0, size=(3840, 2160), bitrate=16.0e6) if (rank == 0 and world == 1 and not args.no_secondary) else None
 
     import torch
     import torch.distributed as dist
@@ -466,6 +468,13 @@ def run_b200(args) -> None:
         line["shot_detection"] = shot
     if e2e_error:
         line["e2e_error"] = e2e_error
+    if world == 1 and not args.no_secondary:
+        try:
+            line["secondary"] = secondary_configs(ctx, torch, clips, clips_4k, args)
+        except Exception as exc:  # noqa: BLE001
+            import traceback
+
+            line["secondary"] = {"error": f"{type(exc).__name__}: {exc} | {traceback.format_exc()[-500:]}"}
     if world == 1 and not args.no_gpu_library:
         try:
             line["gpu_library_baseline"] = gpu_library_baseline(clips[:4], torch)
@@ -476,6 +485,134 @@ def run_b200(args) -> None:
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_configs(ctx, torch, clips_1080p: list[bytes], clips_4k, args) -> dict:
+    """Bounded secondary rows (N=1, rank 0): BASELINE.json configs[0] (C1) on both arms, a configs[3]-shaped row (4K + SoViT-400m) and
+    the transcode-free clip cutter.  Not the headline; each states its own workload."""
+    import uuid
+
+    from cosmos_curate_b200.data_model import Clip, SplitPipeTask, Video
+    from cosmos_curate_b200.models import weights as W
+    from cosmos_curate_b200.models.clip_aesthetics import CLIPAestheticScorer
+    from cosmos_curate_b200.models.siglip import SigLIPImageEmbeddings
+    from cosmos_curate_b200.runtime import mp4_index
+    from cosmos_curate_b200.stages import ClipStreamCopyStage, NvdecClipAestheticStage
+    from cosmos_curate_b200.stages.clip_stream_copy import mp4_cut
+
+    out: dict = {}
+
+    def tasks_of(datas, per_task, seconds):
+        arrs = [np.frombuffer(d, dtype=np.uint8) for d in datas]
+        return [SplitPipeTask(session_id=f"t{t}", video=Video(input_video="v.mp4", clips=[
+            Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0.0, seconds), encoded_data=arrs[(t * per_task + j) % len(arrs)]) for j in range(per_task)]))
+            for t in range(max(1, len(arrs) // per_task))]  # fmt: skip
+
+    def timed(stage, make, reps):
+        stage.process_data(make())  # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(reps):
+            for t in stage.process_data(make()):
+                n += len(t.video.clips) + len(t.video.filtered_clips)
+        torch.cuda.synchronize()
+        return n / (time.perf_counter() - t0), n
+
+    # ---- C1: 32 x 480p 5 s clips, CLIP ViT-B/32 (the configuration the reference itself runs on CPU)
+    sintel = ROOT / "tests" / "golden" / "sintel_clip_10s.mp4"
+    if sintel.exists():
+        src = sintel.read_bytes()
+        c1 = bytes(mp4_cut(src, 0, 120))  # first 5 s (24 fps) by stream copy: the fixture is a single GOP
+        model = CLIPAestheticScorer(seed=0, max_batch=256, config=W.CLIP_VIT_B32)
+        st = NvdecClipAestheticStage(score_threshold=-1e9, reduction="min", write_embedding=True, max_batch=256, num_decoders=args.decoders, seek_keyframes=False, model=model)
+        st.stage_setup()
+        cps, n = timed(st, lambda: tasks_of([c1] * 32, 32, 5.0), 3)
+        st.destroy()
+        model.tower.close()
+        out["c1"] = {"workload": "32 x (854x480 24 fps 5 s H.264 High/CABAC real content: the reference's test fixture cut to 5 s by stream copy) -> 1 fps -> CLIP ViT-B/32 (seeded) + aesthetic head "
+                                 "(BASELINE.json configs[0])", "b200_e2e_clips_per_sec": cps, "clips": n, "api": "NvdecClipAestheticStage.process_data, host mp4 bytes in",
+                     "cpu": cpu_c1(c1)}  # fmt: skip
+
+    # ---- C4-shaped: 4K clips, 2 fps sampling, SoViT-400m/14 @384 embedding-only (HEVC streams cannot be produced here: H.264 at 4K instead)
+    if clips_4k:
+        cfg = W.SIGLIP_SO400M_384
+        idx = mp4_index(clips_4k[0])
+        sig = SigLIPImageEmbeddings(seed=0, max_batch=84, config=cfg)
+        st = NvdecClipAestheticStage(score_threshold=None, target_fps=2.0, write_embedding=True, max_batch=84, num_decoders=args.decoders, seek_keyframes=False, model=sig)
+        st.stage_setup()
+        cps, n = timed(st, lambda: tasks_of(clips_4k * 3, 12, SECONDS), 2)
+        decoded = st.last_call_stats["frames_decoded"]
+        # resident-input tower rate + roofline of its GEMMs (the dominant kernel of this configuration too)
+        from cosmos_curate_b200.runtime import alloc_nv12_pool
+
+        tower = sig.tower
+        pool = alloc_nv12_pool(ctx, 84, idx["width"], idx["height"], colour="swscale")
+        pool.buf.random_(16, 236)
+        for _ in range(2):
+            tower.embed_pool(pool, mean=sig.mean, std=sig.std)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.profile_begin()
+        ev0.record()
+        reps = 3
+        for _ in range(reps):
+            tower.embed_pool(pool, mean=sig.mean, std=sig.std)
+        ev1.record()
+        prof = ctx.profile_end()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / reps
+        pk, _ = peaks()
+        gemm_tf = cfg.gemm_flops_per_image() * 84 * reps / (prof["gemm"]["ms"] / 1e3) / 1e12
+        pre_b = (1.5 * 2160**2 + 3 * 384 * 384 * 2) * 84 * reps
+        st.destroy()
+        tower.close()
+        out["c4_shape"] = {
+            "workload": "3840x2160 30 fps 10 s H.264 ~16 Mb/s synthetic clips (HEVC cannot be produced in this image; NVDEC accepts hvc1/hev1) -> 2 fps (21 frames/clip) -> "
+                        "SigLIP SoViT-400m/14 @384 embedding, seeded weights (BASELINE.json configs[3] shape, one GPU)",
+            "e2e_clips_per_sec": cps, "clips": n, "decoded_frames_per_call": decoded, "resident_frames_per_sec": 84 / ms * 1e3, "resident_ms_per_84_frames": ms,
+            "gemm": {"achieved_tflops": gemm_tf, "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "frac": gemm_tf / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
+                     "ms": prof["gemm"]["ms"] / reps},
+            "attention_ms": prof["attention"]["ms"] / reps, "layernorm_ms": prof["layernorm"]["ms"] / reps,
+            "preprocess": {"ms": prof["preprocess"]["ms"] / reps, "algorithmic_gbs": pre_b / (prof["preprocess"]["ms"] / 1e3) / 1e9},
+            "gflop_per_image": cfg.flops_per_image() / 1e9}  # fmt: skip
+
+    # ---- transcode-free clip cutting (N2): 5 s spans out of the 10 s 1080p sources by stream copy
+    stage = ClipStreamCopyStage()
+    vids = []
+    for i in range(16):
+        v = Video(input_video=f"v{i}.mp4", encoded_data=clips_1080p[i % len(clips_1080p)], clips=[Clip(uuid=uuid.uuid4(), source_video=f"v{i}.mp4", span=s) for s in ((0.0, 5.0), (5.0, 10.0))])
+        v.metadata.duration = SECONDS
+        vids.append(SplitPipeTask(session_id=f"c{i}", video=v))
+    t0 = time.perf_counter()
+    stage.process_data(vids)
+    dt = time.perf_counter() - t0
+    nb = sum(c.encoded_data.nbytes for t in vids for c in t.video.clips)
+    out["clip_cut"] = {"workload": "32 five-second clips cut from sixteen 1080p 10 s sources by stream copy (ClipStreamCopyStage; the reference re-encodes each with libopenh264)",
+                       "clips_per_sec": 32 / dt, "mb_per_sec": nb / dt / 1e6, "host_threads": 1}  # fmt: skip
+    return out
+
+
+def cpu_c1(clip: bytes) -> dict:
+    """The reference CPU path on C1 (32 x 480p 5 s, ViT-B/32): all usable cores, and one core for per-core normalisation."""
+    import torch
+
+    from oracle import cpu_path, vit
+
+    cores = effective_cores()
+    cfg = vit.CLIP_VIT_B32
+    w, sd = vit.random_weights(cfg, seed=0), vit.random_aesthetic_mlp(seed=0, in_dim=cfg.proj_dim)
+    res = {}
+    prev = torch.get_num_threads()
+    try:
+        for name, threads, n in (("all_cores", cores, 32), ("one_core", 1, 4)):
+            path = cpu_path.CpuReferencePath(cfg, w, sd, threads=threads)
+            path.run([clip], 1.0, decode_workers=1, decode_threads=min(4, threads))  # warm-up
+            r = path.run([clip] * n, 1.0, decode_workers=max(1, threads // 4), decode_threads=min(4, threads))
+            res[name] = {"clips_per_sec": r["clips"] / r["seconds"], "threads": threads, "clips": n, "decode_s": r["decode_s"], "model_s": r["model_s"]}
+    finally:
+        torch.set_num_threads(prev)
+    return res
 
 
 def gpu_library_baseline(clips: list[bytes], torch, n_calls: int = 12) -> dict:
@@ -628,6 +765,7 @@ def main() -> None:
     ap.add_argument("--distinct-clips", type=int, default=64)
     ap.add_argument("--tasks-per-call", type=int, default=10, help="SplitPipeTasks (of clips-per-step clips each) per process_data call of the e2e measurement")
     ap.add_argument("--ceiling-seconds", type=float, default=5.0, help="duration of the decode-only ceiling measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C1 / C4-shaped / clip-cut secondary rows")
     ap.add_argument("--no-gpu-library", action="store_true", help="skip the reference GPU library-path baseline")
     ap.add_argument("--decoders", type=int, default=20, help="concurrent NVDEC sessions per GPU (7 engines on B200)")
     ap.add_argument("--e2e-steps", type=int, default=2, help="timed process_data calls of the e2e measurement")

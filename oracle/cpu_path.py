@@ -83,12 +83,12 @@ class CpuReferencePath:
         self.tf = reference_transforms()
 
     @torch.no_grad()
-    def run(self, clips: list[bytes], fps: float = 1.0, decode_workers: int | None = None) -> dict:
+    def run(self, clips: list[bytes], fps: float = 1.0, decode_workers: int | None = None, decode_threads: int = 4) -> dict:
         t0 = time.perf_counter()
         # the reference runs several ClipFrameExtractionStage actors (3 CPUs each, 4 decode threads) side by side
         workers = decode_workers or max(1, self.threads // 4)
         with ThreadPoolExecutor(max_workers=min(workers, len(clips))) as ex:
-            decoded = list(ex.map(lambda c: decode_sampled_frames(c, fps, 4), clips))
+            decoded = list(ex.map(lambda c: decode_sampled_frames(c, fps, decode_threads), clips))
         t1 = time.perf_counter()
         embs, scores, n_frames = [], [], 0
         t_pre = t_model = 0.0

@@ -144,6 +144,8 @@ void cb_destroy(cb_ctx* ctx) {
     cudaFree(kv.second.d_wq);
     cudaFree(kv.second.d_wf);
   }
+  cb::release_tc_plans(ctx);
+  if (ctx->d_tmp_u8) cudaFree(ctx->d_tmp_u8);
   if (ctx->d_norm_lut) cudaFree(ctx->d_norm_lut);
   if (ctx->d_slots) cudaFree(ctx->d_slots);
   for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);

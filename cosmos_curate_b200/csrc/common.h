@@ -27,6 +27,7 @@ struct TapTable {  // antialiased-bicubic tap table for one axis (device memory)
   int* d_size = nullptr;           // [crop_len] tap count per output
   float* d_w = nullptr;            // [crop_len * max_taps] normalised weights
   std::vector<int> h_min, h_size;
+  std::vector<float> h_w;          // host copy of d_w (the tensor-pipe kernel builds its fp16 hi/lo operand tiles from it)
 };
 
 struct CubicTaps {  // cv2.resize(INTER_CUBIC) tap table for one axis (device memory): 4 taps per output
@@ -56,6 +57,8 @@ struct cb_ctx {
   std::vector<int> prof_cat;
   size_t prof_n = 0;
   void* nvdec = nullptr;            // lazily created NVDEC state (nvdec.cpp)
+  uint8_t* d_tmp_u8 = nullptr;      // u8 [n][3][res][res] between the tensor-pipe resample kernel and the normalise/pack kernel
+  size_t tmp_u8_cap = 0;
   int* d_slots = nullptr;           // device staging of the slot list of the current preprocess call
   int slots_cap = 0;
 };
@@ -77,6 +80,10 @@ int make_tensor_map(cb_ctx* ctx, CUtensorMap* out, CUtensorMapDataType dtype, in
                     const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, CUtensorMapSwizzle swizzle);
 
 const TapTable* get_taps(cb_ctx* ctx, int in_size, int out_size, int crop_off, int crop_len);
+// preprocess_tc.cu: tensor-pipe resample (returns CB_OK, 1 = configuration not served -> use the SIMT kernel, < 0 = error)
+int run_clip_preprocess_tc(cb_ctx* ctx, const cb_surface_pool* pool, const int* d_slots, int n, int max_slot, int res, int out_mode, int patch, int k_pad,
+                           int dtype, const TapTable* tx, const TapTable* ty, void* out, cudaStream_t stream);
+void release_tc_plans(cb_ctx* ctx);
 int ensure_norm_lut(cb_ctx* ctx, const float mean[3], const float std_[3], cudaStream_t stream);
 // NV12 -> RGB -> bilinear out_w x out_h for ONE surface at `base` (used on NVDEC-mapped frames), u8 HWC into `out`.
 int bilinear_from_surface(cb_ctx* ctx, const void* base, int pitch, int luma_rows, int w, int h, int out_w, int out_h, uint8_t* out, cudaStream_t stream);

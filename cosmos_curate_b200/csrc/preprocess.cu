@@ -698,6 +698,7 @@ const TapTable* get_taps(cb_ctx* ctx, int in_size, int out_size, int crop_off, i
   cudaMemcpy(t.d_min, t.h_min.data(), crop_len * sizeof(int), cudaMemcpyHostToDevice);
   cudaMemcpy(t.d_size, t.h_size.data(), crop_len * sizeof(int), cudaMemcpyHostToDevice);
   cudaMemcpy(t.d_w, flat.data(), flat.size() * sizeof(float), cudaMemcpyHostToDevice);
+  t.h_w = flat;
   auto res = ctx->taps.emplace(key, std::move(t));
   return &res.first->second;
 }
@@ -824,6 +825,11 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
 
   int max_slot = 0;
   for (int i = 0; i < n; ++i) max_slot = std::max(max_slot, (int)slots[i]);
+  // default: horizontal pass on the tensor pipe (preprocess_tc.cu); CB_PRE_KERNEL=2 / 1 select the SIMT generations for A/B
+  if (!kver || kver[0] == '3') {
+    rc = run_clip_preprocess_tc(ctx, pool, a.slots, n, max_slot, res, out_mode, layout_patch, k_pad, dtype, tx, ty, out, stream);
+    if (rc <= 0) return rc;
+  }
   CUtensorMap map_a, map_b;
   if (is_nv12(pool->format)) {
     uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)max_slot + 1};

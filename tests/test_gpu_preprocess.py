@@ -168,3 +168,36 @@ def test_resize_cubic_from_nv12_and_into_the_tower(ctx):
     ref = vit.forward(cfg, w, preprocess.clip_preprocess(want_f))["embedding"]  # 224x224 input: torchvision Resize / CenterCrop are no-ops
     rel = np.linalg.norm(emb.cpu().numpy() - ref, axis=1) / np.linalg.norm(ref, axis=1)
     assert rel.max() < 1e-3
+
+
+# ------------------------------------------------------------------------------------ tensor-pipe generation vs SIMT generation
+@pytest.mark.parametrize(("h", "w", "pitch", "res", "colour"), [(1080, 1920, 2048, 224, "opencv"), (1080, 1920, 2048, 224, "swscale"), (2160, 3840, 3840, 384, "swscale"),
+                                                                (480, 854, 1024, 224, "swscale"), (720, 1280, 1280, 384, "opencv"), (360, 640, 640, 224, "opencv")])
+def test_tensor_pipe_preprocess_agrees_with_simt_kernel_and_oracle(ctx, monkeypatch, h, w, pitch, res, colour):
+    """clip_preprocess_tc_kernel (horizontal pass as a banded fp16 hi/lo GEMM on tcgen05, the default) against the v2 SIMT kernel
+    (CB_PRE_KERNEL=2) and the oracle: same u8 image within the fp32-summation-order budget, both colour conversions, 1080p -> 224
+    (bench shape), 4K -> 384 (SoViT shape, 24 vertical taps, 256-column windows), widths that are not a multiple of the window."""
+    from gpu_helpers import nv12_pool
+
+    frames = [color.synthetic_nv12(h, w, seed=60 + s) for s in range(2)]
+    rows = h + h // 2
+    buf = np.zeros((2, rows, pitch), dtype=np.uint8)
+    for i, f in enumerate(frames):
+        buf[i, :, :w] = f
+    pool = ctx.nv12_pool(torch.from_numpy(buf).cuda(), w, h, h, colour=colour)
+    got_tc = ctx.preprocess_clip_u8(pool, res=res).cpu().numpy()
+    monkeypatch.setenv("CB_PRE_KERNEL", "2")
+    got_v2 = ctx.preprocess_clip_u8(pool, res=res).cpu().numpy()
+    monkeypatch.delenv("CB_PRE_KERNEL")
+    conv = color.nv12_to_rgb_swscale if colour == "swscale" else color.nv12_to_rgb
+    rgb = np.stack([conv(f, h, w) for f in frames])
+    want = preprocess.clip_resize_crop_u8(rgb, res)
+    _u8_budget(got_v2, want)
+    _u8_budget(got_tc, want)
+    _u8_budget(got_tc, got_v2, frac=2e-4)  # two fp32 summation orders apart
+    # typed + patch outputs of the tensor-pipe path are exactly LUT(u8)
+    lut = preprocess.normalize_lut()
+    want32 = np.stack([lut[c][got_tc[:, c]] for c in range(3)], axis=1)
+    np.testing.assert_array_equal(ctx.preprocess_clip(pool, res=res, dtype=torch.float32).cpu().numpy(), want32)
+    gp = ctx.preprocess_clip(pool, res=res, dtype=torch.float16, layout="patch", patch=14, k_pad=640).cpu().numpy()
+    np.testing.assert_array_equal(gp, preprocess.to_patches(want32.astype(np.float16), 14, 640))

@@ -39,7 +39,7 @@ __device__ __forceinline__ void yuv_to_rgb(int y, int u, int v, int& r, int& g, 
 // ff_yuv2rgb_c_init_tables for ITU-R BT.601 limited range, the default PyAV / cv2 leave in place): 16-bit fixed point,
 // every product truncated by pmulhw - (8Y - 128) * 9539 >> 16 etc. - nearest chroma.  This is what the reference's CPU decode
 // (decode_video_cpu_frame_ids -> frame.to_ndarray(format="rgb24"), decoder_utils.py:439-451) feeds the CLIP transforms.
-// Pinned bit-exactly against cv2/libswscale over the whole u8 range (oracle/color.py, tests/test_oracle_cpu.py).
+// Pinned bit-exactly against cv2/libswscale over the whole u8 range (tests/test_oracle_cpu.py).
 __device__ __forceinline__ void yuv_to_rgb_sws(int y, int u, int v, int& r, int& g, int& b) {
   const int yy = (((y << 3) - 128) * 9539) >> 16;
   const int uu = (u << 3) - 1024, vv = (v << 3) - 1024;

@@ -45,6 +45,7 @@ struct TcArgs {
   const int* tile_nk;      // [n_slabs * 2] k-steps of the N-tile (0 = tile beyond the image)
   const uint8_t* wtiles;   // [n_slabs][2 tiles][hi | lo][kb / 64][2048 B] fp16, already in the swizzled UMMA layout
   const int *ymin, *ysize;
+  const int* unit_last;    // [n_units] output rows complete once unit u has been filtered
   const float* wy;
   int ty;
   uint8_t* out;  // [n][3][res][res]
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const bool sws = a.colour == CB_FMT_NV12_SWS;
   int next_out = 0;
   for (int u = 0; u < a.n_units; ++u) {
-    mbar_wait(raw_full, u & 1);
+    mbar_wait_parked(raw_full, u & 1, 2000);
     // ---- colour conversion straight into the A operand: a thread owns 2 rows x 4 pixels (two chroma samples)
     {
       const uint8_t* ry = sRaw;
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       }
       umma_commit(mma_done);
     }
-    mbar_wait(mma_done, u & 1);
+    mbar_wait_parked(mma_done, u & 1, 2000);  // 255 threads have nothing to do until the MMAs land: do not burn the co-resident CTA's issue slots
     tc_fence_after();
     // ---- epilogue: the filtered rows of this unit -> ring (warp = lane quarter x N-tile)
     {
@@ -216,12 +217,13 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     __syncthreads();
     // ---- vertical pass for every output row whose taps are now complete (ATen order: first product, then FMAs), round half even
     {
-      const int rows_end = a.y_begin + (u + 1) * ru;
-      int last = next_out;
-      while (last < a.res && a.ymin[last] + a.ysize[last] <= rows_end) ++last;
+      const int last = a.unit_last[u];
       const int items = (last - next_out) * 3 * ncols;
       for (int i = tid; i < items; i += kTcThreads) {
-        const int x = i % ncols, t = i / ncols, ch = t % 3, y = next_out + t / 3;
+        int x, t;
+        if (ncols == kNC) x = i & (kNC - 1), t = i >> 5;
+        else x = i % ncols, t = i / ncols;
+        const int yr = t / 3, ch = t - 3 * yr, y = next_out + yr;
         const int y0 = a.ymin[y] - a.y_begin, nt = a.ysize[y];
         const float* w = a.wy + (size_t)y * a.ty;
         float acc = ring[(((y0 & (kRingRows - 1)) * 3 + ch) * kNC) + x] * w[0];
@@ -250,28 +252,56 @@ __device__ __forceinline__ void store_out(void* out, size_t idx, float v, int dt
   else reinterpret_cast<float*>(out)[idx] = v;
 }
 
-__global__ void normalize_pack_kernel(const PackArgs a) {
+__global__ void normalize_pack_kernel(const PackArgs a) {  // mode 1: typed NCHW, one element per thread (parity-test output)
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (a.mode == 1) {
-    const size_t per = (size_t)3 * a.res * a.res;
-    if (i >= per * a.n) return;
-    const int ch = (int)((i % per) / ((size_t)a.res * a.res));
-    store_out(a.out, i, a.lut[ch * 256 + a.src[i]], a.dtype);
-    return;
-  }
+  const size_t plane = (size_t)a.res * a.res;
+  if (i >= 3 * plane * a.n) return;
+  const int ch = (int)((i / plane) % 3);
+  store_out(a.out, i, a.lut[ch * 256 + a.src[i]], a.dtype);
+}
+
+// mode 2: one CTA per (frame, patch row): the k -> (plane, y, x) map of a patch is built once in shared memory, then every thread
+// emits 8 consecutive elements of a zero-padded patch row per iteration as one 16-byte store.
+__global__ void __launch_bounds__(256) pack_patches_kernel(const PackArgs a) {
+  extern __shared__ int koff[];  // [k_pad]: (plane << 24) | offset inside the patch origin's plane, -1 = padding
   const int g = a.res / a.patch, pp = a.patch * a.patch;
-  const size_t total = (size_t)a.n * g * g * a.k_pad;
-  if (i >= total) return;
-  const int kk = (int)(i % a.k_pad);
-  const size_t prow = i / a.k_pad;
-  float v = 0.f;
-  if (kk < 3 * pp) {
-    const int ch = kk / pp, yy = (kk - ch * pp) / a.patch, xx = kk - ch * pp - yy * a.patch;
-    const int px = (int)(prow % g), py = (int)((prow / g) % g);
-    const size_t f = prow / ((size_t)g * g);
-    v = a.lut[ch * 256 + a.src[((f * 3 + ch) * a.res + (size_t)py * a.patch + yy) * a.res + (size_t)px * a.patch + xx]];
+  for (int k = threadIdx.x; k < a.k_pad; k += blockDim.x) {
+    int v = -1;
+    if (k < 3 * pp) {
+      const int ch = k / pp, yy = (k - ch * pp) / a.patch, xx = k - ch * pp - yy * a.patch;
+      v = (ch << 24) | (yy * a.res + xx);
+    }
+    koff[k] = v;
   }
-  store_out(a.out, i, v, a.dtype);
+  __syncthreads();
+  const int py = blockIdx.x, f = blockIdx.y;
+  const size_t plane = (size_t)a.res * a.res;
+  const uint8_t* img = a.src + (size_t)f * 3 * plane + (size_t)py * a.patch * a.res;
+  const int k8 = a.k_pad >> 3;
+  const bool bf = a.dtype == CB_DT_BF16;
+  for (int i = threadIdx.x; i < g * k8; i += blockDim.x) {
+    const int px = i / k8, kk = (i - px * k8) << 3;
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int o = koff[kk + 2 * e + h];
+        const int ch = o >> 24;
+        v[h] = o < 0 ? 0.f : a.lut[ch * 256 + img[(size_t)ch * plane + (o & 0xFFFFFF) + px * a.patch]];
+      }
+      if (bf) {
+        __nv_bfloat162 b = __floats2bfloat162_rn(v[0], v[1]);
+        w[e] = *reinterpret_cast<uint32_t*>(&b);
+      } else {
+        __half2 hh = __floats2half2_rn(v[0], v[1]);
+        w[e] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + (((size_t)f * g + py) * g + px) * a.k_pad + kk);
+    *dst = make_uint4(w[0], w[1], w[2], w[3]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -279,7 +309,7 @@ namespace {
 
 struct TcPlan {  // per (source size, taps): slab windows + pre-swizzled weight tiles on the device
   int n_slabs = 0, kw = 0, kb = 0, ru = 0, n_units = 0, y_begin = 0;
-  int *d_x_lo = nullptr, *d_k0 = nullptr, *d_nk = nullptr;
+  int *d_x_lo = nullptr, *d_k0 = nullptr, *d_nk = nullptr, *d_unit_last = nullptr;
   uint8_t* d_w = nullptr;
   bool ok = false;
 };
@@ -352,7 +382,16 @@ static const TcPlan* get_plan(cb_ctx* ctx, const TapTable* tx, const TapTable* t
             w[((size_t)(s * 4 + j * 2 + 1) * b_tile + off) / 2] = lb;
           }
         }
+    std::vector<int> unit_last(p.n_units);
+    for (int u = 0, last = 0; u < p.n_units; ++u) {
+      const int rows_end = p.y_begin + (u + 1) * p.ru;
+      while (last < res && ty->h_min[last] + ty->h_size[last] <= rows_end) ++last;
+      unit_last[u] = last;
+    }
+    if (p.n_units > 0) unit_last[p.n_units - 1] = res;
     const size_t ib = p.n_slabs * sizeof(int);
+    if (cudaMalloc(&p.d_unit_last, p.n_units * sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemcpy(p.d_unit_last, unit_last.data(), p.n_units * sizeof(int), cudaMemcpyHostToDevice);
     if (cudaMalloc(&p.d_x_lo, ib) != cudaSuccess || cudaMalloc(&p.d_k0, 2 * ib) != cudaSuccess || cudaMalloc(&p.d_nk, 2 * ib) != cudaSuccess ||
         cudaMalloc(&p.d_w, w.size() * 2) != cudaSuccess)
       return nullptr;
@@ -366,7 +405,7 @@ static const TcPlan* get_plan(cb_ctx* ctx, const TapTable* tx, const TapTable* t
 
 void release_tc_plans(cb_ctx* ctx) {
   for (auto& kv : plans(ctx)) {
-    cudaFree(kv.second.d_x_lo), cudaFree(kv.second.d_k0), cudaFree(kv.second.d_nk), cudaFree(kv.second.d_w);
+    cudaFree(kv.second.d_x_lo), cudaFree(kv.second.d_k0), cudaFree(kv.second.d_nk), cudaFree(kv.second.d_w), cudaFree(kv.second.d_unit_last);
   }
   plans(ctx).clear();
 }
@@ -408,7 +447,7 @@ int run_clip_preprocess_tc(cb_ctx* ctx, const cb_surface_pool* pool, const int* 
   a.slots = d_slots, a.n = n, a.res = res, a.ru = p->ru, a.n_units = p->n_units, a.y_begin = p->y_begin, a.kw = p->kw, a.kb = p->kb;
   a.colour = pool->format;
   a.x_lo = p->d_x_lo, a.tile_k0 = p->d_k0, a.tile_nk = p->d_nk, a.wtiles = p->d_w;
-  a.ymin = ty->d_min, a.ysize = ty->d_size, a.wy = ty->d_w, a.ty = ty->max_taps, a.out = u8;
+  a.ymin = ty->d_min, a.ysize = ty->d_size, a.unit_last = p->d_unit_last, a.wy = ty->d_w, a.ty = ty->max_taps, a.out = u8;
   const int b_tile = (p->kb / 64) * 2048;
   const size_t smem = 1024 + (size_t)p->kw * 256 + 4 * (size_t)b_tile + ((((size_t)(p->ru + p->ru / 2) * p->kw) + 127) & ~(size_t)127) + kRingRows * 3 * kNC * 4 + 64;
   CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -418,9 +457,14 @@ int run_clip_preprocess_tc(cb_ctx* ctx, const cb_surface_pool* pool, const int* 
   if (out_mode != 0) {
     PackArgs q{};
     q.src = u8, q.lut = ctx->d_norm_lut, q.n = n, q.res = res, q.mode = out_mode, q.dtype = dtype, q.patch = patch, q.k_pad = k_pad, q.out = out;
-    const size_t total = out_mode == 1 ? (size_t)n * 3 * res * res : (size_t)n * (res / patch) * (res / patch) * k_pad;
     mark_launch(ctx, CB_PROF_PREPROCESS, stream);
-    normalize_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(q);
+    if (out_mode == 1) {
+      const size_t total = (size_t)n * 3 * res * res;
+      normalize_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(q);
+    } else {
+      const int g = res / patch;
+      pack_patches_kernel<<<dim3(g, n), 256, k_pad * sizeof(int), stream>>>(q);
+    }
     CB_CUDA(ctx, cudaGetLastError());
   }
   return CB_OK;

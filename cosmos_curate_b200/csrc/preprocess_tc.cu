@@ -8,7 +8,7 @@
 //   D[(row, colour plane), x] = sum_k  A[(row, colour plane), k] * (Wh[x, k] + Wl[x, k])
 //
 //   * A = the colour-converted pixels as fp16 (0..255 is exact in fp16), written by the SIMT threads straight into the
-//     128-byte-swizzled K-major UMMA layout.  The M dimension stacks 42 source rows x 3 colour planes = 126 of the 128 UMMA
+//     128-byte-swizzled K-major UMMA layout.  The M dimension stacks 40 source rows x 3 colour planes = 120 of the 128 UMMA
 //     rows, so one 128-row operand tile holds a whole unit of work and all three planes share the B operand (the weights).
 //   * B = the fp32 tap weights split into two fp16 terms (hi + lo, 22 significant bits: products with u8 pixels are exact in
 //     the fp32 accumulator, only the summation order differs from ATen's - the <= 1 LSB on <= 1e-4 of the pixels budget the
@@ -17,7 +17,7 @@
 //   * accumulators in TMEM (32 columns per CTA), read back with tcgen05.ld into a 64-row ring of filtered rows in shared memory;
 //     the vertical pass (17 % of the FMAs) stays on the FMA pipe in ATen's order, then round / clamp / store u8.
 //
-// A CTA owns (frame, 32 output columns) and walks the source rows top to bottom in units of 42 rows: TMA load of the NV12
+// A CTA owns (frame, 32 output columns) and walks the source rows top to bottom in units of 40 rows: TMA load of the NV12
 // window (Y + UV boxes) -> convert -> 28 MMAs -> epilogue -> vertical pass for the output rows that became complete.
 // ~100 KB of shared memory per CTA: two CTAs per SM overlap each other's phases.  Output: u8 [n][3][res][res]; normalisation +
 // patch packing is a second, bandwidth-trivial kernel (normalize_pack_kernel) so that this one stays small.
@@ -120,6 +120,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 
   constexpr uint32_t idesc = umma_idesc_f16(128, 16, 0);
   const int q4 = kw >> 2;
+  const int rp0 = tid / q4, xg0 = tid - rp0 * q4, drp = kTcThreads / q4, dxg = kTcThreads - drp * q4;  // item walk of the convert phase
+  const int plane_bytes = (ru >> 3) << 10;                                                             // ru rows = ru / 8 row groups of 1 KB
   const bool sws = a.colour == CB_FMT_NV12_SWS;
   int next_out = 0;
   for (int u = 0; u < a.n_units; ++u) {
@@ -128,8 +130,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     {
       const uint8_t* ry = sRaw;
       const uint8_t* ruv = sRaw + ru * kw;
-      for (int i = tid; i < (ru >> 1) * q4; i += kTcThreads) {
-        const int rp = i / q4, x = (i - rp * q4) << 2, r = rp << 1;
+      for (int rp = rp0, xg = xg0; rp < (ru >> 1);) {
+        const int x = xg << 2, r = rp << 1;
         const uint32_t yw[2] = {*reinterpret_cast<const uint32_t*>(ry + r * kw + x), *reinterpret_cast<const uint32_t*>(ry + (r + 1) * kw + x)};
         const uint32_t uv4 = *reinterpret_cast<const uint32_t*>(ruv + rp * kw + x);
         int px[2][4][3];
@@ -161,20 +163,23 @@ __global__ void __launch_bounds__(kTcThreads, 2)
             }
           }
         }
-        // operand address of (m, k): chunk of 64 k-elements, 8-row group, row, 16-byte unit XOR row (128-byte swizzle), element
-        const int koff = ((x >> 6) << 14), unit = (x & 63) >> 3, sub = (x & 7) << 1;
+        // operand address of (m, k): chunk of 64 k-elements, 8-row group, row, 16-byte unit XOR row (128-byte swizzle), element.
+        // ru is a multiple of 8, so the plane offset ch * ru only moves whole 8-row groups: one row offset serves the three planes.
+        const int koff = ((x >> 6) << 14) + ((x & 7) << 1), unit = (x & 63) >> 3;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
+          const int mr = r + rr;
+          uint8_t* row = sA + koff + ((mr >> 3) << 10) + ((mr & 7) << 7) + ((unit ^ (mr & 7)) << 4);
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
-            const int m = ch * ru + r + rr;
-            uint8_t* dst = sA + koff + ((m >> 3) << 10) + ((m & 7) << 7) + (((unit ^ (m & 7))) << 4) + sub;
             uint2 v;
             v.x = pack_u8_pair_f16(px[rr][0][ch], px[rr][1][ch]);
             v.y = pack_u8_pair_f16(px[rr][2][ch], px[rr][3][ch]);
-            *reinterpret_cast<uint2*>(dst) = v;
+            *reinterpret_cast<uint2*>(row + ch * plane_bytes) = v;
           }
         }
+        xg += dxg, rp += drp;
+        if (xg >= q4) xg -= q4, ++rp;
       }
     }
     fence_proxy_async();  // generic-proxy writes of the operand -> visible to the tensor core (async proxy)
@@ -218,18 +223,37 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     // ---- vertical pass for every output row whose taps are now complete (ATen order: first product, then FMAs), round half even
     {
       const int last = a.unit_last[u];
-      const int items = (last - next_out) * 3 * ncols;
-      for (int i = tid; i < items; i += kTcThreads) {
-        int x, t;
-        if (ncols == kNC) x = i & (kNC - 1), t = i >> 5;
-        else x = i % ncols, t = i / ncols;
-        const int yr = t / 3, ch = t - 3 * yr, y = next_out + yr;
-        const int y0 = a.ymin[y] - a.y_begin, nt = a.ysize[y];
-        const float* w = a.wy + (size_t)y * a.ty;
-        float acc = ring[(((y0 & (kRingRows - 1)) * 3 + ch) * kNC) + x] * w[0];
-        for (int k = 1; k < nt; ++k) acc = fmaf(ring[((((y0 + k) & (kRingRows - 1)) * 3 + ch) * kNC) + x], w[k], acc);
-        const int q = min(max(__float2int_rn(acc), 0), 255);
-        a.out[(((size_t)frame * 3 + ch) * a.res + y) * a.res + x0 + x] = (uint8_t)q;
+      if ((ncols & 3) == 0 && (a.res & 3) == 0) {  // four columns per thread: one 16-byte ring read feeds four FMAs, one 4-byte store
+        const int q = ncols >> 2, items = (last - next_out) * 3 * q;
+        for (int i = tid; i < items; i += kTcThreads) {
+          const int xq = i % q, t = i / q, yr = t / 3, ch = t - 3 * yr, y = next_out + yr;
+          const int nt = a.ysize[y];
+          const float* w = a.wy + (size_t)y * a.ty;
+          const float* col = ring + ch * kNC + 4 * xq;
+          int rr = (a.ymin[y] - a.y_begin) & (kRingRows - 1);
+          float4 v = *reinterpret_cast<const float4*>(col + rr * (3 * kNC));
+          float w0 = w[0];
+          float a0 = v.x * w0, a1 = v.y * w0, a2 = v.z * w0, a3 = v.w * w0;
+          for (int k = 1; k < nt; ++k) {
+            rr = (rr + 1) & (kRingRows - 1);
+            v = *reinterpret_cast<const float4*>(col + rr * (3 * kNC));
+            w0 = w[k];
+            a0 = fmaf(v.x, w0, a0), a1 = fmaf(v.y, w0, a1), a2 = fmaf(v.z, w0, a2), a3 = fmaf(v.w, w0, a3);
+          }
+          const uint32_t packed = (uint32_t)min(max(__float2int_rn(a0), 0), 255) | ((uint32_t)min(max(__float2int_rn(a1), 0), 255) << 8) |
+                                  ((uint32_t)min(max(__float2int_rn(a2), 0), 255) << 16) | ((uint32_t)min(max(__float2int_rn(a3), 0), 255) << 24);
+          *reinterpret_cast<uint32_t*>(a.out + (((size_t)frame * 3 + ch) * a.res + y) * a.res + x0 + 4 * xq) = packed;
+        }
+      } else {
+        const int items = (last - next_out) * 3 * ncols;
+        for (int i = tid; i < items; i += kTcThreads) {
+          const int x = i % ncols, t = i / ncols, yr = t / 3, ch = t - 3 * yr, y = next_out + yr;
+          const int y0 = a.ymin[y] - a.y_begin, nt = a.ysize[y];
+          const float* w = a.wy + (size_t)y * a.ty;
+          float acc = ring[(((y0 & (kRingRows - 1)) * 3 + ch) * kNC) + x] * w[0];
+          for (int k = 1; k < nt; ++k) acc = fmaf(ring[((((y0 + k) & (kRingRows - 1)) * 3 + ch) * kNC) + x], w[k], acc);
+          a.out[(((size_t)frame * 3 + ch) * a.res + y) * a.res + x0 + x] = (uint8_t)min(max(__float2int_rn(acc), 0), 255);
+        }
       }
       next_out = last;
     }
@@ -359,7 +383,7 @@ static const TcPlan* get_plan(cb_ctx* ctx, const TapTable* tx, const TapTable* t
     }
   }
   p.kw = (kw + 63) & ~63, p.kb = (kbmax + 63) & ~63;
-  p.ru = std::min(42, kRingRows - ty->max_taps + 1) & ~1;
+  p.ru = std::min(40, kRingRows - ty->max_taps + 1) & ~7;  // multiple of 8: a colour plane is a whole number of 8-row operand groups
   p.y_begin = ty->src_begin & ~1;
   p.n_units = p.ru > 0 ? (ty->src_end - p.y_begin + p.ru - 1) / p.ru : 0;
   const int b_tile = (p.kb / 64) * 2048;

@@ -35,6 +35,8 @@ namespace cb {
 
 constexpr int kNC = 32;          // output columns per CTA = two UMMA N-tiles of 16
 constexpr int kRingRows = 64;    // ring of horizontally filtered rows
+constexpr int kRingStride = 3 * kNC + 4;  // floats per ring row: +16 B so that the epilogue's row-per-lane 16-byte stores spread over the banks
+constexpr int kVRows = 16, kVTaps = 40;   // vertical-pass weights of one unit staged in shared memory (rows x taps)
 constexpr int kTcThreads = 256;
 
 struct TcArgs {
@@ -79,8 +81,10 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   uint8_t* sB = sA + kw * 256;       // [tile][hi | lo][kb / 64][16 rows][128 B]
   uint8_t* sRaw = sB + 4 * b_tile;   // ru luma rows then ru / 2 chroma rows, kw bytes each
   const int raw_bytes = (((ru + ru / 2) * kw) + 127) & ~127;
-  float* ring = reinterpret_cast<float*>(sRaw + raw_bytes);  // [kRingRows][3][kNC]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ring) + kRingRows * 3 * kNC * 4);
+  float* ring = reinterpret_cast<float*>(sRaw + raw_bytes);  // [kRingRows][kRingStride]: row = [3 planes][kNC] + pad
+  float* sW = ring + kRingRows * kRingStride;                 // [kVRows][kVTaps] vertical taps of the output rows this unit completes
+  int* sY = reinterpret_cast<int*>(sW + kVRows * kVTaps);     // [kVRows][2] first ring row, tap count
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sY + 2 * kVRows);
   uint64_t* raw_full = bars;
   uint64_t* mma_done = bars + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
@@ -125,6 +129,16 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const bool sws = a.colour == CB_FMT_NV12_SWS;
   int next_out = 0;
   for (int u = 0; u < a.n_units; ++u) {
+    {  // vertical taps of the output rows this unit will complete -> shared memory (global loads off the FMA loop's critical path)
+      const int last = a.unit_last[u], nrow = last - next_out;
+      if (nrow <= kVRows && a.ty <= kVTaps) {
+        for (int i = tid; i < nrow * a.ty; i += kTcThreads) {
+          const int rr = i / a.ty, k = i - rr * a.ty;
+          sW[rr * kVTaps + k] = a.wy[(size_t)(next_out + rr) * a.ty + k];
+        }
+        if (tid < nrow) sY[2 * tid] = (a.ymin[next_out + tid] - a.y_begin) & (kRingRows - 1), sY[2 * tid + 1] = a.ysize[next_out + tid];
+      }
+    }
     mbar_wait_parked(raw_full, u & 1, 2000);
     // ---- colour conversion straight into the A operand: a thread owns 2 rows x 4 pixels (two chroma samples)
     {
@@ -212,7 +226,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       const int l = lq * 32 + lane;
       if (l < 3 * ru) {
         const int ch = l / ru, r = l - ch * ru;
-        float4* dst = reinterpret_cast<float4*>(ring + ((((u * ru + r) & (kRingRows - 1)) * 3 + ch) * kNC + half * 16));
+        float4* dst = reinterpret_cast<float4*>(ring + ((u * ru + r) & (kRingRows - 1)) * kRingStride + ch * kNC + half * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
@@ -223,20 +237,21 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     // ---- vertical pass for every output row whose taps are now complete (ATen order: first product, then FMAs), round half even
     {
       const int last = a.unit_last[u];
-      if ((ncols & 3) == 0 && (a.res & 3) == 0) {  // four columns per thread: one 16-byte ring read feeds four FMAs, one 4-byte store
+      if ((ncols & 3) == 0 && (a.res & 3) == 0 && last - next_out <= kVRows && a.ty <= kVTaps) {
+        // four columns per thread: one 16-byte ring read feeds four FMAs, taps from shared memory, one 4-byte store
         const int q = ncols >> 2, items = (last - next_out) * 3 * q;
         for (int i = tid; i < items; i += kTcThreads) {
           const int xq = i % q, t = i / q, yr = t / 3, ch = t - 3 * yr, y = next_out + yr;
-          const int nt = a.ysize[y];
-          const float* w = a.wy + (size_t)y * a.ty;
+          const int nt = sY[2 * yr + 1];
+          const float* w = sW + yr * kVTaps;
           const float* col = ring + ch * kNC + 4 * xq;
-          int rr = (a.ymin[y] - a.y_begin) & (kRingRows - 1);
-          float4 v = *reinterpret_cast<const float4*>(col + rr * (3 * kNC));
+          int rr = sY[2 * yr];
+          float4 v = *reinterpret_cast<const float4*>(col + rr * kRingStride);
           float w0 = w[0];
           float a0 = v.x * w0, a1 = v.y * w0, a2 = v.z * w0, a3 = v.w * w0;
           for (int k = 1; k < nt; ++k) {
             rr = (rr + 1) & (kRingRows - 1);
-            v = *reinterpret_cast<const float4*>(col + rr * (3 * kNC));
+            v = *reinterpret_cast<const float4*>(col + rr * kRingStride);
             w0 = w[k];
             a0 = fmaf(v.x, w0, a0), a1 = fmaf(v.y, w0, a1), a2 = fmaf(v.z, w0, a2), a3 = fmaf(v.w, w0, a3);
           }
@@ -250,8 +265,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
           const int x = i % ncols, t = i / ncols, yr = t / 3, ch = t - 3 * yr, y = next_out + yr;
           const int y0 = a.ymin[y] - a.y_begin, nt = a.ysize[y];
           const float* w = a.wy + (size_t)y * a.ty;
-          float acc = ring[(((y0 & (kRingRows - 1)) * 3 + ch) * kNC) + x] * w[0];
-          for (int k = 1; k < nt; ++k) acc = fmaf(ring[((((y0 + k) & (kRingRows - 1)) * 3 + ch) * kNC) + x], w[k], acc);
+          float acc = ring[(y0 & (kRingRows - 1)) * kRingStride + ch * kNC + x] * w[0];
+          for (int k = 1; k < nt; ++k) acc = fmaf(ring[((y0 + k) & (kRingRows - 1)) * kRingStride + ch * kNC + x], w[k], acc);
           a.out[(((size_t)frame * 3 + ch) * a.res + y) * a.res + x0 + x] = (uint8_t)min(max(__float2int_rn(acc), 0), 255);
         }
       }
@@ -387,7 +402,7 @@ static const TcPlan* get_plan(cb_ctx* ctx, const TapTable* tx, const TapTable* t
   p.y_begin = ty->src_begin & ~1;
   p.n_units = p.ru > 0 ? (ty->src_end - p.y_begin + p.ru - 1) / p.ru : 0;
   const int b_tile = (p.kb / 64) * 2048;
-  const size_t smem = 1024 + (size_t)p.kw * 256 + 4 * (size_t)b_tile + ((((size_t)(p.ru + p.ru / 2) * p.kw) + 127) & ~(size_t)127) + kRingRows * 3 * kNC * 4 + 64;
+  const size_t smem = 1024 + (size_t)p.kw * 256 + 4 * (size_t)b_tile + ((((size_t)(p.ru + p.ru / 2) * p.kw) + 127) & ~(size_t)127) + (kRingRows * kRingStride + kVRows * kVTaps + 2 * kVRows) * 4 + 64;
   p.ok = p.ru >= 16 && p.kw <= 256 && smem <= 227 * 1024;  // TMA box <= 256 columns
   if (p.ok) {
     std::vector<uint16_t> w((size_t)p.n_slabs * 4 * b_tile / 2, 0);
@@ -473,7 +488,7 @@ int run_clip_preprocess_tc(cb_ctx* ctx, const cb_surface_pool* pool, const int* 
   a.x_lo = p->d_x_lo, a.tile_k0 = p->d_k0, a.tile_nk = p->d_nk, a.wtiles = p->d_w;
   a.ymin = ty->d_min, a.ysize = ty->d_size, a.unit_last = p->d_unit_last, a.wy = ty->d_w, a.ty = ty->max_taps, a.out = u8;
   const int b_tile = (p->kb / 64) * 2048;
-  const size_t smem = 1024 + (size_t)p->kw * 256 + 4 * (size_t)b_tile + ((((size_t)(p->ru + p->ru / 2) * p->kw) + 127) & ~(size_t)127) + kRingRows * 3 * kNC * 4 + 64;
+  const size_t smem = 1024 + (size_t)p->kw * 256 + 4 * (size_t)b_tile + ((((size_t)(p->ru + p->ru / 2) * p->kw) + 127) & ~(size_t)127) + (kRingRows * kRingStride + kVRows * kVTaps + 2 * kVRows) * 4 + 64;
   CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mark_launch(ctx, CB_PROF_PREPROCESS, stream);
   clip_preprocess_tc_kernel<<<dim3(p->n_slabs, n), kTcThreads, smem, stream>>>(map_y, map_uv, a);

@@ -128,17 +128,61 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const int plane_bytes = (ru >> 3) << 10;                                                             // ru rows = ru / 8 row groups of 1 KB
   const bool sws = a.colour == CB_FMT_NV12_SWS;
   int next_out = 0;
-  for (int u = 0; u < a.n_units; ++u) {
-    {  // vertical taps of the output rows this unit will complete -> shared memory (global loads off the FMA loop's critical path)
-      const int last = a.unit_last[u], nrow = last - next_out;
-      if (nrow <= kVRows && a.ty <= kVTaps) {
-        for (int i = tid; i < nrow * a.ty; i += kTcThreads) {
-          const int rr = i / a.ty, k = i - rr * a.ty;
-          sW[rr * kVTaps + k] = a.wy[(size_t)(next_out + rr) * a.ty + k];
+  // vertical taps of the output rows unit `uv` completes -> shared memory (global loads off the FMA loop's critical path)
+  auto stage_taps = [&](int uv) {
+    const int last = a.unit_last[uv], nrow = last - next_out;
+    if (nrow <= kVRows && a.ty <= kVTaps) {
+      for (int i = tid; i < nrow * a.ty; i += kTcThreads) {
+        const int rr = i / a.ty, k = i - rr * a.ty;
+        sW[rr * kVTaps + k] = a.wy[(size_t)(next_out + rr) * a.ty + k];
+      }
+      if (tid < nrow) sY[2 * tid] = (a.ymin[next_out + tid] - a.y_begin) & (kRingRows - 1), sY[2 * tid + 1] = a.ysize[next_out + tid];
+    }
+  };
+  // vertical pass for the output rows completed by unit `uv` (ATen order: first product, then FMAs), round half even.  It runs while
+  // the NEXT unit's MMAs are in flight (their issue-to-commit latency, ~2 k cycles of dependent accumulation, used to be a sleep).
+  auto vertical = [&](int uv) {
+    const int u = uv;
+    (void)u;
+
+    const int last = a.unit_last[u];
+    if ((ncols & 3) == 0 && (a.res & 3) == 0 && last - next_out <= kVRows && a.ty <= kVTaps) {
+      // four columns per thread: one 16-byte ring read feeds four FMAs, taps from shared memory, one 4-byte store
+      const int q = ncols >> 2, items = (last - next_out) * 3 * q;
+      for (int i = tid; i < items; i += kTcThreads) {
+        const int xq = i % q, t = i / q, yr = t / 3, ch = t - 3 * yr, y = next_out + yr;
+        const int nt = sY[2 * yr + 1];
+        const float* w = sW + yr * kVTaps;
+        const float* col = ring + ch * kNC + 4 * xq;
+        int rr = sY[2 * yr];
+        float4 v = *reinterpret_cast<const float4*>(col + rr * kRingStride);
+        float w0 = w[0];
+        float a0 = v.x * w0, a1 = v.y * w0, a2 = v.z * w0, a3 = v.w * w0;
+        for (int k = 1; k < nt; ++k) {
+          rr = (rr + 1) & (kRingRows - 1);
+          v = *reinterpret_cast<const float4*>(col + rr * kRingStride);
+          w0 = w[k];
+          a0 = fmaf(v.x, w0, a0), a1 = fmaf(v.y, w0, a1), a2 = fmaf(v.z, w0, a2), a3 = fmaf(v.w, w0, a3);
         }
-        if (tid < nrow) sY[2 * tid] = (a.ymin[next_out + tid] - a.y_begin) & (kRingRows - 1), sY[2 * tid + 1] = a.ysize[next_out + tid];
+        const uint32_t packed = (uint32_t)min(max(__float2int_rn(a0), 0), 255) | ((uint32_t)min(max(__float2int_rn(a1), 0), 255) << 8) |
+                                ((uint32_t)min(max(__float2int_rn(a2), 0), 255) << 16) | ((uint32_t)min(max(__float2int_rn(a3), 0), 255) << 24);
+        *reinterpret_cast<uint32_t*>(a.out + (((size_t)frame * 3 + ch) * a.res + y) * a.res + x0 + 4 * xq) = packed;
+      }
+    } else {
+      const int items = (last - next_out) * 3 * ncols;
+      for (int i = tid; i < items; i += kTcThreads) {
+        const int x = i % ncols, t = i / ncols, yr = t / 3, ch = t - 3 * yr, y = next_out + yr;
+        const int y0 = a.ymin[y] - a.y_begin, nt = a.ysize[y];
+        const float* w = a.wy + (size_t)y * a.ty;
+        float acc = ring[(y0 & (kRingRows - 1)) * kRingStride + ch * kNC + x] * w[0];
+        for (int k = 1; k < nt; ++k) acc = fmaf(ring[((y0 + k) & (kRingRows - 1)) * kRingStride + ch * kNC + x], w[k], acc);
+        a.out[(((size_t)frame * 3 + ch) * a.res + y) * a.res + x0 + x] = (uint8_t)min(max(__float2int_rn(acc), 0), 255);
       }
     }
+    next_out = last;
+  };
+  for (int u = 0; u < a.n_units; ++u) {
+    if (u > 0) stage_taps(u - 1);  // for the vertical pass of the previous unit, which runs below while this unit's MMAs execute
     mbar_wait_parked(raw_full, u & 1, 2000);
     // ---- colour conversion straight into the A operand: a thread owns 2 rows x 4 pixels (two chroma samples)
     {
@@ -215,6 +259,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       }
       umma_commit(mma_done);
     }
+    if (u > 0) vertical(u - 1);
+    __syncthreads();  // the epilogue below overwrites ring rows the vertical pass was still reading
     mbar_wait_parked(mma_done, u & 1, 2000);  // 255 threads have nothing to do until the MMAs land: do not burn the co-resident CTA's issue slots
     tc_fence_after();
     // ---- epilogue: the filtered rows of this unit -> ring (warp = lane quarter x N-tile)
@@ -234,46 +280,11 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     }
     tc_fence_before();
     __syncthreads();
-    // ---- vertical pass for every output row whose taps are now complete (ATen order: first product, then FMAs), round half even
-    {
-      const int last = a.unit_last[u];
-      if ((ncols & 3) == 0 && (a.res & 3) == 0 && last - next_out <= kVRows && a.ty <= kVTaps) {
-        // four columns per thread: one 16-byte ring read feeds four FMAs, taps from shared memory, one 4-byte store
-        const int q = ncols >> 2, items = (last - next_out) * 3 * q;
-        for (int i = tid; i < items; i += kTcThreads) {
-          const int xq = i % q, t = i / q, yr = t / 3, ch = t - 3 * yr, y = next_out + yr;
-          const int nt = sY[2 * yr + 1];
-          const float* w = sW + yr * kVTaps;
-          const float* col = ring + ch * kNC + 4 * xq;
-          int rr = sY[2 * yr];
-          float4 v = *reinterpret_cast<const float4*>(col + rr * kRingStride);
-          float w0 = w[0];
-          float a0 = v.x * w0, a1 = v.y * w0, a2 = v.z * w0, a3 = v.w * w0;
-          for (int k = 1; k < nt; ++k) {
-            rr = (rr + 1) & (kRingRows - 1);
-            v = *reinterpret_cast<const float4*>(col + rr * kRingStride);
-            w0 = w[k];
-            a0 = fmaf(v.x, w0, a0), a1 = fmaf(v.y, w0, a1), a2 = fmaf(v.z, w0, a2), a3 = fmaf(v.w, w0, a3);
-          }
-          const uint32_t packed = (uint32_t)min(max(__float2int_rn(a0), 0), 255) | ((uint32_t)min(max(__float2int_rn(a1), 0), 255) << 8) |
-                                  ((uint32_t)min(max(__float2int_rn(a2), 0), 255) << 16) | ((uint32_t)min(max(__float2int_rn(a3), 0), 255) << 24);
-          *reinterpret_cast<uint32_t*>(a.out + (((size_t)frame * 3 + ch) * a.res + y) * a.res + x0 + 4 * xq) = packed;
-        }
-      } else {
-        const int items = (last - next_out) * 3 * ncols;
-        for (int i = tid; i < items; i += kTcThreads) {
-          const int x = i % ncols, t = i / ncols, yr = t / 3, ch = t - 3 * yr, y = next_out + yr;
-          const int y0 = a.ymin[y] - a.y_begin, nt = a.ysize[y];
-          const float* w = a.wy + (size_t)y * a.ty;
-          float acc = ring[(y0 & (kRingRows - 1)) * kRingStride + ch * kNC + x] * w[0];
-          for (int k = 1; k < nt; ++k) acc = fmaf(ring[((y0 + k) & (kRingRows - 1)) * kRingStride + ch * kNC + x], w[k], acc);
-          a.out[(((size_t)frame * 3 + ch) * a.res + y) * a.res + x0 + x] = (uint8_t)min(max(__float2int_rn(acc), 0), 255);
-        }
-      }
-      next_out = last;
-    }
-    __syncthreads();
   }
+  stage_taps(a.n_units - 1);
+  __syncthreads();
+  vertical(a.n_units - 1);
+  __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 32);
 }
 

@@ -18,7 +18,7 @@ Printed JSON line (rank 0):
           (one call = `--tasks-per-call` tasks x clips-per-step clips); MP4 index + NVDEC decode of every frame up to the last
           sampled one (the reference's decode semantics) + fused preprocess + tower + pinned D2H of scores/embeddings, the decode /
           tower overlap happening inside the stage; wall clock between device synchronisations, max over ranks.
-  e2e_keyframe_seek  the same call with the stage's default seek_keyframes=True (identical frames, only GOPs with sampled frames).
+  e2e_keyframe_seek  the same call with seek_keyframes=True (opt-in: identical frames, only GOPs with sampled frames are decoded).
   roofline      the dominant kernel (tcgen05 GEMM): algorithmic FLOPs per launch / CUDA-event time per launch vs the
                 measured sustained bf16 peak (MEASURED_PEAKS.json); roofline_other has preprocess / LayerNorm (HBM).
   cpu_baseline  the oracle's CPU restatement of the reference path timed on the host cores (N=1, rank 0), bounded sample.
@@ -381,9 +381,9 @@ def run_b200(args) -> None:
                        "e2e_fraction_of_decode_ceiling": (e2e["decoded_frames_per_sec"] / world) / ceil_fps if ceil_fps > 0 else None,
                        "real_content": real}  # fmt: skip
             stage.destroy()
-            stage2 = make_stage(seek=True)  # the stage's default
+            stage2 = make_stage(seek=True)  # opt-in mode of the same stage
             e2e_sparse = e2e_measure(stage2, args.e2e_steps)
-            e2e_sparse["note"] = "CB_DECODE_SEEK_SYNC (stage default): only GOPs holding sampled frames are decoded (identical frames); closed GOP = 30, 1 fps sampling"
+            e2e_sparse["note"] = "seek_keyframes=True (CB_DECODE_SEEK_SYNC): only GOPs holding sampled frames are decoded (identical frames); closed GOP = 30, 1 fps sampling"
             if world > 1:
                 # the one exchange step of the design (BASELINE.json C3/C4): NCCL all-gather of the clip embeddings, then cosine dedup
                 from cosmos_curate_b200.dedup import semdedup_cluster

@@ -37,7 +37,7 @@ constexpr int kNC = 32;          // output columns per CTA = two UMMA N-tiles of
 constexpr int kRingRows = 64;    // ring of horizontally filtered rows
 constexpr int kRingStride = 3 * kNC + 4;  // floats per ring row: +16 B so that the epilogue's row-per-lane 16-byte stores spread over the banks
 constexpr int kVRows = 16, kVTaps = 40;   // vertical-pass weights of one unit staged in shared memory (rows x taps)
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 320;  // 10 warps: 20 row pairs x kw / 4 column groups of the convert phase divide evenly (kw = 128 / 192 / 256)
 
 struct TcArgs {
   const int* slots;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     mbar_wait_parked(mma_done, u & 1, 2000);  // 255 threads have nothing to do until the MMAs land: do not burn the co-resident CTA's issue slots
     tc_fence_after();
     // ---- epilogue: the filtered rows of this unit -> ring (warp = lane quarter x N-tile)
-    {
+    if (warp < 8) {
       const int lq = warp & 3, half = warp >> 2;
       uint32_t v[16];
       tmem_ld_32x32b_x16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(half * 16), v);

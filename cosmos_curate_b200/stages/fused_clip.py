@@ -51,7 +51,7 @@ class NvdecClipAestheticStage(CuratorStage):
         max_batch: int = 256,
         num_decoders: int = 20,
         stage_batch_size: int = 8,
-        seek_keyframes: bool = True,
+        seek_keyframes: bool = False,
         source: Literal["clip", "video_span"] = "clip",
         target_res: tuple[int, int] | None = None,
         cubic_mode: str | None = None,
@@ -65,7 +65,10 @@ class NvdecClipAestheticStage(CuratorStage):
         self._num_gpus_per_worker = num_gpus_per_worker
         self._write_embedding, self._max_batch, self._num_decoders = write_embedding, max_batch, num_decoders
         self._stage_batch_size, self._verbose, self._log_stats = stage_batch_size, verbose, log_stats
-        self._seek = seek_keyframes  # decode only the GOPs that contain sampled frames (identical frames, fewer decoded)
+        # False (default): every frame up to the last sampled one is decoded, the reference's decode work (decoder_utils.py:439-455) and
+        # what bench.py's headline `e2e` times.  True: only the GOPs that hold sampled frames are decoded - bit-identical frames
+        # (tested), 5x the clips/s on 1 fps sampling of GOP-30 clips; recommended in INTEGRATION.md, reported as `e2e_keyframe_seek`.
+        self._seek = seek_keyframes
         if source not in ("clip", "video_span"):
             error_msg = f"source={source!r} not in ('clip', 'video_span')"
             raise ValueError(error_msg)

@@ -389,3 +389,23 @@ def test_fused_stage_embedding_only_with_siglip_tower(ctx):
     assert np.array_equal(e, task.video.clips[1].openai_embedding)
     with pytest.raises(ValueError):
         NvdecClipAestheticStage(score_threshold=0.5, write_embedding=True, model=SigLIPImageEmbeddings(seed=5, config=cfg)).stage_setup()
+
+
+def test_fused_stage_keyframe_seek_gives_identical_results(ctx):
+    """seek_keyframes=True decodes only the GOPs that hold sampled frames; scores and embeddings are bitwise those of the default
+    (every frame decoded, the reference's decode work) - on a multi-GOP residual-coded clip."""
+    from cosmos_curate_b200.stages import NvdecClipAestheticStage
+    from tools import synth_h264
+
+    clip = synth_h264.make_coded_clip(640, 368, 30, 6.0, seed=17, bitrate=1.5e6)
+    model, cfg, w, sd = _model()
+    out = {}
+    for seek in (False, True):
+        task = _clip_task(clip, n_clips=3)
+        st = NvdecClipAestheticStage(score_threshold=-100.0, reduction="mean", write_embedding=True, max_batch=32, num_decoders=3, seek_keyframes=seek, model=model)
+        st.stage_setup()
+        st.process_data([task])
+        out[seek] = ([c.aesthetic_score for c in task.video.clips], [c.openai_embedding for c in task.video.clips], st.last_call_stats["frames_decoded"])
+        st.destroy()
+    assert out[False][0] == out[True][0] and all(np.array_equal(a, b) for a, b in zip(out[False][1], out[True][1]))
+    assert out[True][2] < out[False][2] == 3 * 180  # 7 sampled frames per clip: the seek mode skips most of every GOP

@@ -41,7 +41,7 @@ constexpr int kTcThreads = 320;  // 10 warps: 20 row pairs x kw / 4 column group
 
 struct TcArgs {
   const int* slots;
-  int n, res, ru, n_units, y_begin, kw, kb, colour;
+  int n, res, ru, n_units, y_begin, kw, kb, colour, wait_ns;
   const int* x_lo;         // [n_slabs] first source column of the slab window (multiple of 16)
   const int* tile_k0;      // [n_slabs * 2] first k-step (16 source columns) of the N-tile inside the window
   const int* tile_nk;      // [n_slabs * 2] k-steps of the N-tile (0 = tile beyond the image)
@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   };
   for (int u = 0; u < a.n_units; ++u) {
     if (u > 0) stage_taps(u - 1);  // for the vertical pass of the previous unit, which runs below while this unit's MMAs execute
-    mbar_wait_parked(raw_full, u & 1, 2000);
+    if (a.wait_ns) mbar_wait_parked(raw_full, u & 1, a.wait_ns);
+    else mbar_wait(raw_full, u & 1);
     // ---- colour conversion straight into the A operand: a thread owns 2 rows x 4 pixels (two chroma samples)
     {
       const uint8_t* ry = sRaw;
@@ -261,7 +262,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     }
     if (u > 0) vertical(u - 1);
     __syncthreads();  // the epilogue below overwrites ring rows the vertical pass was still reading
-    mbar_wait_parked(mma_done, u & 1, 2000);  // 255 threads have nothing to do until the MMAs land: do not burn the co-resident CTA's issue slots
+    if (a.wait_ns) mbar_wait_parked(mma_done, u & 1, a.wait_ns);  // suspend-time hint: do not burn the co-resident CTA's issue slots
+    else mbar_wait(mma_done, u & 1);
     tc_fence_after();
     // ---- epilogue: the filtered rows of this unit -> ring (warp = lane quarter x N-tile)
     if (warp < 8) {
@@ -496,6 +498,10 @@ int run_clip_preprocess_tc(cb_ctx* ctx, const cb_surface_pool* pool, const int* 
   TcArgs a{};
   a.slots = d_slots, a.n = n, a.res = res, a.ru = p->ru, a.n_units = p->n_units, a.y_begin = p->y_begin, a.kw = p->kw, a.kb = p->kb;
   a.colour = pool->format;
+  {
+    const char* w = getenv("CB_PRE_WAIT_NS");  // A/B switch for the mbarrier waits: 0 = spin, else try_wait suspend-time hint in ns
+    a.wait_ns = w ? atoi(w) : 2000;
+  }
   a.x_lo = p->d_x_lo, a.tile_k0 = p->d_k0, a.tile_nk = p->d_nk, a.wtiles = p->d_w;
   a.ymin = ty->d_min, a.ysize = ty->d_size, a.unit_last = p->d_unit_last, a.wy = ty->d_w, a.ty = ty->max_taps, a.out = u8;
   const int b_tile = (p->kb / 64) * 2048;

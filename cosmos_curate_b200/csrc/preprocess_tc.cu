@@ -14,7 +14,7 @@
 //     the fp32 accumulator, only the summation order differs from ATen's - the <= 1 LSB on <= 1e-4 of the pixels budget the
 //     fp32 paths already share).  An N-tile is 16 output columns; its K window is the ~100 source columns those columns
 //     tap (7 k-steps of 16), so the band is ~70 % dense instead of a dense 1080-wide GEMM.
-//   * accumulators in TMEM (32 columns per CTA), read back with tcgen05.ld into a 64-row ring of filtered rows in shared memory;
+//   * accumulators in TMEM (64 columns per CTA: N-tile x weight term, four independent accumulation chains), read back with tcgen05.ld into a 64-row ring of filtered rows in shared memory;
 //     the vertical pass (17 % of the FMAs) stays on the FMA pipe in ATen's order, then round / clamp / store u8.
 //
 // A CTA owns (frame, 32 output columns) and walks the source rows top to bottom in units of 40 rows: TMA load of the NV12
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     tma_prefetch_desc(&map_y), tma_prefetch_desc(&map_uv);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 32);
+    tmem_alloc(tmem_slot, 64);
     tmem_relinquish();
   }
   {
@@ -246,15 +246,21 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     if (tid == 0) {
       if (u + 1 < a.n_units) issue(u + 1);  // the raw window is free again
       tc_fence_after();
+      // Four independent accumulators - (N-tile, weight term) - interleaved k-step by k-step: a chain of accumulations into ONE
+      // TMEM tile serialises on the MMA pipeline latency (measured: 28 back-to-back dependent MMAs cost ~3.5 k cycles, 44 % of the
+      // warp samples slept on the commit barrier); hi and lo partial sums are added in the epilogue instead.
+      const int nk0 = a.tile_nk[slab * 2], nk1 = a.tile_nk[slab * 2 + 1], k00 = a.tile_k0[slab * 2], k01 = a.tile_k0[slab * 2 + 1];
+      const int nkm = nk0 > nk1 ? nk0 : nk1;
+      for (int kk = 0; kk < nkm; ++kk) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int nk = a.tile_nk[slab * 2 + j], k0 = a.tile_k0[slab * 2 + j];
-        for (int hl = 0; hl < 2; ++hl) {
-          for (int kk = 0; kk < nk; ++kk) {
-            const int qa = k0 + kk;
-            const uint64_t da = umma_desc_sw128(smem_u32(sA) + (uint32_t)((qa >> 2) << 14) + (uint32_t)((qa & 3) << 5));
+        for (int j = 0; j < 2; ++j) {
+          if (kk >= (j ? nk1 : nk0)) continue;
+          const int qa = (j ? k01 : k00) + kk;
+          const uint64_t da = umma_desc_sw128(smem_u32(sA) + (uint32_t)((qa >> 2) << 14) + (uint32_t)((qa & 3) << 5));
+#pragma unroll
+          for (int hl = 0; hl < 2; ++hl) {
             const uint64_t db = umma_desc_sw128(smem_u32(sB) + (uint32_t)((j * 2 + hl) * b_tile) + (uint32_t)((kk >> 2) << 11) + (uint32_t)((kk & 3) << 5));
-            umma_f16(tmem + (uint32_t)(j * 16), da, db, idesc, (hl | kk) != 0);
+            umma_f16(tmem + (uint32_t)((j * 2 + hl) * 16), da, db, idesc, kk != 0);
           }
         }
       }
@@ -268,8 +274,9 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     // ---- epilogue: the filtered rows of this unit -> ring (warp = lane quarter x N-tile)
     if (warp < 8) {
       const int lq = warp & 3, half = warp >> 2;
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(half * 16), v);
+      uint32_t v[16], vl[16];
+      tmem_ld_32x32b_x16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(half * 32), v);        // hi-weight partial sums
+      tmem_ld_32x32b_x16(tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(half * 32 + 16), vl);  // lo-weight partial sums
       tmem_ld_wait();
       const int l = lq * 32 + lane;
       if (l < 3 * ru) {
@@ -277,7 +284,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         float4* dst = reinterpret_cast<float4*>(ring + ((u * ru + r) & (kRingRows - 1)) * kRingStride + ch * kNC + half * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          dst[q] = make_float4(__uint_as_float(v[4 * q]) + __uint_as_float(vl[4 * q]), __uint_as_float(v[4 * q + 1]) + __uint_as_float(vl[4 * q + 1]),
+                               __uint_as_float(v[4 * q + 2]) + __uint_as_float(vl[4 * q + 2]), __uint_as_float(v[4 * q + 3]) + __uint_as_float(vl[4 * q + 3]));
       }
     }
     tc_fence_before();
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   __syncthreads();
   vertical(a.n_units - 1);
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 32);
+  if (warp == 1) tmem_dealloc(tmem, 64);
 }
 
 // u8 [n][3][res][res] -> normalised output: typed NCHW (mode 1) or zero-padded patch rows [n][(res/p)^2][k_pad] (mode 2)

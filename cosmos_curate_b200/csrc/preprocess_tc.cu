@@ -36,6 +36,7 @@ namespace cb {
 constexpr int kNC = 32;          // output columns per CTA = two UMMA N-tiles of 16
 constexpr int kRingRows = 64;    // ring of horizontally filtered rows
 constexpr int kRingStride = 3 * kNC + 4;  // floats per ring row: +16 B so that the epilogue's row-per-lane 16-byte stores spread over the banks
+constexpr int kMaxUnits = 128;            // units per frame column (4K: 55)
 constexpr int kVRows = 16, kVTaps = 40;   // vertical-pass weights of one unit staged in shared memory (rows x taps)
 constexpr int kTcThreads = 320;  // 10 warps: 20 row pairs x kw / 4 column groups of the convert phase divide evenly (kw = 128 / 192 / 256)
 
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   float* ring = reinterpret_cast<float*>(sRaw + raw_bytes);  // [kRingRows][kRingStride]: row = [3 planes][kNC] + pad
   float* sW = ring + kRingRows * kRingStride;                 // [kVRows][kVTaps] vertical taps of the output rows this unit completes
   int* sY = reinterpret_cast<int*>(sW + kVRows * kVTaps);     // [kVRows][2] first ring row, tap count
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sY + 2 * kVRows);
+  int* sUL = sY + 2 * kVRows;                                 // [kMaxUnits] copy of unit_last (a global load per phase would sit on the critical path)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sUL + kMaxUnits);
   uint64_t* raw_full = bars;
   uint64_t* mma_done = bars + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     const uint4* src = reinterpret_cast<const uint4*>(a.wtiles + (size_t)slab * 4 * b_tile);
     uint4* dst = reinterpret_cast<uint4*>(sB);
     for (int i = tid; i < (4 * b_tile) >> 4; i += kTcThreads) dst[i] = src[i];
+    for (int i = tid; i < a.n_units; i += kTcThreads) sUL[i] = a.unit_last[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -123,6 +126,11 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   if (tid == 0) issue(0);
 
   constexpr uint32_t idesc = umma_idesc_f16(128, 16, 0);
+  // per-CTA constants of the MMA issuer: k-step windows of the two N-tiles and the operand descriptor bases (16-byte units)
+  const int nk0 = a.tile_nk[slab * 2], nk1 = a.tile_nk[slab * 2 + 1], k00 = a.tile_k0[slab * 2], k01 = a.tile_k0[slab * 2 + 1];
+  const int nkm = nk0 > nk1 ? nk0 : nk1;
+  const uint64_t desc_a0 = umma_desc_sw128(smem_u32(sA)), desc_b0 = umma_desc_sw128(smem_u32(sB));
+  const uint32_t b_tile16 = (uint32_t)b_tile >> 4;
   const int q4 = kw >> 2;
   const int rp0 = tid / q4, xg0 = tid - rp0 * q4, drp = kTcThreads / q4, dxg = kTcThreads - drp * q4;  // item walk of the convert phase
   const int plane_bytes = (ru >> 3) << 10;                                                             // ru rows = ru / 8 row groups of 1 KB
@@ -130,8 +138,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   int next_out = 0;
   // vertical taps of the output rows unit `uv` completes -> shared memory (global loads off the FMA loop's critical path)
   auto stage_taps = [&](int uv) {
-    const int last = a.unit_last[uv], nrow = last - next_out;
-    if (nrow <= kVRows && a.ty <= kVTaps) {
+    const int last = sUL[uv], nrow = last - next_out;
+    if (nrow > 0 && nrow <= kVRows && a.ty <= kVTaps) {
       for (int i = tid; i < nrow * a.ty; i += kTcThreads) {
         const int rr = i / a.ty, k = i - rr * a.ty;
         sW[rr * kVTaps + k] = a.wy[(size_t)(next_out + rr) * a.ty + k];
@@ -145,7 +153,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     const int u = uv;
     (void)u;
 
-    const int last = a.unit_last[u];
+    const int last = sUL[u];
     if ((ncols & 3) == 0 && (a.res & 3) == 0 && last - next_out <= kVRows && a.ty <= kVTaps) {
       // four columns per thread: one 16-byte ring read feeds four FMAs, taps from shared memory, one 4-byte store
       const int q = ncols >> 2, items = (last - next_out) * 3 * q;
@@ -249,19 +257,15 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       // Four independent accumulators - (N-tile, weight term) - interleaved k-step by k-step: a chain of accumulations into ONE
       // TMEM tile serialises on the MMA pipeline latency (measured: 28 back-to-back dependent MMAs cost ~3.5 k cycles, 44 % of the
       // warp samples slept on the commit barrier); hi and lo partial sums are added in the epilogue instead.
-      const int nk0 = a.tile_nk[slab * 2], nk1 = a.tile_nk[slab * 2 + 1], k00 = a.tile_k0[slab * 2], k01 = a.tile_k0[slab * 2 + 1];
-      const int nkm = nk0 > nk1 ? nk0 : nk1;
       for (int kk = 0; kk < nkm; ++kk) {
+        const uint64_t kb_off = (uint64_t)(((kk >> 2) << 7) + ((kk & 3) << 1));  // chunk of 64 k: 2048 B, k-step: 32 B
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           if (kk >= (j ? nk1 : nk0)) continue;
           const int qa = (j ? k01 : k00) + kk;
-          const uint64_t da = umma_desc_sw128(smem_u32(sA) + (uint32_t)((qa >> 2) << 14) + (uint32_t)((qa & 3) << 5));
+          const uint64_t da = desc_a0 + (uint64_t)(((qa >> 2) << 10) + ((qa & 3) << 1));  // chunk: 16384 B
 #pragma unroll
-          for (int hl = 0; hl < 2; ++hl) {
-            const uint64_t db = umma_desc_sw128(smem_u32(sB) + (uint32_t)((j * 2 + hl) * b_tile) + (uint32_t)((kk >> 2) << 11) + (uint32_t)((kk & 3) << 5));
-            umma_f16(tmem + (uint32_t)((j * 2 + hl) * 16), da, db, idesc, kk != 0);
-          }
+          for (int hl = 0; hl < 2; ++hl) umma_f16(tmem + (uint32_t)((j * 2 + hl) * 16), da, desc_b0 + (uint64_t)((j * 2 + hl) * b_tile16) + kb_off, idesc, kk != 0);
         }
       }
       umma_commit(mma_done);
@@ -423,8 +427,8 @@ static const TcPlan* get_plan(cb_ctx* ctx, const TapTable* tx, const TapTable* t
   p.y_begin = ty->src_begin & ~1;
   p.n_units = p.ru > 0 ? (ty->src_end - p.y_begin + p.ru - 1) / p.ru : 0;
   const int b_tile = (p.kb / 64) * 2048;
-  const size_t smem = 1024 + (size_t)p.kw * 256 + 4 * (size_t)b_tile + ((((size_t)(p.ru + p.ru / 2) * p.kw) + 127) & ~(size_t)127) + (kRingRows * kRingStride + kVRows * kVTaps + 2 * kVRows) * 4 + 64;
-  p.ok = p.ru >= 16 && p.kw <= 256 && smem <= 227 * 1024;  // TMA box <= 256 columns
+  const size_t smem = 1024 + (size_t)p.kw * 256 + 4 * (size_t)b_tile + ((((size_t)(p.ru + p.ru / 2) * p.kw) + 127) & ~(size_t)127) + (kRingRows * kRingStride + kVRows * kVTaps + 2 * kVRows + kMaxUnits) * 4 + 64;
+  p.ok = p.ru >= 16 && p.kw <= 256 && p.n_units <= kMaxUnits && smem <= 227 * 1024;  // TMA box <= 256 columns
   if (p.ok) {
     std::vector<uint16_t> w((size_t)p.n_slabs * 4 * b_tile / 2, 0);
     for (int s = 0; s < p.n_slabs; ++s)
@@ -513,7 +517,7 @@ int run_clip_preprocess_tc(cb_ctx* ctx, const cb_surface_pool* pool, const int* 
   a.x_lo = p->d_x_lo, a.tile_k0 = p->d_k0, a.tile_nk = p->d_nk, a.wtiles = p->d_w;
   a.ymin = ty->d_min, a.ysize = ty->d_size, a.unit_last = p->d_unit_last, a.wy = ty->d_w, a.ty = ty->max_taps, a.out = u8;
   const int b_tile = (p->kb / 64) * 2048;
-  const size_t smem = 1024 + (size_t)p->kw * 256 + 4 * (size_t)b_tile + ((((size_t)(p->ru + p->ru / 2) * p->kw) + 127) & ~(size_t)127) + (kRingRows * kRingStride + kVRows * kVTaps + 2 * kVRows) * 4 + 64;
+  const size_t smem = 1024 + (size_t)p->kw * 256 + 4 * (size_t)b_tile + ((((size_t)(p->ru + p->ru / 2) * p->kw) + 127) & ~(size_t)127) + (kRingRows * kRingStride + kVRows * kVTaps + 2 * kVRows + kMaxUnits) * 4 + 64;
   CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mark_launch(ctx, CB_PROF_PREPROCESS, stream);
   clip_preprocess_tc_kernel<<<dim3(p->n_slabs, n), kTcThreads, smem, stream>>>(map_y, map_uv, a);

@@ -46,7 +46,7 @@ struct TcArgs {
   const int* x_lo;         // [n_slabs] first source column of the slab window (multiple of 16)
   const int* tile_k0;      // [n_slabs * 2] first k-step (16 source columns) of the N-tile inside the window
   const int* tile_nk;      // [n_slabs * 2] k-steps of the N-tile (0 = tile beyond the image)
-  const uint8_t* wtiles;   // [n_slabs][2 tiles][hi | lo][kb / 64][2048 B] fp16, already in the swizzled UMMA layout
+  const uint8_t* wtiles;   // [n_slabs][2 tiles][kb / 64][32 rows (hi | lo)][128 B] fp16, already in the swizzled UMMA layout
   const int *ymin, *ysize;
   const int* unit_last;    // [n_units] output rows complete once unit u has been filtered
   const float* wy;
@@ -77,10 +77,10 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const int kw = a.kw, ru = a.ru;
-  const int b_tile = (a.kb >> 6) * 2048;
+  const int b_tile = (a.kb >> 6) * 4096;  // one N-tile of the B operand: 32 rows (16 columns x {hi, lo} weight term) x kb
   uint8_t* sA = smem;                // [kw / 64][16 row groups][8 rows][128 B]
-  uint8_t* sB = sA + kw * 256;       // [tile][hi | lo][kb / 64][16 rows][128 B]
-  uint8_t* sRaw = sB + 4 * b_tile;   // ru luma rows then ru / 2 chroma rows, kw bytes each
+  uint8_t* sB = sA + kw * 256;       // [tile][kb / 64][32 rows: hi 0..15 | lo 16..31][128 B]
+  uint8_t* sRaw = sB + 2 * b_tile;   // ru luma rows then ru / 2 chroma rows, kw bytes each
   const int raw_bytes = (((ru + ru / 2) * kw) + 127) & ~127;
   float* ring = reinterpret_cast<float*>(sRaw + raw_bytes);  // [kRingRows][kRingStride]: row = [3 planes][kNC] + pad
   float* sW = ring + kRingRows * kRingStride;                 // [kVRows][kVTaps] vertical taps of the output rows this unit completes
@@ -107,9 +107,9 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     tmem_relinquish();
   }
   {
-    const uint4* src = reinterpret_cast<const uint4*>(a.wtiles + (size_t)slab * 4 * b_tile);
+    const uint4* src = reinterpret_cast<const uint4*>(a.wtiles + (size_t)slab * 2 * b_tile);
     uint4* dst = reinterpret_cast<uint4*>(sB);
-    for (int i = tid; i < (4 * b_tile) >> 4; i += kTcThreads) dst[i] = src[i];
+    for (int i = tid; i < (2 * b_tile) >> 4; i += kTcThreads) dst[i] = src[i];
     for (int i = tid; i < a.n_units; i += kTcThreads) sUL[i] = a.unit_last[i];
   }
   tc_fence_before();
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   };
   if (tid == 0) issue(0);
 
-  constexpr uint32_t idesc = umma_idesc_f16(128, 16, 0);
+  constexpr uint32_t idesc = umma_idesc_f16(128, 32, 0);  // N = 32: the hi and lo weight terms of 16 output columns side by side
   // per-CTA constants of the MMA issuer: k-step windows of the two N-tiles and the operand descriptor bases (16-byte units)
   const int nk0 = a.tile_nk[slab * 2], nk1 = a.tile_nk[slab * 2 + 1], k00 = a.tile_k0[slab * 2], k01 = a.tile_k0[slab * 2 + 1];
   const int nkm = nk0 > nk1 ? nk0 : nk1;
@@ -257,15 +257,17 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       // Four independent accumulators - (N-tile, weight term) - interleaved k-step by k-step: a chain of accumulations into ONE
       // TMEM tile serialises on the MMA pipeline latency (measured: 28 back-to-back dependent MMAs cost ~3.5 k cycles, 44 % of the
       // warp samples slept on the commit barrier); hi and lo partial sums are added in the epilogue instead.
+      // One MMA per (N-tile, k-step): a UMMA with M = 128 streams its 128 A rows from shared memory in ~128 cycles whatever N is
+      // (measured: 28 N=16 MMAs per unit cost ~3.5 k cycles, 44 % of the warp samples slept on the commit), so the hi and lo weight
+      // terms ride in the SAME instruction as N = 32 - two accumulators per tile (TMEM columns 0..15 | 16..31), added in the epilogue.
       for (int kk = 0; kk < nkm; ++kk) {
-        const uint64_t kb_off = (uint64_t)(((kk >> 2) << 7) + ((kk & 3) << 1));  // chunk of 64 k: 2048 B, k-step: 32 B
+        const uint64_t kb_off = (uint64_t)(((kk >> 2) << 8) + ((kk & 3) << 1));  // chunk of 64 k: 32 rows x 128 B = 4096 B, k-step: 32 B
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           if (kk >= (j ? nk1 : nk0)) continue;
           const int qa = (j ? k01 : k00) + kk;
           const uint64_t da = desc_a0 + (uint64_t)(((qa >> 2) << 10) + ((qa & 3) << 1));  // chunk: 16384 B
-#pragma unroll
-          for (int hl = 0; hl < 2; ++hl) umma_f16(tmem + (uint32_t)((j * 2 + hl) * 16), da, desc_b0 + (uint64_t)((j * 2 + hl) * b_tile16) + kb_off, idesc, kk != 0);
+          umma_f16(tmem + (uint32_t)(j * 32), da, desc_b0 + (uint64_t)(j * b_tile16) + kb_off, idesc, kk != 0);
         }
       }
       umma_commit(mma_done);
@@ -426,11 +428,11 @@ static const TcPlan* get_plan(cb_ctx* ctx, const TapTable* tx, const TapTable* t
   p.ru = std::min(40, kRingRows - ty->max_taps + 1) & ~7;  // multiple of 8: a colour plane is a whole number of 8-row operand groups
   p.y_begin = ty->src_begin & ~1;
   p.n_units = p.ru > 0 ? (ty->src_end - p.y_begin + p.ru - 1) / p.ru : 0;
-  const int b_tile = (p.kb / 64) * 2048;
-  const size_t smem = 1024 + (size_t)p.kw * 256 + 4 * (size_t)b_tile + ((((size_t)(p.ru + p.ru / 2) * p.kw) + 127) & ~(size_t)127) + (kRingRows * kRingStride + kVRows * kVTaps + 2 * kVRows + kMaxUnits) * 4 + 64;
+  const int b_tile = (p.kb / 64) * 4096;
+  const size_t smem = 1024 + (size_t)p.kw * 256 + 2 * (size_t)b_tile + ((((size_t)(p.ru + p.ru / 2) * p.kw) + 127) & ~(size_t)127) + (kRingRows * kRingStride + kVRows * kVTaps + 2 * kVRows + kMaxUnits) * 4 + 64;
   p.ok = p.ru >= 16 && p.kw <= 256 && p.n_units <= kMaxUnits && smem <= 227 * 1024;  // TMA box <= 256 columns
   if (p.ok) {
-    std::vector<uint16_t> w((size_t)p.n_slabs * 4 * b_tile / 2, 0);
+    std::vector<uint16_t> w((size_t)p.n_slabs * 2 * b_tile / 2, 0);
     for (int s = 0; s < p.n_slabs; ++s)
       for (int j = 0; j < 2; ++j)
         for (int nrow = 0; nrow < 16; ++nrow) {
@@ -441,9 +443,11 @@ static const TcPlan* get_plan(cb_ctx* ctx, const TapTable* tx, const TapTable* t
             if (t < 0 || t >= tx->h_size[c]) continue;
             const float wv = tx->h_w[(size_t)c * tx->max_taps + t];
             const uint16_t hb = f32_to_f16_bits(wv), lb = f32_to_f16_bits(wv - f16_bits_to_f32(hb));
-            const size_t off = (size_t)(k >> 6) * 2048 + (size_t)(nrow >> 3) * 1024 + (size_t)(nrow & 7) * 128 + (size_t)((((k & 63) >> 3) ^ (nrow & 7)) << 4) + (size_t)((k & 7) << 1);
-            w[((size_t)(s * 4 + j * 2 + 0) * b_tile + off) / 2] = hb;
-            w[((size_t)(s * 4 + j * 2 + 1) * b_tile + off) / 2] = lb;
+            for (int hl = 0; hl < 2; ++hl) {
+              const int nr = hl * 16 + nrow;  // row of the 32-row B tile
+              const size_t off = (size_t)(k >> 6) * 4096 + (size_t)(nr >> 3) * 1024 + (size_t)(nr & 7) * 128 + (size_t)((((k & 63) >> 3) ^ (nr & 7)) << 4) + (size_t)((k & 7) << 1);
+              w[((size_t)(s * 2 + j) * b_tile + off) / 2] = hl ? lb : hb;
+            }
           }
         }
     std::vector<int> unit_last(p.n_units);
@@ -516,8 +520,8 @@ int run_clip_preprocess_tc(cb_ctx* ctx, const cb_surface_pool* pool, const int* 
   }
   a.x_lo = p->d_x_lo, a.tile_k0 = p->d_k0, a.tile_nk = p->d_nk, a.wtiles = p->d_w;
   a.ymin = ty->d_min, a.ysize = ty->d_size, a.unit_last = p->d_unit_last, a.wy = ty->d_w, a.ty = ty->max_taps, a.out = u8;
-  const int b_tile = (p->kb / 64) * 2048;
-  const size_t smem = 1024 + (size_t)p->kw * 256 + 4 * (size_t)b_tile + ((((size_t)(p->ru + p->ru / 2) * p->kw) + 127) & ~(size_t)127) + (kRingRows * kRingStride + kVRows * kVTaps + 2 * kVRows + kMaxUnits) * 4 + 64;
+  const int b_tile = (p->kb / 64) * 4096;
+  const size_t smem = 1024 + (size_t)p->kw * 256 + 2 * (size_t)b_tile + ((((size_t)(p->ru + p->ru / 2) * p->kw) + 127) & ~(size_t)127) + (kRingRows * kRingStride + kVRows * kVTaps + 2 * kVRows + kMaxUnits) * 4 + 64;
   CB_CUDA(ctx, cudaFuncSetAttribute(clip_preprocess_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mark_launch(ctx, CB_PROF_PREPROCESS, stream);
   clip_preprocess_tc_kernel<<<dim3(p->n_slabs, n), kTcThreads, smem, stream>>>(map_y, map_uv, a);

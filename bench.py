@@ -210,8 +210,8 @@ def run_b200(args) -> None:
 
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # its banner goes to stdout: keep stdout to the one JSON line
-            os.environ["NCCL_DEBUG"] = "WARN"
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):  # both print the version banner to stdout: keep stdout to the one JSON line
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import uuid
@@ -391,7 +391,8 @@ def run_b200(args) -> None:
 
                 tasks = stage2.process_data(make_tasks(99))
                 local_emb = torch.from_numpy(np.stack([c.openai_embedding for t in tasks for c in t.video.clips + t.video.filtered_clips])).cuda()
-                all_gather_embeddings(local_emb)  # warm-up (communicator creation)
+                warm, _ = all_gather_embeddings(local_emb)  # warm-up: communicator creation, first-call allocations of the dedup kernels
+                semdedup_cluster(np.arange(warm.shape[0]), warm, torch.zeros(warm.shape[0]), eps=0.01)
                 barrier()
                 g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                 g0.record()

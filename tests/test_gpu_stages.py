@@ -409,3 +409,31 @@ def test_fused_stage_keyframe_seek_gives_identical_results(ctx):
         st.destroy()
     assert out[False][0] == out[True][0] and all(np.array_equal(a, b) for a, b in zip(out[False][1], out[True][1]))
     assert out[True][2] < out[False][2] == 3 * 180  # 7 sampled frames per clip: the seek mode skips most of every GOP
+
+
+def test_fused_stage_mixed_resolutions_in_one_call(ctx):
+    """BASELINE.json configs[4] mixes 720p / 1080p / 4K clips in one stream: clips of different sizes inside ONE process_data call go
+    through per-resolution surface-pool rings and batches; every clip gets the score it gets when processed alone."""
+    from cosmos_curate_b200.data_model import Clip
+    from cosmos_curate_b200.stages import NvdecClipAestheticStage
+    from tools import synth_h264
+
+    sources = [synth_h264.make_coded_clip(640, 368, 30, 2.0, seed=31, bitrate=1.0e6), synth_h264.make_coded_clip(1280, 720, 30, 2.0, seed=32, bitrate=2.0e6),
+               (GOLDEN / "sintel_clip_10s.mp4").read_bytes(), synth_h264.make_coded_clip(1920, 1080, 30, 2.0, seed=33, bitrate=4.0e6)]
+    model, cfg, w, sd = _model()
+    stage = NvdecClipAestheticStage(score_threshold=-100.0, reduction="mean", write_embedding=True, max_batch=16, num_decoders=4, model=model)
+    stage.stage_setup()
+    alone = []
+    for s in sources:
+        t = _clip_task(s)
+        stage.process_data([t])
+        alone.append((t.video.clips[0].aesthetic_score, t.video.clips[0].openai_embedding))
+    order = [0, 1, 2, 3, 1, 0, 3, 2, 2, 1]  # interleaved sizes, more frames than one batch holds (max_batch = 16)
+    task = _clip_task(sources[0], n_clips=0)
+    task.video.clips = [Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0.0, 2.0), encoded_data=sources[k]) for k in order]
+    stage.process_data([task])
+    assert len(task.video.clips) == len(order)
+    for clip, k in zip(task.video.clips, order):
+        assert clip.aesthetic_score == alone[k][0] and np.array_equal(clip.openai_embedding, alone[k][1]), k
+    assert stage.last_call_stats["batches"] >= 4
+    stage.destroy()

@@ -15,7 +15,7 @@ Printed JSON line (rank 0):
   value   clips/s, whole job, decoded NV12 surfaces of the step already resident in HBM (preprocess + tower + head),
           timed with CUDA events, max over ranks.
   e2e     clips/s through the PRODUCT stage: NvdecClipAestheticStage.process_data(tasks) on host SplitPipeTasks holding mp4 bytes
-          (one call = `--tasks-per-call` tasks x clips-per-step clips); MP4 index + NVDEC decode of every frame up to the last
+          (one call = `--tasks-per-call` = 20 tasks x clips-per-step clips = 480 clips, a few source videos' worth); MP4 index + NVDEC decode of every frame up to the last
           sampled one (the reference's decode semantics) + fused preprocess + tower + pinned D2H of scores/embeddings, the decode /
           tower overlap happening inside the stage; wall clock between device synchronisations, max over ranks.
   e2e_keyframe_seek  the same call with seek_keyframes=True (opt-in: identical frames, only GOPs with sampled frames are decoded).
@@ -764,7 +764,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--clips-per-step", type=int, default=24)
     ap.add_argument("--distinct-clips", type=int, default=64)
-    ap.add_argument("--tasks-per-call", type=int, default=10, help="SplitPipeTasks (of clips-per-step clips each) per process_data call of the e2e measurement")
+    ap.add_argument("--tasks-per-call", type=int, default=20, help="SplitPipeTasks (of clips-per-step clips each) per process_data call of the e2e measurement")
     ap.add_argument("--ceiling-seconds", type=float, default=5.0, help="duration of the decode-only ceiling measurement")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C1 / C4-shaped / clip-cut secondary rows")
     ap.add_argument("--no-gpu-library", action="store_true", help="skip the reference GPU library-path baseline")

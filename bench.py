@@ -204,6 +204,7 @@ def run_b200(args) -> None:
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     clips = make_clips(args.distinct_clips, rank)  # fork pool: before torch / CUDA are touched
     clips_4k = make_clips(4, 0, size=(3840, 2160), bitrate=16.0e6) if (rank == 0 and world == 1 and not args.no_secondary) else None
+    clips_720 = make_clips(8, 0, size=(1280, 720), bitrate=2.0e6) if (rank == 0 and world == 1 and not args.no_secondary) else None
 
     import torch
     import torch.distributed as dist
@@ -471,7 +472,7 @@ def run_b200(args) -> None:
         line["e2e_error"] = e2e_error
     if world == 1 and not args.no_secondary:
         try:
-            line["secondary"] = secondary_configs(ctx, torch, clips, clips_4k, args)
+            line["secondary"] = secondary_configs(ctx, torch, clips, clips_4k, args, clips_720)
         except Exception as exc:  # noqa: BLE001
             import traceback
 
@@ -488,7 +489,7 @@ def run_b200(args) -> None:
         dist.destroy_process_group()
 
 
-def secondary_configs(ctx, torch, clips_1080p: list[bytes], clips_4k, args) -> dict:
+def secondary_configs(ctx, torch, clips_1080p: list[bytes], clips_4k, args, clips_720=None) -> dict:
     """Bounded secondary rows (N=1, rank 0): BASELINE.json configs[0] (C1) on both arms, a configs[3]-shaped row (4K + SoViT-400m) and
     the transcode-free clip cutter.  Not the headline; each states its own workload."""
     import uuid
@@ -577,6 +578,28 @@ def secondary_configs(ctx, torch, clips_1080p: list[bytes], clips_4k, args) -> d
             "attention_ms": prof["attention"]["ms"] / reps, "layernorm_ms": prof["layernorm"]["ms"] / reps,
             "preprocess": {"ms": prof["preprocess"]["ms"] / reps, "algorithmic_gbs": pre_b / (prof["preprocess"]["ms"] / 1e3) / 1e9},
             "gflop_per_image": cfg.flops_per_image() / 1e9}  # fmt: skip
+
+    # ---- C5-shaped: 40 % 720p / 40 % 1080p / 20 % 4K in one stream through the aesthetic stage (per-resolution pool rings and batches)
+    if clips_4k and clips_720:
+        model = CLIPAestheticScorer(seed=0, max_batch=264, config=W.CLIP_VIT_L14)
+        st = NvdecClipAestheticStage(score_threshold=5.0, reduction="min", write_embedding=True, max_batch=264, num_decoders=args.decoders, seek_keyframes=False, model=model)
+        st.stage_setup()
+        mix = []
+        for i in range(120):
+            mix.append(clips_720[i % len(clips_720)] if i % 5 in (0, 2) else clips_4k[i % len(clips_4k)] if i % 5 == 4 else clips_1080p[i % len(clips_1080p)])
+        ctx.profile_begin()
+        cps, n = timed(st, lambda: tasks_of(mix, 24, SECONDS), 1)
+        prof = ctx.profile_end()
+        px = {"720p": 1280 * 720, "1080p": 1920 * 1080, "2160p": 3840 * 2160}
+        mean_px = 0.4 * px["720p"] + 0.4 * px["1080p"] + 0.2 * px["2160p"]
+        st.destroy()
+        model.tower.close()
+        out["c5_mix"] = {
+            "workload": "120 clips per call: 40 % 1280x720 (2 Mb/s), 40 % 1920x1080 (4 Mb/s), 20 % 3840x2160 (16 Mb/s) H.264 10 s clips interleaved -> 1 fps -> CLIP ViT-L/14 + aesthetic "
+                        "filter (BASELINE.json configs[4] mix on one GPU; the reference's split / caption / writer stages around it are out of scope)",
+            "e2e_clips_per_sec": cps, "clips": n, "decoded_megapixels_per_sec": cps * 300 * mean_px / 1e6,
+            "kernel_ms_over_warmup_and_timed_call": {k: v["ms"] for k, v in prof.items() if v["launches"]},
+            "note": "NVDEC-bound: pixel rate equals the 1080p run's (decoded fps x pixels per frame)"}  # fmt: skip
 
     # ---- transcode-free clip cutting (N2): 5 s spans out of the 10 s 1080p sources by stream copy
     stage = ClipStreamCopyStage()

@@ -13,14 +13,17 @@
 //   * B = the fp32 tap weights split into two fp16 terms (hi + lo, 22 significant bits: products with u8 pixels are exact in
 //     the fp32 accumulator, only the summation order differs from ATen's - the <= 1 LSB on <= 1e-4 of the pixels budget the
 //     fp32 paths already share).  An N-tile is 16 output columns; its K window is the ~100 source columns those columns
-//     tap (7 k-steps of 16), so the band is ~70 % dense instead of a dense 1080-wide GEMM.
-//   * accumulators in TMEM (64 columns per CTA: N-tile x weight term, four independent accumulation chains), read back with tcgen05.ld into a 64-row ring of filtered rows in shared memory;
-//     the vertical pass (17 % of the FMAs) stays on the FMA pipe in ATen's order, then round / clamp / store u8.
+//     tap (7 k-steps of 16), so the band is ~70 % dense instead of a dense 1080-wide GEMM.  The hi and lo terms of a tile sit
+//     side by side in the B tile (N = 32): a UMMA with M = 128 streams its A rows from shared memory in ~128 cycles whatever N
+//     is, so the number of instructions, not their width, is what costs (14 per unit).
+//   * accumulators in TMEM (64 columns per CTA: N-tile x weight term), read back with tcgen05.ld, hi + lo added, into a 64-row
+//     ring of filtered rows in shared memory; the vertical pass (17 % of the FMAs) stays on the FMA pipe in ATen's order (it
+//     runs while the next unit's MMAs are in flight), then round / clamp / store u8.
 //
 // A CTA owns (frame, 32 output columns) and walks the source rows top to bottom in units of 40 rows: TMA load of the NV12
-// window (Y + UV boxes) -> convert -> 28 MMAs -> epilogue -> vertical pass for the output rows that became complete.
-// ~100 KB of shared memory per CTA: two CTAs per SM overlap each other's phases.  Output: u8 [n][3][res][res]; normalisation +
-// patch packing is a second, bandwidth-trivial kernel (normalize_pack_kernel) so that this one stays small.
+// window (Y + UV boxes) -> convert -> 14 MMAs -> epilogue -> vertical pass for the output rows that became complete.
+// ~105 KB of shared memory per CTA: two CTAs per SM overlap each other's phases.  Output: u8 [n][3][res][res]; normalisation +
+// patch packing is a second, bandwidth-trivial kernel (pack_patches_kernel / normalize_pack_kernel) so that this one stays small.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>

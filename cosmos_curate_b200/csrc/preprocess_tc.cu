@@ -46,6 +46,7 @@ constexpr int kTcThreads = 320;  // 10 warps: 20 row pairs x kw / 4 column group
 struct TcArgs {
   const int* slots;
   int n, res, ru, n_units, y_begin, kw, kb, colour, wait_ns;
+  int nc;                  // output columns per CTA slab: 32 (two N-tiles), or 16 when the downscale is so strong that 32 columns' window exceeds a TMA box
   const int* x_lo;         // [n_slabs] first source column of the slab window (multiple of 16)
   const int* tile_k0;      // [n_slabs * 2] first k-step (16 source columns) of the N-tile inside the window
   const int* tile_nk;      // [n_slabs * 2] k-steps of the N-tile (0 = tile beyond the image)
@@ -97,8 +98,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slab = blockIdx.x, frame = blockIdx.y;
   const int slot = a.slots[frame];
-  const int x_lo = a.x_lo[slab], x0 = slab * kNC;
-  const int ncols = min(kNC, a.res - x0);
+  const int x_lo = a.x_lo[slab], x0 = slab * a.nc;
+  const int ncols = min(a.nc, a.res - x0);
 
   if (tid == 0) {
     mbar_init(raw_full, 1), mbar_init(mma_done, 1);
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(256) pack_patches_kernel(const PackArgs a) {
 namespace {
 
 struct TcPlan {  // per (source size, taps): slab windows + pre-swizzled weight tiles on the device
-  int n_slabs = 0, kw = 0, kb = 0, ru = 0, n_units = 0, y_begin = 0;
+  int n_slabs = 0, kw = 0, kb = 0, ru = 0, n_units = 0, y_begin = 0, nc = kNC;
   int *d_x_lo = nullptr, *d_k0 = nullptr, *d_nk = nullptr, *d_unit_last = nullptr;
   uint8_t* d_w = nullptr;
   bool ok = false;
@@ -408,24 +409,29 @@ static const TcPlan* get_plan(cb_ctx* ctx, const TapTable* tx, const TapTable* t
   auto it = cache.find(key);
   if (it != cache.end()) return &it->second;
   TcPlan p;
-  p.n_slabs = (res + kNC - 1) / kNC;
-  std::vector<int> x_lo(p.n_slabs), k0(p.n_slabs * 2, 0), nk(p.n_slabs * 2, 0);
+  std::vector<int> x_lo, k0, nk;
   int kw = 0, kbmax = 0;
-  for (int s = 0; s < p.n_slabs; ++s) {
-    const int c0 = s * kNC, c1 = std::min(res, c0 + kNC);
-    x_lo[s] = tx->h_min[c0] & ~15;
-    int hi = 0;
-    for (int c = c0; c < c1; ++c) hi = std::max(hi, tx->h_min[c] + tx->h_size[c]);
-    kw = std::max(kw, hi - x_lo[s]);
-    for (int j = 0; j < 2; ++j) {
-      const int t0 = c0 + 16 * j, t1 = std::min(c1, t0 + 16);
-      if (t0 >= t1) continue;
-      const int first = (tx->h_min[t0] - x_lo[s]) / 16;
-      int end = 0;
-      for (int c = t0; c < t1; ++c) end = std::max(end, tx->h_min[c] + tx->h_size[c] - x_lo[s]);
-      k0[s * 2 + j] = first, nk[s * 2 + j] = (end - first * 16 + 15) / 16;
-      kbmax = std::max(kbmax, nk[s * 2 + j] * 16);
+  for (int nc : {kNC, 16}) {  // 32 columns per slab unless their source window exceeds one TMA box (4K -> 224: 9.6x downscale)
+    p.nc = nc, p.n_slabs = (res + nc - 1) / nc;
+    x_lo.assign(p.n_slabs, 0), k0.assign(p.n_slabs * 2, 0), nk.assign(p.n_slabs * 2, 0);
+    kw = 0, kbmax = 0;
+    for (int s = 0; s < p.n_slabs; ++s) {
+      const int c0 = s * nc, c1 = std::min(res, c0 + nc);
+      x_lo[s] = tx->h_min[c0] & ~15;
+      int hi = 0;
+      for (int c = c0; c < c1; ++c) hi = std::max(hi, tx->h_min[c] + tx->h_size[c]);
+      kw = std::max(kw, hi - x_lo[s]);
+      for (int j = 0; j < 2; ++j) {
+        const int t0 = c0 + 16 * j, t1 = std::min(c1, t0 + 16);
+        if (t0 >= t1) continue;
+        const int first = (tx->h_min[t0] - x_lo[s]) / 16;
+        int end = 0;
+        for (int c = t0; c < t1; ++c) end = std::max(end, tx->h_min[c] + tx->h_size[c] - x_lo[s]);
+        k0[s * 2 + j] = first, nk[s * 2 + j] = (end - first * 16 + 15) / 16;
+        kbmax = std::max(kbmax, nk[s * 2 + j] * 16);
+      }
     }
+    if (kw <= 256) break;
   }
   p.kw = (kw + 63) & ~63, p.kb = (kbmax + 63) & ~63;
   p.ru = std::min(40, kRingRows - ty->max_taps + 1) & ~7;  // multiple of 8: a colour plane is a whole number of 8-row operand groups
@@ -439,7 +445,7 @@ static const TcPlan* get_plan(cb_ctx* ctx, const TapTable* tx, const TapTable* t
     for (int s = 0; s < p.n_slabs; ++s)
       for (int j = 0; j < 2; ++j)
         for (int nrow = 0; nrow < 16; ++nrow) {
-          const int c = s * kNC + 16 * j + nrow;
+          const int c = s * p.nc + 16 * j + nrow;
           if (c >= res || nk[s * 2 + j] == 0) continue;
           for (int k = 0; k < nk[s * 2 + j] * 16; ++k) {
             const int t = x_lo[s] + k0[s * 2 + j] * 16 + k - tx->h_min[c];
@@ -515,6 +521,7 @@ int run_clip_preprocess_tc(cb_ctx* ctx, const cb_surface_pool* pool, const int* 
                        strides, box_uv, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (rc) return rc;
   TcArgs a{};
+  a.nc = p->nc;
   a.slots = d_slots, a.n = n, a.res = res, a.ru = p->ru, a.n_units = p->n_units, a.y_begin = p->y_begin, a.kw = p->kw, a.kb = p->kb;
   a.colour = pool->format;
   {

@@ -172,7 +172,8 @@ def test_resize_cubic_from_nv12_and_into_the_tower(ctx):
 
 # ------------------------------------------------------------------------------------ tensor-pipe generation vs SIMT generation
 @pytest.mark.parametrize(("h", "w", "pitch", "res", "colour"), [(1080, 1920, 2048, 224, "opencv"), (1080, 1920, 2048, 224, "swscale"), (2160, 3840, 3840, 384, "swscale"),
-                                                                (480, 854, 1024, 224, "swscale"), (720, 1280, 1280, 384, "opencv"), (360, 640, 640, 224, "opencv")])
+                                                                (480, 854, 1024, 224, "swscale"), (720, 1280, 1280, 384, "opencv"), (360, 640, 640, 224, "opencv"),
+                                                                (2160, 3840, 3840, 224, "swscale")])
 def test_tensor_pipe_preprocess_agrees_with_simt_kernel_and_oracle(ctx, monkeypatch, h, w, pitch, res, colour):
     """clip_preprocess_tc_kernel (horizontal pass as a banded fp16 hi/lo GEMM on tcgen05, the default) against the v2 SIMT kernel
     (CB_PRE_KERNEL=2) and the oracle: same u8 image within the fp32-summation-order budget, both colour conversions, 1080p -> 224
@@ -186,15 +187,22 @@ def test_tensor_pipe_preprocess_agrees_with_simt_kernel_and_oracle(ctx, monkeypa
         buf[i, :, :w] = f
     pool = ctx.nv12_pool(torch.from_numpy(buf).cuda(), w, h, h, colour=colour)
     got_tc = ctx.preprocess_clip_u8(pool, res=res).cpu().numpy()
+    from cosmos_curate_b200._lib import CurateB200Error
+
     monkeypatch.setenv("CB_PRE_KERNEL", "2")
-    got_v2 = ctx.preprocess_clip_u8(pool, res=res).cpu().numpy()
+    try:
+        got_v2 = ctx.preprocess_clip_u8(pool, res=res).cpu().numpy()
+    except CurateB200Error:  # 4K -> 224 (9.6x, 40 taps): beyond the SIMT kernel's tile window; the tensor-pipe kernel narrows its slabs to 16 columns
+        assert (h, res) == (2160, 224)
+        got_v2 = None
     monkeypatch.delenv("CB_PRE_KERNEL")
     conv = color.nv12_to_rgb_swscale if colour == "swscale" else color.nv12_to_rgb
     rgb = np.stack([conv(f, h, w) for f in frames])
     want = preprocess.clip_resize_crop_u8(rgb, res)
-    _u8_budget(got_v2, want)
     _u8_budget(got_tc, want)
-    _u8_budget(got_tc, got_v2, frac=2e-4)  # two fp32 summation orders apart
+    if got_v2 is not None:
+        _u8_budget(got_v2, want)
+        _u8_budget(got_tc, got_v2, frac=2e-4)  # two fp32 summation orders apart
     # typed + patch outputs of the tensor-pipe path are exactly LUT(u8)
     lut = preprocess.normalize_lut()
     want32 = np.stack([lut[c][got_tc[:, c]] for c in range(3)], axis=1)

@@ -792,14 +792,20 @@ int run_clip_preprocess(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t*
   while (ring < kSR + ty->max_taps) ring <<= 1;
   a.ring = ring;
   a.x_align = 16;  // cp.async.bulk.tensor needs the box to start on a 16-byte boundary of the innermost dimension
-  // widest source span of any column tile
-  int span = 0;
-  const int tiles = (a.res_out + a.tc - 1) / a.tc;
-  for (int t = 0; t < tiles; ++t) {
-    const int c0 = t * a.tc, c1 = std::min(a.res_out, c0 + a.tc);
-    int lo = tx->h_min[c0] & ~(a.x_align - 1), hi = 0;
-    for (int c = c0; c < c1; ++c) hi = std::max(hi, tx->h_min[c] + tx->h_size[c]);
-    span = std::max(span, hi - lo);
+  // widest source span of any column tile; strong downscales (4K -> 224: 9.6 source pixels per output column) halve the tile so that
+  // the window still fits one TMA box (256 bytes of the innermost dimension)
+  int span = 0, tiles = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    span = 0;
+    tiles = (a.res_out + a.tc - 1) / a.tc;
+    for (int t = 0; t < tiles; ++t) {
+      const int c0 = t * a.tc, c1 = std::min(a.res_out, c0 + a.tc);
+      int lo = tx->h_min[c0] & ~(a.x_align - 1), hi = 0;
+      for (int c = c0; c < c1; ++c) hi = std::max(hi, tx->h_min[c] + tx->h_size[c]);
+      span = std::max(span, hi - lo);
+    }
+    if (span <= 256 || attempt == 1) break;
+    a.tc = out_mode == 2 ? layout_patch * std::max(1, 16 / layout_patch) : 16;
   }
   a.swa = (span + 15) & ~15;
   // v2: widest union window of any group of 4 adjacent output columns

@@ -192,7 +192,7 @@ def test_tensor_pipe_preprocess_agrees_with_simt_kernel_and_oracle(ctx, monkeypa
     monkeypatch.setenv("CB_PRE_KERNEL", "2")
     try:
         got_v2 = ctx.preprocess_clip_u8(pool, res=res).cpu().numpy()
-    except CurateB200Error:  # 4K -> 224 (9.6x, 40 taps): beyond the SIMT kernel's tile window; the tensor-pipe kernel narrows its slabs to 16 columns
+    except CurateB200Error:  # a downscale beyond the SIMT kernel's (halved) tile window
         assert (h, res) == (2160, 224)
         got_v2 = None
     monkeypatch.delenv("CB_PRE_KERNEL")
@@ -209,3 +209,21 @@ def test_tensor_pipe_preprocess_agrees_with_simt_kernel_and_oracle(ctx, monkeypa
     np.testing.assert_array_equal(ctx.preprocess_clip(pool, res=res, dtype=torch.float32).cpu().numpy(), want32)
     gp = ctx.preprocess_clip(pool, res=res, dtype=torch.float16, layout="patch", patch=14, k_pad=640).cpu().numpy()
     np.testing.assert_array_equal(gp, preprocess.to_patches(want32.astype(np.float16), 14, 640))
+
+
+def test_clip_preprocess_4k_rgb_frames_strong_downscale(ctx):
+    """4K host RGB frames -> 224 (9.6 source pixels per output column, 40 taps): the SIMT kernel halves its column tile so that the
+    window still fits one TMA box; against torchvision's own CUDA transform (clip.py:48-70)."""
+    tv = pytest.importorskip("torchvision.transforms")
+    t = tv.Compose([tv.Resize(224, interpolation=tv.InterpolationMode.BICUBIC, antialias=True), tv.CenterCrop(224)])
+    rng = np.random.default_rng(8)
+    fr = rng.integers(0, 256, size=(1, 2160, 3840, 3), dtype=np.uint8)
+    x = torch.from_numpy(fr).cuda()
+    want = t(x.permute(0, 3, 1, 2)).cpu().numpy()
+    pool = ctx.rgb_pool(x)
+    _u8_budget(ctx.preprocess_clip_u8(pool).cpu().numpy(), want)
+    lut = preprocess.normalize_lut()
+    want32 = np.stack([lut[c][want[:, c]] for c in range(3)], axis=1)
+    gp = ctx.preprocess_clip(pool, dtype=torch.float16, layout="patch", patch=14, k_pad=640).cpu().numpy()
+    ref = preprocess.to_patches(want32.astype(np.float16), 14, 640)
+    assert (gp != ref).mean() < 2e-4  # the same <= 1e-4 u8 budget seen through the LUT

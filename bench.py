@@ -601,6 +601,33 @@ def secondary_configs(ctx, torch, clips_1080p: list[bytes], clips_4k, args, clip
             "kernel_ms_over_warmup_and_timed_call": {k: v["ms"] for k, v in prof.items() if v["launches"] and k != "other"},  # "other" would absorb the idle gaps while the SMs wait for NVDEC
             "note": "NVDEC-bound: pixel rate equals the 1080p run's (decoded fps x pixels per frame)"}  # fmt: skip
 
+    # ---- video-tower input tubes (N5, formulation only): 1080p clips -> 2 fps -> 8 kept frames -> cv2-bilinear 224 x 224 + ImageNet normalise
+    from cosmos_curate_b200.runtime import alloc_nv12_pool
+    from cosmos_curate_b200.stages import InternVideo2FrameCreationStage
+
+    st = InternVideo2FrameCreationStage(target_fps=2.0, source="nvdec", num_decoders=args.decoders, stage_batch_size=4)
+    st.stage_setup()
+    cps, n = timed(st, lambda: tasks_of(clips_1080p[:48], 12, SECONDS), 1)
+    pool = alloc_nv12_pool(ctx, 256, 1920, 1080, "swscale")
+    pool.buf.random_(0, 256)
+    ctx.video_tube(pool, 224, 224)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(10):
+        ctx.video_tube(pool, 224, 224)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 10
+    tube_b = 256 * 224 * 224 * (4 * 3 + 3 * 4)  # 4 taps x (Y + UV pair) read, 3 float32 written, per output pixel
+    st.destroy()
+    del pool
+    out["iv2_tubes"] = {
+        "workload": "48 1080p 10 s clips -> 2 fps sampling -> frames[::2][:8] -> cv2.resize(224, 224) + ImageNet normalise -> float32 [1,8,3,224,224] on the host "
+                    "(InternVideo2FrameCreationStage, source=nvdec; the tower itself is not part of this path)",
+        "e2e_clips_per_sec": cps, "clips": n, "d2h_bytes_per_clip": 8 * 3 * 224 * 224 * 4,
+        "kernel": {"ms_per_256_frames": ms, "algorithmic_gbs": tube_b / (ms / 1e3) / 1e9, "bound": "hbm (sparse: 4 source pixels per output; sector-granular reads)"},
+        "note": "NVDEC-bound like the headline: every frame up to the last kept one is decoded"}  # fmt: skip
+
     # ---- transcode-free clip cutting (N2): 5 s spans out of the 10 s 1080p sources by stream copy
     stage = ClipStreamCopyStage()
     vids = []

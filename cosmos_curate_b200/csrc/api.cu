@@ -144,6 +144,10 @@ void cb_destroy(cb_ctx* ctx) {
     cudaFree(kv.second.d_wq);
     cudaFree(kv.second.d_wf);
   }
+  for (auto& kv : ctx->linear_taps) {
+    cudaFree(kv.second.d_first);
+    cudaFree(kv.second.d_wq);
+  }
   cb::release_tc_plans(ctx);
   if (ctx->d_tmp_u8) cudaFree(ctx->d_tmp_u8);
   if (ctx->d_norm_lut) cudaFree(ctx->d_norm_lut);

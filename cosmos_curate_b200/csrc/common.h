@@ -48,6 +48,7 @@ struct cb_ctx {
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
   std::map<std::tuple<int, int, int, int>, cb::TapTable> taps;  // (in, out, crop_off, crop_len)
   std::map<std::pair<int, int>, cb::CubicTaps> cubic_taps;      // (src, dst)
+  std::map<std::tuple<int, int, int>, cb::CubicTaps> linear_taps;  // (src, dst, zero fx at the borders): d_first + d_wq[dst][2]
   float* d_norm_lut = nullptr;                                  // [3*256] fp32, normalise LUT currently loaded
   float lut_mean[3] = {0, 0, 0}, lut_std[3] = {0, 0, 0};
   std::atomic<unsigned long long> launches{0};  // kernels launched by this library (bench.py reports it); decode threads launch too

@@ -644,6 +644,85 @@ __global__ void resize_cubic_kernel(const CubicArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ video-tower tubes
+// cv2.resize(frame, (out_w, out_h)) [INTER_LINEAR, u8] + ((x / 255 - mean) / std) -> fp32 CHW: the input formulation of the
+// video embedding towers (InternVideo2MultiModality._construct_frames / _normalize, models/internvideo2_mm.py:385-405).
+// OpenCV's fixed-point arithmetic, bit for bit: int16 weights at 2^11 (each of the pair rounded on its own), horizontal pass
+// in int32, vertical pass (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2; an exact 2x2 decimation is what
+// cv2 reroutes to INTER_AREA ((a + b + c + d + 2) >> 2); equal sizes copy.  HBM-bound and sparse: 4 source pixels per output.
+struct TubeArgs {
+  const uint8_t* base;
+  size_t slot_stride;
+  const int* slots;
+  int n, w, h, pitch, luma_rows, format, out_w, out_h, mode;  // mode 0 linear, 1 area 2x2, 2 copy
+  const int *x0, *y0;
+  const short *ax, *by;
+  float mean[3], std_[3];
+  float* out_f32;    // [n][3][out_h][out_w] or null
+  uint8_t* out_u8;   // [n][out_h][out_w][3] or null
+};
+
+__device__ __forceinline__ void fetch_rgb_any(const TubeArgs& a, const uint8_t* fr, int x, int y, int& r, int& g, int& b) {
+  if (is_nv12(a.format)) {
+    fetch_rgb_nv12(fr, a.pitch, a.luma_rows, x, y, r, g, b, a.format);
+  } else {
+    const uint8_t* px = fr + (size_t)y * a.pitch + 3 * x;
+    r = px[0], g = px[1], b = px[2];
+  }
+}
+
+__global__ void video_tube_kernel(const TubeArgs a) {
+  __shared__ float lut[3][256];
+  for (int t = threadIdx.x; t < 768; t += blockDim.x) {
+    const int c = t >> 8, v = t & 255;
+    lut[c][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), a.mean[c]), a.std_[c]);
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = a.out_w * a.out_h;
+  if (i >= a.n * per) return;
+  const int f = i / per, p = i - f * per, yo = p / a.out_w, xo = p - yo * a.out_w;
+  const uint8_t* fr = a.base + (size_t)a.slots[f] * a.slot_stride;
+  int v[3];
+  if (a.mode == 2) {
+    fetch_rgb_any(a, fr, xo, yo, v[0], v[1], v[2]);
+  } else if (a.mode == 1) {
+    int s[3] = {2, 2, 2};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int r, g, b;
+      fetch_rgb_any(a, fr, 2 * xo + (k & 1), 2 * yo + (k >> 1), r, g, b);
+      s[0] += r, s[1] += g, s[2] += b;
+    }
+    v[0] = s[0] >> 2, v[1] = s[1] >> 2, v[2] = s[2] >> 2;
+  } else {
+    const int xs = a.x0[xo], ys = a.y0[yo];
+    const int xa = min(max(xs, 0), a.w - 1), xb = min(max(xs + 1, 0), a.w - 1);
+    const int ya = min(max(ys, 0), a.h - 1), yb = min(max(ys + 1, 0), a.h - 1);
+    const int a0 = a.ax[2 * xo], a1 = a.ax[2 * xo + 1], b0 = a.by[2 * yo], b1 = a.by[2 * yo + 1];
+    int p00[3], p01[3], p10[3], p11[3];
+    fetch_rgb_any(a, fr, xa, ya, p00[0], p00[1], p00[2]);
+    fetch_rgb_any(a, fr, xb, ya, p01[0], p01[1], p01[2]);
+    fetch_rgb_any(a, fr, xa, yb, p10[0], p10[1], p10[2]);
+    fetch_rgb_any(a, fr, xb, yb, p11[0], p11[1], p11[2]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int s0 = p00[c] * a0 + p01[c] * a1, s1 = p10[c] * a0 + p11[c] * a1;
+      v[c] = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+    }
+  }
+  if (a.out_u8) {
+    uint8_t* o = a.out_u8 + (size_t)i * 3;
+    o[0] = (uint8_t)v[0], o[1] = (uint8_t)v[1], o[2] = (uint8_t)v[2];
+  }
+  if (a.out_f32) {
+    float* o = a.out_f32 + (size_t)f * 3 * per + p;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[(size_t)c * per] = lut[c][v[c] & 255];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 static float cubic_aa(float x) {  // Keys a = -0.5, float32 like ATen's bicubic_filter
   const float a = -0.5f;
@@ -977,6 +1056,73 @@ static int run_resize_cubic(cb_ctx* ctx, const cb_surface_pool* pool, const int3
   return CB_OK;
 }
 
+// OpenCV resize() linear taps: the column table zeroes fx at the borders, the row table clamps rows instead (resize.cpp).
+static const CubicTaps* get_linear_taps(cb_ctx* ctx, int src, int dst, bool zero_at_border) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto key = std::make_tuple(src, dst, zero_at_border ? 1 : 0);
+  auto it = ctx->linear_taps.find(key);
+  if (it != ctx->linear_taps.end()) return &it->second;
+  std::vector<int> first(dst);
+  std::vector<short> wq(2 * (size_t)dst);
+  const double inv_scale = (double)dst / (double)src, scale = 1.0 / inv_scale;
+  for (int d = 0; d < dst; ++d) {
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    int sx = (int)std::floor(fx);
+    fx -= (float)sx;
+    if (zero_at_border) {
+      if (sx < 0) fx = 0.f, sx = 0;
+      if (sx >= src - 1) fx = 0.f, sx = src - 1;
+    }
+    first[d] = sx;
+    const float c[2] = {1.f - fx, fx};
+    for (int k = 0; k < 2; ++k) {
+      const float q = std::nearbyint(c[k] * 2048.f);  // saturate_cast<short>(float) = cvRound: half to even
+      wq[2 * (size_t)d + k] = (short)std::min(32767.f, std::max(-32768.f, q));
+    }
+  }
+  CubicTaps t;
+  if (cudaMalloc(&t.d_first, dst * sizeof(int)) != cudaSuccess || cudaMalloc(&t.d_wq, 2 * (size_t)dst * sizeof(short)) != cudaSuccess)
+    return nullptr;
+  cudaMemcpy(t.d_first, first.data(), dst * sizeof(int), cudaMemcpyHostToDevice);
+  cudaMemcpy(t.d_wq, wq.data(), 2 * (size_t)dst * sizeof(short), cudaMemcpyHostToDevice);
+  return &(ctx->linear_taps[key] = t);
+}
+
+static int run_video_tube(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int out_w, int out_h, const float mean[3],
+                          const float std_[3], float* out_f32, uint8_t* out_u8, cudaStream_t stream) {
+  int rc = check_pool(ctx, pool, n, slots);
+  if (rc) return rc;
+  if (n == 0) return CB_OK;
+  if (!out_f32 && !out_u8) return fail(ctx, CB_ERR_ARG, "null output");
+  if (out_w <= 0 || out_h <= 0 || out_w > 8192 || out_h > 8192) return fail(ctx, CB_ERR_ARG, "bad output size %dx%d", out_w, out_h);
+  if (out_f32 && (!mean || !std_)) return fail(ctx, CB_ERR_ARG, "null mean/std");
+  if (is_nv12(pool->format) && ((pool->width | pool->height) & 1)) return fail(ctx, CB_ERR_UNSUPPORTED, "NV12 needs even dimensions");
+  if ((long long)n * out_w * out_h > 0x7fffffffLL) return fail(ctx, CB_ERR_ARG, "too many output pixels for one call");
+  TubeArgs a{};
+  a.base = (const uint8_t*)pool->base, a.slot_stride = pool->slot_stride;
+  a.n = n, a.w = pool->width, a.h = pool->height, a.pitch = pool->pitch, a.luma_rows = pool->luma_rows, a.format = pool->format;
+  a.out_w = out_w, a.out_h = out_h, a.out_f32 = out_f32, a.out_u8 = out_u8;
+  for (int c = 0; c < 3; ++c) a.mean[c] = mean ? mean[c] : 0.f, a.std_[c] = std_ ? std_[c] : 1.f;
+  if (a.w == out_w && a.h == out_h) {
+    a.mode = 2;
+  } else if (a.w == 2 * out_w && a.h == 2 * out_h) {
+    a.mode = 1;
+  } else {
+    a.mode = 0;
+    const CubicTaps* tx = get_linear_taps(ctx, a.w, out_w, true);
+    const CubicTaps* ty = get_linear_taps(ctx, a.h, out_h, false);
+    if (!tx || !ty) return fail(ctx, CB_ERR_CUDA, "linear tap table allocation failed");
+    a.x0 = tx->d_first, a.ax = tx->d_wq, a.y0 = ty->d_first, a.by = ty->d_wq;
+  }
+  rc = upload_slots(ctx, slots, n, stream, &a.slots);
+  if (rc) return rc;
+  mark_launch(ctx, CB_PROF_PREPROCESS, stream);
+  const long long total = (long long)n * out_w * out_h;
+  video_tube_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(a);
+  CB_CUDA(ctx, cudaGetLastError());
+  return CB_OK;
+}
+
 int bilinear_from_surface(cb_ctx* ctx, const void* base, int pitch, int luma_rows, int w, int h, int out_w, int out_h, uint8_t* out,
                           cudaStream_t stream) {
   SimpleArgs a{};
@@ -1018,6 +1164,12 @@ int cb_resize_cubic_u8(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* 
                        void* stream) {
   if (!ctx) return CB_ERR_ARG;
   return cb::run_resize_cubic(ctx, pool, slots, n, out_w, out_h, mode, out, (cudaStream_t)stream);
+}
+
+int cb_video_tube(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int out_w, int out_h, const float mean[3],
+                  const float std_[3], float* out_f32, uint8_t* out_u8, void* stream) {
+  if (!ctx) return CB_ERR_ARG;
+  return cb::run_video_tube(ctx, pool, slots, n, out_w, out_h, mean, std_, out_f32, out_u8, (cudaStream_t)stream);
 }
 
 int cb_nv12_to_rgb(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, uint8_t* out, void* stream) {

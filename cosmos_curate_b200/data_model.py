@@ -84,7 +84,9 @@ except Exception:  # noqa: BLE001
         encoded_data: LazyData = attrs.field(factory=LazyData, converter=LazyData.coerce)
         extracted_frames: LazyData = attrs.field(factory=LazyData)
         aesthetic_score: float | None = None
+        cosmos_embed1_frames: LazyData = attrs.field(factory=LazyData, converter=LazyData.coerce)
         cosmos_embed1_embedding: np.ndarray | None = None
+        intern_video_2_frames: LazyData = attrs.field(factory=LazyData, converter=LazyData.coerce)
         intern_video_2_embedding: np.ndarray | None = None
         openai_embedding: np.ndarray | None = None
         errors: dict[str, str] = attrs.Factory(dict)

@@ -16,6 +16,8 @@ from ._lib import SurfacePool, VitCfg, check
 
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)  # reference: cosmos_curate/models/clip.py:57-60
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+IMAGENET_MEAN = (0.485, 0.456, 0.406)  # reference: cosmos_curate/models/internvideo2_mm.py:378-379
+IMAGENET_STD = (0.229, 0.224, 0.225)
 
 _TORCH_DT = {torch.float16: _lib.DT_F16, torch.bfloat16: _lib.DT_BF16, torch.float32: _lib.DT_F32}
 
@@ -146,6 +148,16 @@ class Context:
         check(self.lib.cb_resize_cubic_u8(self.h, C.byref(pool.desc), ptr, len(arr), out_w, out_h, mode, out.data_ptr(), _stream_ptr()),
               "cb_resize_cubic_u8", self.h)  # fmt: skip
         return out
+
+    def video_tube(self, pool: "Pool", out_w: int, out_h: int, slots=None, mean=IMAGENET_MEAN, std=IMAGENET_STD, want_u8: bool = False):
+        """cv2.resize(frame, (out_w, out_h)) + ((x / 255 - mean) / std) per frame -> float32 cuda [n, 3, out_h, out_w]
+        (internvideo2_mm.py:385-405); with want_u8 also the resized uint8 [n, out_h, out_w, 3] frames."""
+        arr, ptr = self._slots(pool, slots)
+        out = torch.empty((len(arr), 3, out_h, out_w), dtype=torch.float32, device=pool.buf.device)
+        u8 = torch.empty((len(arr), out_h, out_w, 3), dtype=torch.uint8, device=pool.buf.device) if want_u8 else None
+        check(self.lib.cb_video_tube(self.h, C.byref(pool.desc), ptr, len(arr), out_w, out_h, _f3(mean), _f3(std), out.data_ptr(),
+                                     u8.data_ptr() if want_u8 else None, _stream_ptr()), "cb_video_tube", self.h)  # fmt: skip
+        return (out, u8) if want_u8 else out
 
     def nv12_to_rgb(self, pool: "Pool", slots=None) -> torch.Tensor:
         arr, ptr = self._slots(pool, slots)

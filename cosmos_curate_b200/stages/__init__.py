@@ -6,6 +6,7 @@ Same-name drop-ins (constructor arguments, task mutations and error convention o
     VideoFrameExtractionStage   cosmos_curate/pipelines/video/clipping/frame_extraction_stages.py:71-204
     ImageCLIPEmbeddingStage     cosmos_curate/pipelines/image/embedding/image_embedding_stages.py:219-283
     TransNetV2ClipExtractionStage  cosmos_curate/pipelines/video/clipping/transnetv2_extraction_stages.py:39-212
+    InternVideo2FrameCreationStage  cosmos_curate/pipelines/video/embedding/internvideo2_stages.py:43-184 (the tower's input tube)
 New fused stage (replaces ClipFrameExtractionStage -> AestheticFilterStage [-> clip embedding] in one GPU pass):
     NvdecClipAestheticStage
     NvdecShotDetectionStage      (VideoFrameExtractionStage -> TransNetV2ClipExtractionStage, frames stay in HBM)
@@ -16,5 +17,6 @@ from .aesthetic_filter import AestheticFilterStage  # noqa: F401
 from .clip_stream_copy import ClipStreamCopyStage  # noqa: F401
 from .fused_clip import NvdecClipAestheticStage  # noqa: F401
 from .frame_extraction import ClipFrameExtractionStage, VideoFrameExtractionStage  # noqa: F401
+from .internvideo2_frames import InternVideo2FrameCreationStage  # noqa: F401
 from .image_embedding import ImageCLIPEmbeddingStage  # noqa: F401
 from .transnetv2_extraction import NvdecShotDetectionStage, TransNetV2ClipExtractionStage  # noqa: F401

@@ -118,6 +118,16 @@ int cb_preprocess_bilinear_u8(cb_ctx* ctx, const cb_surface_pool* pool, const in
 int cb_resize_cubic_u8(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int out_w, int out_h, int mode,
                        uint8_t* out, void* stream);
 
+/* The video embedding towers' input formulation, per selected frame: cv2.resize(frame, (out_w, out_h)) [INTER_LINEAR on
+ * uint8: OpenCV's fixed-point arithmetic bit for bit, incl. its INTER_AREA reroute of an exact 2x2 decimation] then
+ * ((x / 255 - mean) / std) in float32.  Replaces InternVideo2MultiModality._construct_frames / _normalize
+ * (cosmos_curate/models/internvideo2_mm.py:385-405), called by InternVideo2FrameCreationStage
+ * (pipelines/video/embedding/internvideo2_stages.py:177).  RGB or NV12 pools (NV12 is colour-converted per tap).
+ * out_f32 [n][3][out_h][out_w] and/or out_u8 [n][out_h][out_w][3] (the resized frames before normalisation); either may be
+ * null, not both. */
+int cb_video_tube(cb_ctx* ctx, const cb_surface_pool* pool, const int32_t* slots, int n, int out_w, int out_h, const float mean[3],
+                  const float std_[3], float* out_f32, uint8_t* out_u8, void* stream);
+
 /* Full-resolution NV12 -> RGB24 (HWC, tightly packed): what decode_video_cpu_frame_ids returns per
  * frame (decoder_utils.py:439-451) / cvcuda.cvtcolor_into (nvcodec_utils.py:178).  Only for callers that
  * must hand RGB frames to an unmodified downstream stage. */

@@ -310,6 +310,46 @@ def gen_resize_cubic() -> None:
     print("resize_cubic_ref.npz", {k: v.shape for k, v in out.items() if k.endswith("_ipp")})
 
 
+def gen_video_tube() -> None:
+    """InternVideo2 input tubes from the reference's own `_construct_frames` / `_construct_image` (internvideo2_mm.py:390-415).
+    Small target sizes keep the fixture small; the 224 x 224 cases store a sha256 of the float32 tube, the frames being
+    regenerated from the seed by the test."""
+    import hashlib
+
+    import cv2
+
+    iv2 = ref_import.internvideo2_formulator()
+    rng = np.random.default_rng(20250924)
+
+    def frames(n, h, w):
+        out = []
+        for _ in range(n):
+            smooth = cv2.GaussianBlur(rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8), (0, 0), 1.2)
+            out.append(np.where(rng.random((h, w, 1)) < 0.5, smooth, rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)).astype(np.uint8))
+        return out
+
+    out = {}
+    # name: (n_frames, (src_h, src_w), target_size = (w, h))
+    cases = {"down_21f": (21, (90, 122), (56, 40)), "decimate2x_8f": (8, (80, 112), (56, 40)), "up_9f": (9, (20, 30), (56, 40)),
+             "same_17f": (17, (40, 56), (56, 40)), "tall_16f": (16, (131, 37), (40, 56))}
+    for name, (n, (h, w), tsize) in cases.items():
+        fr = frames(n, h, w)
+        out[name + "_in"] = np.stack(fr)
+        out[name + "_size"] = np.array(tsize)
+        out[name + "_tube"] = iv2._construct_frames(fr, fnum=8, target_size=tsize)
+        out[name + "_image"] = iv2._construct_image(fr[-1], target_size=tsize)
+    out["short_tube"] = iv2._construct_frames(frames(5, 16, 16), fnum=8, target_size=(8, 8))  # too few frames: empty array
+    for name, (n, (h, w)) in {"hd": (11, (1080, 1920)), "sd": (21, (480, 854)), "uhd": (8, (2160, 3840))}.items():
+        big_rng = np.random.default_rng([20250924, h])
+        fr = [big_rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8) for _ in range(n)]
+        tube = iv2._construct_frames(fr, fnum=8, target_size=(224, 224))
+        out[name + "_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(tube).tobytes()).digest(), dtype=np.uint8)
+        out[name + "_shape"] = np.array([n, h, w])
+    out["cv2_version"] = np.frombuffer(cv2.__version__.encode(), dtype=np.uint8)
+    np.savez_compressed(OUT / "video_tube_ref.npz", **out)
+    print("video_tube_ref.npz", {k: v.shape for k, v in out.items() if k.endswith("_tube")})
+
+
 def gen_dedup() -> None:
     core = ref_import.dedup_core()
     out = {}
@@ -341,6 +381,7 @@ def main() -> None:
     gen_transnet()
     gen_resize_cubic()
     gen_dedup()
+    gen_video_tube()
 
 
 if __name__ == "__main__":

@@ -128,3 +128,25 @@ def dedup_core():
     ns: dict = {}
     exec(compile(src, str(path), "exec"), ns)  # noqa: S102 - reference code, build container only
     return lambda E, tile=4096: ns["_core"](np.ascontiguousarray(E, dtype=np.float32).copy(), tile, np)
+
+
+def internvideo2_formulator():
+    """An `InternVideo2MultiModality` carrying only what `_construct_frames` / `_construct_image` / `_normalize` read
+    (cosmos_curate/models/internvideo2_mm.py:378-415): the reference's own frame formulation, no weights, no tower."""
+    _install_stubs()
+    import importlib
+
+    import numpy as np
+
+    if "easydict" not in sys.modules:
+        try:
+            import easydict  # noqa: F401
+        except ImportError:
+            stub = types.ModuleType("easydict")
+            stub.EasyDict = dict  # only used to wrap the tower's config
+            sys.modules["easydict"] = stub
+    mod = importlib.import_module("cosmos_curate.models.internvideo2_mm")
+    obj = object.__new__(mod.InternVideo2MultiModality)
+    obj._v_mean = np.array([0.485, 0.456, 0.406], dtype=np.float32).reshape(1, 1, 3)  # setup(), :378-379
+    obj._v_std = np.array([0.229, 0.224, 0.225], dtype=np.float32).reshape(1, 1, 3)
+    return obj

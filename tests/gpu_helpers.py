@@ -16,14 +16,14 @@ def ctx():
     c.close()
 
 
-def nv12_pool(ctx, frames_nv12, width: int, height: int, pitch: int, luma_rows: int):
+def nv12_pool(ctx, frames_nv12, width: int, height: int, pitch: int, luma_rows: int, colour: str = "opencv"):
     rows = luma_rows + height // 2
     buf = np.zeros((len(frames_nv12), rows, pitch), dtype=np.uint8)
     for i, f in enumerate(frames_nv12):
         buf[i, :height, :width] = f[:height, :width]
         buf[i, luma_rows : luma_rows + height // 2, :width] = f[height:, :width]
     t = torch.from_numpy(buf).cuda()
-    return ctx.nv12_pool(t, width, height, luma_rows)
+    return ctx.nv12_pool(t, width, height, luma_rows, colour=colour)
 
 
 def u8_budget(got: np.ndarray, want: np.ndarray, frac: float = 1e-4):

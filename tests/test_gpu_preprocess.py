@@ -227,3 +227,61 @@ def test_clip_preprocess_4k_rgb_frames_strong_downscale(ctx):
     gp = ctx.preprocess_clip(pool, dtype=torch.float16, layout="patch", patch=14, k_pad=640).cpu().numpy()
     ref = preprocess.to_patches(want32.astype(np.float16), 14, 640)
     assert (gp != ref).mean() < 2e-4  # the same <= 1e-4 u8 budget seen through the LUT
+
+
+# ------------------------------------------------------------------------------------ video-tower tubes (InternVideo2 input formulation)
+def test_video_tube_matches_the_reference_formulation_bit_for_bit(ctx):
+    """cb_video_tube against tubes produced by the reference's own InternVideo2MultiModality._construct_frames
+    (internvideo2_mm.py:390-405: cv2.resize + numpy float32 normalise): every float32 bit equal - linear taps, the 2x2
+    decimation cv2 reroutes to INTER_AREA, the copy for equal sizes, upscaling, a tall source - and, at the real 224 x 224
+    size, a sha256 of the whole tube for SD / HD / 4K sources."""
+    import hashlib
+
+    from conftest import load_golden
+    from cosmos_curate_b200.models.internvideo2_frames import InternVideo2FrameFormulator, select_frame_ids
+    from oracle import video_tube as T
+
+    g = load_golden("video_tube_ref.npz")
+    for name in sorted(k[:-3] for k in g.files if k.endswith("_in")):
+        fr, (tw, th) = g[name + "_in"], (int(v) for v in g[name + "_size"])
+        ids = select_frame_ids(len(fr), 8)
+        assert ids == T.select_frames(len(fr), 8)
+        pool = ctx.rgb_pool(torch.from_numpy(np.ascontiguousarray(fr[ids])).cuda())
+        tube, u8 = ctx.video_tube(pool, tw, th, want_u8=True)
+        np.testing.assert_array_equal(tube.cpu().numpy()[None], g[name + "_tube"], err_msg=name)
+        np.testing.assert_array_equal(u8.cpu().numpy(), np.stack([T.resize_linear_u8(fr[i], th, tw) for i in ids]), err_msg=name)
+    m = InternVideo2FrameFormulator()
+    m.setup()
+    assert m.get_target_num_frames() == 8 and m.model_id_names == []
+    for name in ("sd", "hd", "uhd"):
+        n, h, w = (int(v) for v in g[name + "_shape"])
+        rng = np.random.default_rng([20250924, h])
+        fr = [rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8) for _ in range(n)]
+        tube = m.formulate_input_frames(fr)
+        assert tube.shape == (1, 8, 3, 224, 224) and tube.dtype == np.float32
+        assert hashlib.sha256(np.ascontiguousarray(tube).tobytes()).digest() == g[name + "_sha256"].tobytes(), name
+        if name == "sd":
+            np.testing.assert_array_equal(m.formulate_input_image(fr[3]), T.construct_image(fr[3]))
+            np.testing.assert_array_equal(tube, T.construct_frames(fr))
+    assert m.formulate_input_frames(fr[:5]).shape == (0,)  # too few frames: the reference's empty float32 array
+    mixed = [np.full((40, 60, 3), 7, np.uint8)] * 4 + [np.full((50, 30, 3), 200, np.uint8)] * 4  # frame-by-frame resize: sizes may differ
+    np.testing.assert_array_equal(m.formulate_input_frames(mixed), T.construct_frames(mixed))
+
+
+@pytest.mark.parametrize("colour", ["swscale", "opencv"])
+def test_video_tube_from_nv12_surfaces(ctx, colour):
+    """NV12 decode surfaces (colour-converted per tap) -> tube, bit-exact with convert-then-formulate on the CPU."""
+    from cosmos_curate_b200._lib import CurateB200Error
+    from oracle import video_tube as T
+
+    conv = color.nv12_to_rgb_swscale if colour == "swscale" else color.nv12_to_rgb
+    for (h, w, pitch, rows) in [(1080, 1920, 2048, 1088), (360, 640, 640, 360), (448, 448, 512, 448)]:
+        frames = [color.synthetic_nv12(h, w, seed=300 + s) for s in range(3)]
+        pool = _nv12_pool(ctx, frames, w, h, pitch, rows, colour=colour)
+        rgb = [conv(f, h, w) for f in frames]
+        slots = np.array([2, 0, 2, 1], dtype=np.int32)
+        got = ctx.video_tube(pool, 224, 224, slots=slots).cpu().numpy()
+        want = T.construct_frames([rgb[i] for i in slots], fnum=4)[0]
+        np.testing.assert_array_equal(got, want)
+    with pytest.raises(CurateB200Error):
+        ctx.video_tube(pool, 0, 224)

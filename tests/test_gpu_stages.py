@@ -437,3 +437,60 @@ def test_fused_stage_mixed_resolutions_in_one_call(ctx):
         assert clip.aesthetic_score == alone[k][0] and np.array_equal(clip.openai_embedding, alone[k][1]), k
     assert stage.last_call_stats["batches"] >= 4
     stage.destroy()
+
+
+def test_internvideo2_frame_creation_stage_matches_the_reference_formulation(ctx):
+    """InternVideo2FrameCreationStage (internvideo2_stages.py:43-184): `clip.intern_video_2_frames` bit-equal to the
+    reference's _construct_frames arithmetic (oracle/video_tube.py, pinned to the imported reference) on the frames the
+    upstream extraction stage delivered; the NVDEC-direct source gives the same tube without host frames; short clips are
+    re-sampled at a doubled rate; the reference's error keys."""
+    from cosmos_curate_b200.data_model import Clip
+    from cosmos_curate_b200.interfaces import run_pipeline
+    from cosmos_curate_b200.stages import ClipFrameExtractionStage, InternVideo2FrameCreationStage
+    from oracle import video_tube as T
+    from tools import synth_h264
+
+    sig2 = "FrameExtractionPolicy.sequence-2000"
+    sintel = (GOLDEN / "sintel_clip_10s.mp4").read_bytes()
+    short = synth_h264.make_clip(640, 360, 30, 1.5, seed=9, gop=30, pan=(1, 2))  # 45 frames: 2 fps -> 4, 4 fps -> 7, 8 fps -> 13 frames
+    task = _clip_task(sintel)
+    task.video.clips.append(Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0, 1.5), encoded_data=short))
+    task.video.clips.append(Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0, 1)))  # no data
+    task.video.clips.append(Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0, 1), encoded_data=sintel))  # data, no frames
+    extract = ClipFrameExtractionStage(target_fps=[2])
+    extract.stage_setup()
+    extract.process_data([task])
+    task.video.clips[3].extracted_frames.drop()
+    frames = [c.extracted_frames.resolve()[sig2].copy() for c in task.video.clips[:2]]
+    assert frames[0].shape == (21, 480, 854, 3) and frames[1].shape[0] < 8
+    stage = InternVideo2FrameCreationStage(target_fps=2.0, log_stats=True)
+    assert stage.resources.cpus == 1.0 and stage.model.get_target_num_frames() == 8
+    out = run_pipeline([task], [stage])
+    assert out is not None and "InternVideo2FrameCreationStage" in task.stage_perf
+    c0, c1, c2, c3 = task.video.clips
+    tube0 = c0.intern_video_2_frames.resolve()
+    assert tube0.shape == (1, 8, 3, 224, 224) and tube0.dtype == np.float32
+    np.testing.assert_array_equal(tube0, T.construct_frames(list(frames[0])))
+    assert not c0.extracted_frames  # last consumer: dropped (internvideo2_stages.py:178)
+    assert c2.errors == {"encoded_data": "empty"} and not c2.intern_video_2_frames
+    assert c3.errors == {f"frames-{sig2}": "missing"} and not c3.intern_video_2_frames
+    # short clip: re-extracted at 8 fps (13 frames), stride 1, first 8 kept
+    ext8 = ClipFrameExtractionStage(target_fps=[8])
+    ext8.stage_setup()
+    t8 = _clip_task(short)
+    ext8.process_data([t8])
+    f8 = t8.video.clips[0].extracted_frames.resolve()["FrameExtractionPolicy.sequence-8000"]
+    assert f8.shape[0] >= 8
+    np.testing.assert_array_equal(c1.intern_video_2_frames.resolve(), T.construct_frames(list(f8)))
+    # NVDEC-direct source: same tubes, no upstream extraction stage
+    t_dir = _clip_task(sintel)
+    t_dir.video.clips.append(Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0, 1.5), encoded_data=short))
+    t_dir.video.clips.append(Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0, 1), encoded_data=b"\x00" * 4096))
+    tiny = synth_h264.make_clip(320, 192, 30, 0.2, seed=3, gop=30)  # 6 frames: never reaches 8 below 20 fps
+    t_dir.video.clips.append(Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0, 0.2), encoded_data=tiny))
+    run_pipeline([t_dir], [InternVideo2FrameCreationStage(target_fps=2.0, source="nvdec")])
+    d0, d1, d2, d3 = t_dir.video.clips
+    np.testing.assert_array_equal(d0.intern_video_2_frames.resolve(), tube0)
+    np.testing.assert_array_equal(d1.intern_video_2_frames.resolve(), c1.intern_video_2_frames.resolve())
+    assert d2.errors["frame_extraction"] == "video_decode_failed" and not d2.intern_video_2_frames
+    assert d3.intern_video_2_frames.resolve().shape == (0,) and not d3.errors  # the reference's empty array for too short clips

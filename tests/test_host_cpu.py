@@ -190,3 +190,38 @@ def test_pynvc_target_size_rule():
     assert sampling.pynvc_target_size(854, 480) == (285, 160)    # factor 3: round(284.67), 160
     assert sampling.pynvc_target_size(200, 100) == (200, 100)
     assert sampling.pynvc_target_size(1920, 1080, 48, 27) == (48, 27)
+
+
+def test_internvideo2_frame_selection_and_resampling_rule():
+    """Host logic of InternVideo2FrameCreationStage: `frames[::len // fnum][:fnum]` (internvideo2_mm.py:399-400) against the
+    oracle's restatement, the rate-doubling rule for short clips (internvideo2_stages.py:157-176) expressed on id lists,
+    and the error keys that need no GPU."""
+    import uuid
+
+    from cosmos_curate_b200.data_model import Clip, SplitPipeTask, Video
+    from cosmos_curate_b200.models.internvideo2_frames import select_frame_ids
+    from cosmos_curate_b200.stages.internvideo2_frames import InternVideo2FrameCreationStage, sampled_ids_with_regen
+    from oracle import sampling as O
+    from oracle import video_tube as T
+
+    for n in range(0, 70):
+        assert select_frame_ids(n, 8) == T.select_frames(n, 8) == (list(range(n))[:: max(1, n // 8)][:8] if n >= 8 else [])
+    ts = (np.arange(300) / 30.0).astype(np.float32)
+    ids, used = sampled_ids_with_regen(ts, 2.0, 8)
+    assert used == 2.0 and len(ids) == 21
+    ts = (np.arange(45) / 30.0).astype(np.float32)  # 1.5 s: 2 fps -> 4 frames, 4 fps -> 7, 8 fps -> 13
+    ids, used = sampled_ids_with_regen(ts, 2.0, 8)
+    want_ids, want_counts, _ = O.sample_closest(ts, 8.0, start=ts[0], stop=ts[-1], endpoint=True, dedup=True)
+    assert used == 8.0 and np.array_equal(ids, np.repeat(want_ids, want_counts)) and len(ids) >= 8
+    ts = (np.arange(6) / 30.0).astype(np.float32)  # 0.2 s: still < 8 frames at 16 fps, 32 fps is beyond max_fps = 20
+    ids, used = sampled_ids_with_regen(ts, 2.0, 8)
+    assert used == 16.0 and len(ids) < 8
+    stage = InternVideo2FrameCreationStage(target_fps=2.0)
+    assert stage._frame_extraction_signature == "FrameExtractionPolicy.sequence-2000"
+    with pytest.raises(ValueError, match="source"):
+        InternVideo2FrameCreationStage(source="cpu")
+    clips = [Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0.0, 1.0)), Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0.0, 1.0), encoded_data=b"xx")]
+    task = SplitPipeTask(session_id="s", video=Video(input_video="v.mp4", clips=clips))
+    assert stage.process_data([task]) == [task]  # neither clip reaches the GPU
+    assert clips[0].errors == {"encoded_data": "empty"}
+    assert clips[1].errors == {"frames-FrameExtractionPolicy.sequence-2000": "missing"}

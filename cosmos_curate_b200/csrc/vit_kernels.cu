@@ -7,6 +7,8 @@
 //   clip_tail_kernel       post_layernorm(CLS) -> visual_projection -> L2 normalise -> aesthetic affine head
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include <type_traits>
 
 #include "common.h"
@@ -29,14 +31,18 @@ __device__ __forceinline__ float warp_max(float v) {
 // One warp per row; D <= 32*4*kMaxChunks.  Two-pass statistics in registers (mean, then centred variance).
 constexpr int kLnMaxChunks = 12;  // D <= 1536
 
-template <bool OUT_F16>
+// CHUNKS > 0: the row length is the compile-time constant 128 * CHUNKS (the towers' widths get their own instantiation: the
+// register array is exactly the row, 46 instead of 78 registers at 1024, so more rows are in flight per SM); CHUNKS == 0: any
+// multiple of 128 up to 128 * kLnMaxChunks.  Same operations in the same order either way.
+template <bool OUT_F16, int CHUNKS = 0>
 __device__ __forceinline__ void ln_row(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                        void* __restrict__ y, int d, float eps, int lane, const float* __restrict__ add = nullptr) {
-  float4 v[kLnMaxChunks];
-  const int chunks = d >> 7;  // 128 floats per warp pass
+  constexpr int kMax = CHUNKS > 0 ? CHUNKS : kLnMaxChunks;
+  float4 v[kMax];
+  const int chunks = CHUNKS > 0 ? CHUNKS : d >> 7;  // 128 floats per warp pass
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i)
+  for (int i = 0; i < kMax; ++i)
     if (i < chunks) {
       v[i] = ((const float4*)x)[lane + 32 * i];
       if (add) {
@@ -48,14 +54,14 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ x, const float*
   const float mean = warp_sum(s) / (float)d;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i)
+  for (int i = 0; i < kMax; ++i)
     if (i < chunks) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
       q += (a * a + b * b) + (c * c + e * e);
     }
   const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
 #pragma unroll
-  for (int i = 0; i < kLnMaxChunks; ++i)
+  for (int i = 0; i < kMax; ++i)
     if (i < chunks) {
       const float4 g = __ldg((const float4*)gamma + lane + 32 * i), b = __ldg((const float4*)beta + lane + 32 * i);
       const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
@@ -71,11 +77,12 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ x, const float*
     }
 }
 
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+template <int CHUNKS, int MINB>
+__global__ void __launch_bounds__(256, MINB) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __half* __restrict__ y, int rows, int d, float eps) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  ln_row<true>(x + (size_t)row * d, gamma, beta, y + (size_t)row * d, d, eps, threadIdx.x & 31);
+  ln_row<true, CHUNKS>(x + (size_t)row * d, gamma, beta, y + (size_t)row * d, d, eps, threadIdx.x & 31);
 }
 
 // ------------------------------------------------------------------------------- token assembly
@@ -522,7 +529,21 @@ int layernorm_f16(cb_ctx* ctx, const float* x, const float* gamma, const float* 
   if (rows <= 0) return CB_OK;
   if (d % 128 || d > 128 * kLnMaxChunks) return fail(ctx, CB_ERR_UNSUPPORTED, "layernorm: d=%d must be a multiple of 128 and <= %d", d, 128 * kLnMaxChunks);
   mark_launch(ctx, CB_PROF_LAYERNORM, stream);
-  layernorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, gamma, beta, (__half*)y, rows, d, eps);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  static const int variant = [] {  // A/B switch: 0 = generic instantiation, 1 = row-length instantiations, 2 = + 4 blocks per SM at <= 1024
+    const char* e = std::getenv("CB_LN_VARIANT");
+    return e ? std::atoi(e) : 2;
+  }();
+  const int chunks = variant == 0 ? 0 : d >> 7;
+  switch (chunks) {  // ViT-B 768, ViT-L 1024, SoViT-400m 1152
+    case 6: layernorm_kernel<6, 4><<<grid, 256, 0, stream>>>(x, gamma, beta, (__half*)y, rows, d, eps); break;
+    case 8:
+      if (variant == 1) layernorm_kernel<8, 3><<<grid, 256, 0, stream>>>(x, gamma, beta, (__half*)y, rows, d, eps);
+      else layernorm_kernel<8, 4><<<grid, 256, 0, stream>>>(x, gamma, beta, (__half*)y, rows, d, eps);
+      break;
+    case 9: layernorm_kernel<9, 3><<<grid, 256, 0, stream>>>(x, gamma, beta, (__half*)y, rows, d, eps); break;
+    default: layernorm_kernel<0, 3><<<grid, 256, 0, stream>>>(x, gamma, beta, (__half*)y, rows, d, eps); break;
+  }
   CB_CUDA(ctx, cudaGetLastError());
   return CB_OK;
 }

@@ -474,17 +474,33 @@ class DecoderPool:
             except OSError:
                 pass
 
-    def decoder(self) -> Decoder:
-        d = getattr(self._tls, "dec", None)
+    MAX_SHAPES = 4  # sessions a worker thread keeps, one per stream shape (least recently used closed beyond that)
+
+    def decoder(self, shape=None) -> Decoder:
+        """This thread's session for streams of `shape` (any hashable, normally (width, height)).  A cuvid decoder is bound to
+        one coded size: feeding a session a clip of another resolution destroys and re-creates it (hundreds of ms, serialised
+        in the driver - measured: a 720p / 1080p / 4K mix ran 4-12x below the NVDEC rate with one session per thread), so a
+        thread keeps one session per shape instead."""
+        decs = getattr(self._tls, "decs", None)
+        if decs is None:
+            decs = self._tls.decs = {}
+        d = decs.pop(shape, None)
         if d is None or d.h is None:
-            d = self._tls.dec = Decoder(self.ctx)
+            while len(decs) >= self.MAX_SHAPES:
+                old = decs.pop(next(iter(decs)))
+                with self._lock:
+                    if old in self._decoders:
+                        self._decoders.remove(old)
+                old.close()
+            d = Decoder(self.ctx)
             with self._lock:
                 self._decoders.append(d)
+        decs[shape] = d  # most recently used last
         return d
 
-    def submit(self, fn, *args, **kw):
-        """fn(decoder, *args, **kw) on a pool thread with that thread's own session."""
-        return self._tp.submit(lambda: fn(self.decoder(), *args, **kw))
+    def submit(self, fn, *args, shape=None, **kw):
+        """fn(decoder, *args, **kw) on a pool thread with that thread's own session (for streams of `shape`, see decoder())."""
+        return self._tp.submit(lambda: fn(self.decoder(shape), *args, **kw))
 
     def close(self) -> None:
         self._tp.shutdown(wait=True)

@@ -238,7 +238,7 @@ class NvdecClipAestheticStage(CuratorStage):
             ring_pos[size] = (r + 1) % self.RING
             pool = self._pool(size, r)
             slots_of[k] = (pool, k % self.RING)
-            futs[k] = [self._decode_pool.submit(decode_one, data, ids, pool, first) for _, data, ids, first in items]
+            futs[k] = [self._decode_pool.submit(decode_one, data, ids, pool, first, shape=size) for _, data, ids, first in items]
 
         def finalize(k):
             """Batch k's results are on the host once its event has fired: write them onto the clips."""

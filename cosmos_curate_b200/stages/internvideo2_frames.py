@@ -158,7 +158,7 @@ class InternVideo2FrameCreationStage(CuratorStage):
             pool = self._pool(size, r, cap)
             futs, first = [], 0
             for _, data, ids, _ in clips:
-                futs.append((first, self._decoders().submit(decode_one, data, ids, pool, first)))
+                futs.append((first, self._decoders().submit(decode_one, data, ids, pool, first, shape=size)))
                 first += len(ids)
             return pool, futs
 

@@ -599,7 +599,8 @@ def secondary_configs(ctx, torch, clips_1080p: list[bytes], clips_4k, args, clip
                         "filter (BASELINE.json configs[4] mix on one GPU; the reference's split / caption / writer stages around it are out of scope)",
             "e2e_clips_per_sec": cps, "clips": n, "decoded_megapixels_per_sec": cps * 300 * mean_px / 1e6,
             "kernel_ms_over_warmup_and_timed_call": {k: v["ms"] for k, v in prof.items() if v["launches"] and k != "other"},  # "other" would absorb the idle gaps while the SMs wait for NVDEC
-            "note": "NVDEC-bound: pixel rate equals the 1080p run's (decoded fps x pixels per frame)"}  # fmt: skip
+            "note": "compare decoded_megapixels_per_sec with the 1080p ceiling (decode_roofline.decode_only_frames_per_sec x 2.07 Mpx); one NVDEC session per stream shape per "
+                    "worker thread - a session that is fed another resolution is destroyed and re-created by the driver (tools/mixed_decode_probe.py)"}  # fmt: skip
 
     # ---- video-tower input tubes (N5, formulation only): 1080p clips -> 2 fps -> 8 kept frames -> cv2-bilinear 224 x 224 + ImageNet normalise
     from cosmos_curate_b200.runtime import alloc_nv12_pool

@@ -194,3 +194,40 @@ def test_nvdec_matches_libavcodec_on_residual_coded_clip(ctx, tmp_path):
         np.testing.assert_array_equal(uv[:, 0::2], pcm[256:320].reshape(8, 8)[2:, 2:])  # Cb
         np.testing.assert_array_equal(uv[:, 1::2], pcm[320:384].reshape(8, 8)[2:, 2:])  # Cr
     dec.close()
+
+
+def test_decoder_pool_keeps_one_session_per_stream_shape(ctx):
+    """runtime.DecoderPool: a worker thread owns one NVDEC session per stream shape (re-creating a session at a resolution
+    switch costs ~0.4 s, tools/mixed_decode_probe.py), at most MAX_SHAPES of them (least recently used closed), and the frames
+    do not depend on which session decoded them."""
+    from cosmos_curate_b200.runtime import Decoder, DecoderPool, alloc_nv12_pool
+    from tools import synth_h264
+
+    shapes = [(320, 192), (640, 360), (352, 288), (480, 272), (256, 144)]
+    clips = {s: synth_h264.make_clip(s[0], s[1], 30, 0.2, seed=i, gop=30) for i, s in enumerate(shapes)}
+    pools = {s: alloc_nv12_pool(ctx, 2, s[0], s[1]) for s in shapes}
+    ids, slots = np.array([0, 5], dtype=np.int32), np.arange(2, dtype=np.int32)
+    ref = {}
+    one = Decoder(ctx)
+    for s in shapes:
+        one.decode(clips[s], ids, pools[s], slots)
+        ref[s] = pools[s].buf.cpu().numpy().copy()
+        pools[s].buf.zero_()
+    one.close()
+    dp = DecoderPool(ctx, 1)  # one worker thread: every job meets the same thread-local session table
+    seen = []
+
+    def job(dec, s):
+        seen.append(id(dec))
+        return dec.decode(clips[s], ids, pools[s], slots)["frames_emitted"]
+
+    for s in shapes[:2] * 3:
+        assert dp.submit(job, s, shape=s).result() == 2
+    assert len(set(seen)) == 2 and seen[0] == seen[2] == seen[4] and seen[1] == seen[3] == seen[5]
+    for s in shapes:  # five shapes through a table of MAX_SHAPES = 4
+        assert dp.submit(job, s, shape=s).result() == 2
+        np.testing.assert_array_equal(pools[s].buf.cpu().numpy(), ref[s])
+    assert len(dp._decoders) == DecoderPool.MAX_SHAPES
+    assert dp.submit(job, shapes[0], shape=None).result() == 2  # shape-less callers keep working (one shared session)
+    dp.close()
+    assert not dp._decoders

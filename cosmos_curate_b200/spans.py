@@ -1,0 +1,131 @@
+"""Fixed-stride clip spans: the host arithmetic of the reference's second splitting algorithm
+(`--splitting-algorithm fixed-stride`, cosmos_curate/pipelines/video/clipping/clip_extraction_stages.py:444-660): the caller
+side of the hot path - it decides which `(start_s, end_s)` windows of a source video become clips.  Same function names minus
+the leading underscore, same results (floats compared bit for bit in tests/test_spans_cpu.py against the reference functions
+executed from their own source).
+
+    videos_durations              num_frames / framerate per video, -1.0 when unknown (:490-512; not last - first timestamp, as
+                                  the reference itself notes)
+    videos_timestamps             per-video timestamp arrays, `errors["timestamps"] = "missing"` on every video without (:465-487)
+    validate_video_timestamps     (:444-462)
+    make_spans_fixed_stride       the window walk (:515-552)
+    make_clip_uuids               uuid5(NAMESPACE_URL, f"{session_id}_{start}_{end}") (:555-565)
+    populate_clips_fixed_stride   one shared span list for all cameras of a session (:568-660)
+    assert_video_clip_alignment   multi-camera time alignment check (pipelines/video/utils/data_model.py:634-690)
+"""
+
+from __future__ import annotations
+
+import uuid
+from uuid import UUID
+
+import numpy as np
+
+from .data_model import Clip, Video
+
+try:
+    from loguru import logger
+except Exception:  # noqa: BLE001
+    import logging
+
+    logger = logging.getLogger(__name__)
+
+
+def validate_video_timestamps(video_timestamps: list[np.ndarray]) -> None:
+    if len(video_timestamps) == 0:
+        msg = "No timestamps found for videos"
+        raise ValueError(msg)
+    if any(len(ts) == 0 for ts in video_timestamps):
+        msg = "Some videos have no timestamps"
+        raise ValueError(msg)
+
+
+def videos_timestamps(videos: list[Video]) -> list[np.ndarray]:
+    for video in videos:
+        if (video.timestamps is None or len(video.timestamps) == 0) and "timestamps" not in video.errors:
+            video.errors["timestamps"] = "missing"
+    missing = [v for v in videos if v.timestamps is None or len(v.timestamps) == 0]
+    if missing:
+        msg = f"Videos missing timestamps: {[str(v.input_video) for v in missing]}"
+        raise ValueError(msg)
+    return [v.timestamps for v in videos]
+
+
+def videos_durations(videos: list[Video]) -> list[float]:
+    def duration(video: Video) -> float:
+        num_frames, framerate = video.metadata.num_frames, video.metadata.framerate
+        if num_frames is None or framerate is None or framerate <= 0:
+            return -1.0
+        return float(num_frames / framerate)
+
+    return [duration(v) for v in videos]
+
+
+def make_spans_fixed_stride(start_s: float, end_s: float, clip_len_s: float, clip_stride_s: float, min_clip_length_s: float) -> list[tuple[float, float]]:
+    """Windows of clip_len_s every clip_stride_s from start_s while the window START is before end_s; the last ones are cut at
+    end_s and kept only if still >= min_clip_length_s long.  The start accumulates by repeated addition (float semantics)."""
+    spans: list[tuple[float, float]] = []
+    start_span_s = start_s
+    while start_span_s < end_s:
+        end_span_s = min(start_span_s + clip_len_s, end_s)
+        if (end_span_s - start_span_s) >= min_clip_length_s:
+            spans.append((start_span_s, end_span_s))
+        start_span_s += clip_stride_s
+    return spans
+
+
+def make_clip_uuids(session_id: str, spans: list[tuple[float, float]]) -> list[UUID]:
+    return [uuid.uuid5(uuid.NAMESPACE_URL, f"{session_id}_{span[0]}_{span[1]}") for span in spans]
+
+
+def populate_clips_fixed_stride(videos: list[Video], session_id: str, clip_len_s: float, clip_stride_s: float, min_clip_length_s: float,
+                                *, limit_clips: int = 0) -> None:  # fmt: skip
+    """Appends one `Clip(uuid, source_video, span)` per span to EVERY video of the session (multi-camera sessions share spans).
+    The window is [0, min over videos of (first timestamp + duration) - max first timestamp), the reference's backwards-compatible
+    choice (:582-638)."""
+    durations = videos_durations(videos)
+    if len([d for d in durations if d > 0]) < len(videos):
+        msg = "Some videos have invalid (zero or negative) duration"
+        raise ValueError(msg)
+    video_ts = videos_timestamps(videos)
+    validate_video_timestamps(video_ts)
+    starts_s = [float(ts[0]) for ts in video_ts]
+    ends_s = [t + d for t, d in zip(starts_s, durations, strict=True)]
+    start_s = max(starts_s)
+    if start_s > 0.1:  # noqa: PLR2004
+        logger.warning(f"Videos start at {start_s:.2f}s (not 0), but duration-based end_s assumes start=0. This may cause unexpected span boundaries.")
+    end_s = min(ends_s) - start_s
+    spans = make_spans_fixed_stride(0.0, end_s, clip_len_s, clip_stride_s, min_clip_length_s)
+    if limit_clips > 0:
+        spans = spans[:limit_clips]
+    for span, clip_uuid in zip(spans, make_clip_uuids(session_id, spans), strict=True):
+        for video in videos:
+            video.clips.append(Clip(uuid=clip_uuid, source_video=str(video.input_video), span=span))
+
+
+def check_clip_time_alignment(clips_per_video: list[list[Clip]]) -> list[int]:
+    """Indices at which the cameras' clips do not share one span (data_model.py:595-631); ValueError when the cameras hold
+    different numbers of clips."""
+    if not clips_per_video:
+        return []
+    counts = [len(c) for c in clips_per_video]
+    if not all(n == counts[0] for n in counts):
+        msg = f"Cannot check time alignment: videos have different clip counts {counts}. All videos must have the same number of clips."
+        raise ValueError(msg)
+    return [i for i in range(counts[0]) if any(c[i].span != clips_per_video[0][i].span for c in clips_per_video[1:])]
+
+
+def assert_video_clip_alignment(videos: list[Video]) -> None:
+    if not videos:
+        return
+    processed = [len(v.clips) + len(v.filtered_clips) for v in videos]
+    if not all(p == processed[0] for p in processed):
+        msg = (f"Multi-cam videos have processed different numbers of clips: {processed}. "
+               "All cameras should process clips together to maintain time alignment.")  # fmt: skip
+        raise ValueError(msg)
+    for name, per_video in (("clips", [v.clips for v in videos]), ("filtered clips", [v.filtered_clips for v in videos])):
+        bad = check_clip_time_alignment(per_video)
+        if bad:
+            spans = [c[bad[0]].span for c in per_video]
+            msg = f"Multi-cam {name} at index {bad[0]} have misaligned spans: {spans}. Misaligned indices: {bad}"
+            raise ValueError(msg)

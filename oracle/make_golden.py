@@ -350,6 +350,37 @@ def gen_video_tube() -> None:
     print("video_tube_ref.npz", {k: v.shape for k, v in out.items() if k.endswith("_tube")})
 
 
+def gen_fixed_stride() -> None:
+    """Spans / clip uuids / populated clips from the reference's own fixed-stride helpers (clip_extraction_stages.py:444-660).
+    Floats are stored as float.hex() strings: the window start accumulates by repeated addition, the comparison is bit for bit."""
+    import types
+
+    f = ref_import.fixed_stride_functions()
+    out: dict = {"spans": [], "populate": []}
+    for end_s in (30.0, 12.0, 9.99, 100.0 / 3.0, 0.0, 7.25):
+        for clip_len, stride, min_len in ((10.0, 10.0, 10.0), (10.0, 5.0, 5.0), (10.0, 10.0, 2.0), (3.3, 0.1 * 7, 1.0), (1.0 / 3.0, 0.1, 0.2), (5.0, 12.5, 0.0)):
+            spans = f["_make_spans_fixed_stride"](0.0, end_s, clip_len, stride, min_len)
+            uuids = f["_make_clip_uuids"]("s3://bucket/session-7", spans)
+            out["spans"].append({"args": [float.hex(0.0), float.hex(end_s), float.hex(clip_len), float.hex(stride), float.hex(min_len)],
+                                 "spans": [[float.hex(a), float.hex(b)] for a, b in spans], "uuids": [str(u) for u in uuids]})
+
+    def video(name, n_frames, fps, t0):
+        ts = (t0 + np.arange(n_frames) / fps).astype(np.float32)
+        return types.SimpleNamespace(input_video=name, timestamps=ts, errors={}, clips=[], metadata=types.SimpleNamespace(num_frames=n_frames, framerate=fps))
+
+    cases = {"single_30s": ([("a.mp4", 900, 30.0, 0.0)], (10.0, 10.0, 10.0, 0)), "single_limit2": ([("a.mp4", 900, 30.0, 0.0)], (10.0, 5.0, 5.0, 2)),
+             "multicam_offsets": ([("cam0.mp4", 900, 30.0, 0.0), ("cam1.mp4", 700, 24.0, 0.5), ("cam2.mp4", 1000, 29.97, 0.25)], (4.0, 2.5, 1.5, 0)),
+             "ntsc": ([("n.mp4", 1799, 30000 / 1001, 0.0)], (10.0, 10.0, 5.0, 0))}
+    for name, (vids, (clip_len, stride, min_len, limit)) in cases.items():
+        vs = [video(*v) for v in vids]
+        f["_populate_clips_fixed_stride"](vs, "session/" + name, clip_len, stride, min_len, limit_clips=limit)
+        out["populate"].append({"name": name, "videos": [[v[0], v[1], float.hex(float(v[2])), float.hex(float(v[3]))] for v in vids],
+                                "args": [float.hex(clip_len), float.hex(stride), float.hex(min_len), limit],
+                                "clips": [[[str(c.uuid), c.source_video, float.hex(c.span[0]), float.hex(c.span[1])] for c in v.clips] for v in vs]})
+    (OUT / "fixed_stride_ref.json").write_text(json.dumps(out, indent=1))
+    print("fixed_stride_ref.json", len(out["spans"]), "span cases,", len(out["populate"]), "populate cases")
+
+
 def gen_dedup() -> None:
     core = ref_import.dedup_core()
     out = {}
@@ -382,6 +413,7 @@ def main() -> None:
     gen_resize_cubic()
     gen_dedup()
     gen_video_tube()
+    gen_fixed_stride()
 
 
 if __name__ == "__main__":

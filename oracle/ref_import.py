@@ -150,3 +150,31 @@ def internvideo2_formulator():
     obj._v_mean = np.array([0.485, 0.456, 0.406], dtype=np.float32).reshape(1, 1, 3)  # setup(), :378-379
     obj._v_std = np.array([0.229, 0.224, 0.225], dtype=np.float32).reshape(1, 1, 3)
     return obj
+
+
+def fixed_stride_functions():
+    """The reference's own span helpers (clip_extraction_stages.py:444-565), executed from its source: the module itself needs ray
+    and the Rust extension at import time, these five functions need numpy and uuid only."""
+    import ast
+    import uuid
+    from uuid import UUID
+
+    import numpy as np
+    import numpy.typing as npt
+
+    path = REFERENCE_ROOT / "cosmos_curate" / "pipelines" / "video" / "clipping" / "clip_extraction_stages.py"
+    tree = ast.parse(path.read_text())
+    wanted = {"_validate_video_timestamps", "_get_videos_timestamps", "_get_videos_durations", "_make_spans_fixed_stride", "_make_clip_uuids",
+              "_populate_clips_fixed_stride"}  # fmt: skip
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {n.name for n in body} == wanted
+    import logging
+    import types
+
+    def clip(uuid, source_video, span):  # noqa: A002 - the reference passes these three keywords (:650-654)
+        return types.SimpleNamespace(uuid=uuid, source_video=source_video, span=span)
+
+    ns = {"np": np, "npt": npt, "uuid": uuid, "UUID": UUID, "Video": object, "Clip": clip, "logger": logging.getLogger("reference")}
+    src = "from __future__ import annotations\n" + "\n\n".join(ast.unparse(n) for n in body)
+    exec(compile(src, str(path), "exec"), ns)  # noqa: S102 - reference code, build container only
+    return {k: ns[k] for k in wanted}

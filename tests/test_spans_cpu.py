@@ -1,0 +1,108 @@
+"""Fixed-stride clip spans (host logic, no GPU): cosmos_curate_b200/spans.py + FixedStrideExtractorStage against
+(a) vectors produced by the reference's own functions executed from source (tests/golden/fixed_stride_ref.json, floats compared
+bit for bit) and (b) the known answers of the reference's test-suite
+(tests/cosmos_curate/pipelines/video/clipping/test_fixed_stride_extraction.py)."""
+
+from __future__ import annotations
+
+import json
+import uuid
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from cosmos_curate_b200 import spans as S
+from cosmos_curate_b200.data_model import Clip, SplitPipeTask, Video
+from cosmos_curate_b200.stages import FixedStrideExtractorStage
+
+
+def _video(name="v.mp4", n_frames=900, fps=30.0, t0=0.0, with_ts=True):
+    v = Video(input_video=name)
+    m = v.metadata
+    m.num_frames, m.framerate, m.height, m.width, m.duration, m.video_codec = n_frames, fps, 1080, 1920, n_frames / fps if fps else 0.0, "h264"
+    if with_ts:
+        v.timestamps = (t0 + np.arange(n_frames) / (fps or 1.0)).astype(np.float32)
+    return v
+
+
+def test_spans_and_uuids_match_the_reference_functions_bit_for_bit():
+    g = json.loads((GOLDEN / "fixed_stride_ref.json").read_text())
+    assert len(g["spans"]) == 36
+    for case in g["spans"]:
+        args = [float.fromhex(a) for a in case["args"]]
+        spans = S.make_spans_fixed_stride(*args)
+        assert [[float.hex(a), float.hex(b)] for a, b in spans] == case["spans"], case["args"]
+        assert [str(u) for u in S.make_clip_uuids("s3://bucket/session-7", spans)] == case["uuids"]
+    for case in g["populate"]:
+        vids = [_video(n, nf, float.fromhex(fps), float.fromhex(t0)) for n, nf, fps, t0 in case["videos"]]
+        clip_len, stride, min_len = (float.fromhex(a) for a in case["args"][:3])
+        S.populate_clips_fixed_stride(vids, "session/" + case["name"], clip_len, stride, min_len, limit_clips=case["args"][3])
+        got = [[[str(c.uuid), c.source_video, float.hex(c.span[0]), float.hex(c.span[1])] for c in v.clips] for v in vids]
+        assert got == case["clips"], case["name"]
+        S.assert_video_clip_alignment(vids)
+
+
+def test_reference_known_answers():
+    """test_fixed_stride_extraction.py:662-805, 959-990 (spans) and :605-660 (durations)."""
+    assert S.make_spans_fixed_stride(0.0, 30.0, 10.0, 10.0, 5.0) == [(0.0, 10.0), (10.0, 20.0), (20.0, 30.0)]
+    assert S.make_spans_fixed_stride(0.0, 30.0, 10.0, 5.0, 5.0) == [(0.0, 10.0), (5.0, 15.0), (10.0, 20.0), (15.0, 25.0), (20.0, 30.0), (25.0, 30.0)]
+    assert S.make_spans_fixed_stride(0.0, 12.0, 10.0, 10.0, 5.0) == [(0.0, 10.0)]  # the 2 s tail is below min_clip_length_s
+    assert S.make_spans_fixed_stride(0.0, 12.0, 10.0, 10.0, 2.0) == [(0.0, 10.0), (10.0, 12.0)]
+    assert S.make_spans_fixed_stride(0.0, 5.0, 10.0, 10.0, 10.0) == []
+    a = S.make_clip_uuids("session", [(0.0, 10.0), (10.0, 20.0)])
+    assert a == S.make_clip_uuids("session", [(0.0, 10.0), (10.0, 20.0)]) and a[0] != a[1]
+    assert a[0] == uuid.uuid5(uuid.NAMESPACE_URL, "session_0.0_10.0")
+    assert S.make_clip_uuids("other", [(0.0, 10.0)]) != a[:1]
+    assert S.videos_durations([]) == []
+    assert S.videos_durations([_video(n_frames=90, fps=30.0), _video(n_frames=100, fps=0.0)]) == [3.0, -1.0]
+    with pytest.raises(ValueError, match="No timestamps"):
+        S.validate_video_timestamps([])
+    with pytest.raises(ValueError, match="no timestamps"):
+        S.validate_video_timestamps([np.zeros(3, np.float32), np.zeros(0, np.float32)])
+    S.validate_video_timestamps([np.zeros(3, np.float32)])
+    cams = [_video("a.mp4"), _video("b.mp4", with_ts=False), _video("c.mp4", with_ts=False)]
+    cams[2].errors["timestamps"] = "demux failed"  # an earlier stage's message is preserved (:1075-1084)
+    with pytest.raises(ValueError, match="missing timestamps"):
+        S.videos_timestamps(cams)
+    assert cams[0].errors == {} and cams[1].errors == {"timestamps": "missing"} and cams[2].errors == {"timestamps": "demux failed"}
+
+
+def test_stage_default_parameters_and_task_mutations():
+    """FixedStrideExtractorStage on SplitPipeTasks (test_fixed_stride_extraction.py:49-145, 245-404, 933-957)."""
+    st = FixedStrideExtractorStage()
+    assert (st.clip_len_s, st.clip_stride_s, st.min_clip_length_s, st._limit_clips) == (10, 10, 10, 0)
+    task = SplitPipeTask(session_id="sess-1", video=_video("s3://b/v.mp4"))
+    assert st.process_data([task]) == [task] and not task.errors
+    clips = task.video.clips
+    assert [c.span for c in clips] == [(0.0, 10.0), (10.0, 20.0), (20.0, 30.0)]
+    assert all(c.source_video == "s3://b/v.mp4" and not c.encoded_data for c in clips)
+    assert clips[1].uuid == uuid.uuid5(uuid.NAMESPACE_URL, "sess-1_10.0_20.0")
+    # limit, overlap, stats
+    t2 = SplitPipeTask(session_id="sess-2", video=_video())
+    FixedStrideExtractorStage(clip_len_s=10, clip_stride_s=5, min_clip_length_s=5, limit_clips=2, log_stats=True).process_data([t2])
+    assert [c.span for c in t2.video.clips] == [(0.0, 10.0), (5.0, 15.0)] and "FixedStrideExtractorStage" in t2.stage_perf
+    # too short for one clip: no clips, no error
+    t3 = SplitPipeTask(session_id="sess-3", video=_video(n_frames=150))
+    FixedStrideExtractorStage().process_data([t3])
+    assert t3.video.clips == [] and not t3.errors
+    # missing timestamps / incomplete metadata: recorded on the task (and the video), never raised
+    t4 = SplitPipeTask(session_id="sess-4", video=_video(with_ts=False))
+    FixedStrideExtractorStage().process_data([t4])
+    assert "failed to populate clips" in t4.errors["FixedStrideExtractorStage"] and t4.video.errors == {"timestamps": "missing"} and not t4.video.clips
+    t5 = SplitPipeTask(session_id="sess-5", video=_video())
+    t5.video.metadata.video_codec = None
+    FixedStrideExtractorStage().process_data([t5])
+    assert "Incomplete metadata" in t5.errors["FixedStrideExtractorStage"] and t5.video.errors == {"metadata": "incomplete"}
+    # multi-camera session: every camera receives the same spans and uuids
+    t6 = SplitPipeTask(session_id="rig", videos=[_video("cam0.mp4"), _video("cam1.mp4", n_frames=600, fps=24.0)])
+    FixedStrideExtractorStage(clip_len_s=10, clip_stride_s=10, min_clip_length_s=5).process_data([t6])
+    a, b = t6.videos
+    assert [c.span for c in a.clips] == [c.span for c in b.clips] == [(0.0, 10.0), (10.0, 20.0), (20.0, 25.0)]  # the shorter camera bounds the window
+    assert [c.uuid for c in a.clips] == [c.uuid for c in b.clips] and {c.source_video for c in b.clips} == {"cam1.mp4"}
+    b.clips[1] = Clip(uuid=b.clips[1].uuid, source_video="cam1.mp4", span=(10.0, 19.0))
+    with pytest.raises(ValueError, match="misaligned"):
+        S.assert_video_clip_alignment(t6.videos)
+    b.clips.pop()
+    with pytest.raises(ValueError, match="different numbers"):
+        S.assert_video_clip_alignment(t6.videos)

@@ -125,6 +125,39 @@ except Exception:  # noqa: BLE001
             m = self.metadata
             return all([m.height, m.width, m.duration, m.framerate, m.num_frames, m.video_codec])
 
+        @property
+        def fraction(self) -> float:  # data_model.py:496-507
+            if self.num_total_clips == 0:
+                return 1.0
+            return (len(self.clips) + len(self.filtered_clips)) / self.num_total_clips
+
+        @property
+        def weight(self) -> float:
+            """data_model.py:509-523: duration normalised to 5 minutes x the fraction of its clips this chunk carries
+            (what sharding.shard_by_weight balances across ranks)."""
+            if self.metadata.size is None:
+                return 0
+            assert self.metadata.duration is not None
+            return self.metadata.duration / 300 * self.fraction
+
+        def nvdec_support(self) -> bool:
+            """data_model.py:554-577: h264 with an 8-bit 4:2:0 / nv16 pixel format, hevc 4:2:0 / 4:4:4; everything else goes
+            to the CPU decoder in the reference (here: is refused by cb_decoder_decode with CB_ERR_UNSUPPORTED)."""
+            codec, pix = self.metadata.video_codec, self.metadata.pixel_format
+            if codec is None or pix is None:
+                return False
+            if codec == "h264" and ("nv16" in pix or "420p" in pix):
+                return True
+            if codec == "hevc" and ("420p" in pix or "444p" in pix):
+                return True
+            return False
+
+        def is_10_bit_color(self) -> bool | None:  # data_model.py:579-583
+            pix = self.metadata.pixel_format
+            if pix is None:
+                return None
+            return "10le" in pix or "10be" in pix
+
         def populate_metadata(self) -> None:
             """data_model.py:455-494, with the moov index instead of an ffprobe subprocess."""
             from .runtime import mp4_index
@@ -170,6 +203,17 @@ except Exception:  # noqa: BLE001
         @property
         def video(self) -> Video:
             return self.videos[0]
+
+        @property
+        def weight(self) -> float:  # data_model.py:779-790: multi-camera tasks sum their videos
+            return sum(v.weight for v in self.videos)
+
+        @property
+        def fraction(self) -> float:  # data_model.py:744-758
+            total = sum(v.num_total_clips for v in self.videos)
+            if total == 0:
+                return 1.0
+            return sum(len(v.clips) + len(v.filtered_clips) for v in self.videos) / total
 
         def get_major_size(self) -> int:
             total = 0

@@ -106,3 +106,30 @@ def test_stage_default_parameters_and_task_mutations():
     b.clips.pop()
     with pytest.raises(ValueError, match="different numbers"):
         S.assert_video_clip_alignment(t6.videos)
+
+
+def test_video_weight_fraction_and_decoder_heuristics():
+    """Video / SplitPipeTask helpers of the reference data model the path's callers read (data_model.py:496-583, 744-790;
+    reference test: tests/cosmos_curate/pipelines/video/utils/test_data_model.py:340-380)."""
+    v = _video()
+    assert v.weight == 0  # size unknown: not downloaded yet
+    v.metadata.size = 1 << 20
+    assert v.fraction == 1.0 and v.weight == pytest.approx(30.0 / 300)
+    v.num_total_clips = 4
+    v.clips = [Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0.0, 1.0))]
+    assert v.fraction == 0.25 and v.weight == pytest.approx(0.1 * 0.25)
+    w = _video("w.mp4", n_frames=1800)
+    w.metadata.size = 5
+    task = SplitPipeTask(session_id="s", videos=[v, w])
+    assert task.weight == pytest.approx(v.weight + w.weight)  # multi-camera: the sum over its videos
+    assert task.fraction == pytest.approx(1 / 4)
+    for codec, pix, want in (("h264", "yuv420p", True), ("h264", "yuv420p10le", True), ("h264", "yuv444p", False), ("hevc", "yuv420p10le", True),
+                             ("hevc", "yuv444p", True), ("hevc", "yuv422p", False), ("av1", "yuv420p", False), ("h264", None, False), (None, "yuv420p", False)):
+        v.metadata.video_codec, v.metadata.pixel_format = codec, pix
+        assert v.nvdec_support() is want, (codec, pix)
+    v.metadata.pixel_format = "yuv420p10le"
+    assert v.is_10_bit_color() is True
+    v.metadata.pixel_format = "yuv420p"
+    assert v.is_10_bit_color() is False
+    v.metadata.pixel_format = None
+    assert v.is_10_bit_color() is None

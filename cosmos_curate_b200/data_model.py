@@ -91,6 +91,10 @@ except Exception:  # noqa: BLE001
         openai_embedding: np.ndarray | None = None
         errors: dict[str, str] = attrs.Factory(dict)
 
+        @property
+        def duration(self) -> float:  # data_model.py:310-318
+            return self.span[1] - self.span[0]
+
     @attrs.define
     class VideoMetadata:  # data_model.py:392-410 (not decoder_utils.VideoMetadata: different field names)
         size: int | None = None
@@ -183,6 +187,10 @@ except Exception:  # noqa: BLE001
         rss_delta_mb: float = 0.0
         wall_start: float = 0.0
         wall_end: float = 0.0
+
+        def reset(self) -> None:  # performance_utils.py:126-135
+            self.process_time = self.actor_idle_time = self.input_data_size_mb = 0.0
+            self.rss_before_mb = self.rss_after_mb = self.rss_delta_mb = self.wall_start = self.wall_end = 0.0
 
     @attrs.define
     class SplitPipeTask(PipelineTask):

@@ -12,16 +12,20 @@ executed from their own source).
     make_clip_uuids               uuid5(NAMESPACE_URL, f"{session_id}_{start}_{end}") (:555-565)
     populate_clips_fixed_stride   one shared span list for all cameras of a session (:568-660)
     assert_video_clip_alignment   multi-camera time alignment check (pipelines/video/utils/data_model.py:634-690)
+    split_by_chunk_size           core/utils/misc/grouping.py:36-66
+    slice_video_clips, chunk_tasks   one task per ~num_clips_per_chunk * 8 s of clips, all cameras cut at the same clip indices
+                                  (clip_extraction_stages.py:46-163; what ClipTranscodingStage returns, :301)
 """
 
 from __future__ import annotations
 
+import copy
 import uuid
 from uuid import UUID
 
 import numpy as np
 
-from .data_model import Clip, Video
+from .data_model import Clip, SplitPipeTask, Video
 
 try:
     from loguru import logger
@@ -129,3 +133,53 @@ def assert_video_clip_alignment(videos: list[Video]) -> None:
             spans = [c[bad[0]].span for c in per_video]
             msg = f"Multi-cam {name} at index {bad[0]} have misaligned spans: {spans}. Misaligned indices: {bad}"
             raise ValueError(msg)
+
+
+def split_by_chunk_size(iterable, chunk_size: int, custom_size_func=lambda x: 1, *, drop_incomplete_chunk: bool = False):  # noqa: ARG005
+    """Greedy chunks: a chunk closes as soon as its accumulated size reaches chunk_size (the closing item included)."""
+    out, cur = [], 0
+    for value in iterable:
+        out.append(value)
+        cur += custom_size_func(value)
+        if cur >= chunk_size:
+            yield out
+            out, cur = [], 0
+    if out and not drop_incomplete_chunk:
+        yield out
+
+
+def slice_video_clips(video: Video, start: int, end: int, chunk_index: int, num_chunks: int) -> Video:
+    """A new Video holding clips[start:end]; payloads, metadata, timestamps and clip_stats are shared, errors are copied."""
+    if end < start:
+        msg = f"End index {end} is less than start index {start}"
+        raise ValueError(msg)
+    if start < 0 or end > len(video.clips):
+        msg = f"Start index {start} or end index {end} is out of range [0, {len(video.clips)})"
+        raise ValueError(msg)
+    return Video(input_video=video.input_video, relative_path=video.relative_path, encoded_data=video.encoded_data, metadata=video.metadata,
+                 frame_array=video.frame_array, timestamps=video.timestamps, clips=video.clips[start:end], num_total_clips=len(video.clips),
+                 num_clip_chunks=num_chunks, clip_chunk_index=chunk_index, clip_stats=video.clip_stats, errors=copy.deepcopy(video.errors))  # fmt: skip
+
+
+def chunk_tasks(tasks: list[SplitPipeTask], num_clips_per_chunk: int, *, verbose: bool = False) -> list[SplitPipeTask]:
+    """Each task becomes one subtask per chunk of the PRIMARY video's clips; a chunk closes once its clips' whole-second durations
+    reach num_clips_per_chunk * 8; every camera is cut at the same clip indices.  stage_perf is carried by the first subtask and
+    reset on the others."""
+    out: list[SplitPipeTask] = []
+    for task in tasks:
+        chunks = list(split_by_chunk_size(task.videos[0].clips, num_clips_per_chunk * 8, lambda c: int(c.span[1] - c.span[0])))
+        start = 0
+        for idx, chunk in enumerate(chunks):
+            end = start + len(chunk)
+            sub = SplitPipeTask(session_id=task.session_id, videos=[slice_video_clips(v, start, end, idx, len(chunks)) for v in task.videos],
+                                stage_perf=copy.deepcopy(task.stage_perf))  # fmt: skip
+            start = end
+            if idx > 0:
+                for stats in sub.stage_perf.values():
+                    stats.reset()
+            if verbose:
+                logger.info(f"Spawning subtask {idx} with {len(sub.video.clips)} clips and weight={sub.weight:.2f}")
+            out.append(sub)
+    for task in out:
+        assert_video_clip_alignment(task.videos)
+    return out

@@ -23,6 +23,7 @@ from .._lib import CurateB200Error, check
 from ..data_model import StageTimer
 from ..interfaces import CuratorStage, CuratorStageResource
 from ..runtime import _as_u8, mp4_index
+from ..spans import chunk_tasks
 
 try:
     from loguru import logger
@@ -67,9 +68,13 @@ def span_sample_range(idx: dict, span: tuple[float, float]) -> tuple[int, int, f
 
 
 class ClipStreamCopyStage(CuratorStage):
-    def __init__(self, *, snap_spans: bool = True, num_cpus_per_worker: float = 1.0, verbose: bool = False, log_stats: bool = False) -> None:
+    def __init__(self, *, snap_spans: bool = True, num_cpus_per_worker: float = 1.0, num_clips_per_chunk: int | None = None, verbose: bool = False,
+                 log_stats: bool = False) -> None:  # fmt: skip
         self._timer = StageTimer(self)
         self._snap, self._cpus, self._verbose, self._log_stats = snap_spans, num_cpus_per_worker, verbose, log_stats
+        # ClipTranscodingStage re-chunks its output into tasks of ~num_clips_per_chunk * 8 s of clips (default 32, :184, :301); None keeps
+        # the incoming tasks (one chunk each)
+        self._num_clips_per_chunk = num_clips_per_chunk
 
     @property
     def resources(self) -> CuratorStageResource:
@@ -110,4 +115,6 @@ class ClipStreamCopyStage(CuratorStage):
             if self._log_stats:
                 stage_name, stats = self._timer.log_stats()
                 task.stage_perf[stage_name] = stats
+        if self._num_clips_per_chunk is not None:
+            return chunk_tasks(tasks, self._num_clips_per_chunk, verbose=self._verbose)
         return tasks

@@ -377,6 +377,15 @@ def gen_fixed_stride() -> None:
         out["populate"].append({"name": name, "videos": [[v[0], v[1], float.hex(float(v[2])), float.hex(float(v[3]))] for v in vids],
                                 "args": [float.hex(clip_len), float.hex(stride), float.hex(min_len), limit],
                                 "clips": [[[str(c.uuid), c.source_video, float.hex(c.span[0]), float.hex(c.span[1])] for c in v.clips] for v in vs]})
+    # chunk sizes of chunk_tasks (clip_extraction_stages.py:131-139): the reference's split_by_chunk_size over clip spans with its size function
+    grouping = ref_import.grouping_module()
+    out["chunks"] = []
+    rng = np.random.default_rng(7)
+    for n_clips, per_chunk in ((100, 32), (7, 1), (33, 4), (0, 32), (50, 2)):
+        starts = np.cumsum(rng.uniform(0.3, 14.0, size=n_clips))
+        spans = [(float(a), float(a + d)) for a, d in zip(starts, rng.uniform(0.2, 12.0, size=n_clips))]
+        sizes = [len(c) for c in grouping.split_by_chunk_size(spans, per_chunk * 8, lambda x: int(x[1] - x[0]))]
+        out["chunks"].append({"spans": [[float.hex(a), float.hex(b)] for a, b in spans], "num_clips_per_chunk": per_chunk, "chunk_sizes": sizes})
     (OUT / "fixed_stride_ref.json").write_text(json.dumps(out, indent=1))
     print("fixed_stride_ref.json", len(out["spans"]), "span cases,", len(out["populate"]), "populate cases")
 

@@ -178,3 +178,11 @@ def fixed_stride_functions():
     src = "from __future__ import annotations\n" + "\n\n".join(ast.unparse(n) for n in body)
     exec(compile(src, str(path), "exec"), ns)  # noqa: S102 - reference code, build container only
     return {k: ns[k] for k in wanted}
+
+
+def grouping_module():
+    """cosmos_curate/core/utils/misc/grouping.py (pure Python): split_by_chunk_size is what chunk_tasks sizes its subtasks with."""
+    _install_stubs()
+    import importlib
+
+    return importlib.import_module("cosmos_curate.core.utils.misc.grouping")

@@ -133,3 +133,42 @@ def test_video_weight_fraction_and_decoder_heuristics():
     assert v.is_10_bit_color() is False
     v.metadata.pixel_format = None
     assert v.is_10_bit_color() is None
+
+
+def test_chunk_tasks_matches_the_reference_chunking():
+    """chunk_tasks / slice_video_clips (clip_extraction_stages.py:46-163): chunk sizes equal to the reference's
+    split_by_chunk_size on the same spans; every camera cut at the same indices; chunk bookkeeping fields; stats reset."""
+    from cosmos_curate_b200.data_model import StagePerfStats
+
+    g = json.loads((GOLDEN / "fixed_stride_ref.json").read_text())
+    assert list(S.split_by_chunk_size(range(10), 4)) == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
+    assert list(S.split_by_chunk_size(range(10), 4, drop_incomplete_chunk=True)) == [[0, 1, 2, 3], [4, 5, 6, 7]]
+    for case in g["chunks"]:
+        spans = [(float.fromhex(a), float.fromhex(b)) for a, b in case["spans"]]
+        cams = []
+        for name in ("cam0.mp4", "cam1.mp4"):
+            v = _video(name)
+            v.metadata.size = 1
+            v.clips = [Clip(uuid=uuid.uuid5(uuid.NAMESPACE_URL, f"{i}"), source_video=name, span=sp) for i, sp in enumerate(spans)]
+            v.errors["note"] = "kept"
+            cams.append(v)
+        task = SplitPipeTask(session_id="rig", videos=cams, stage_perf={"Up": StagePerfStats(process_time=2.0)})
+        subs = S.chunk_tasks([task], case["num_clips_per_chunk"])
+        assert [len(t.video.clips) for t in subs] == case["chunk_sizes"]
+        pos = 0
+        for i, t in enumerate(subs):
+            assert t.session_id == "rig" and len(t.videos) == 2
+            for v, src in zip(t.videos, cams):
+                assert v.clips == src.clips[pos : pos + len(v.clips)]
+                assert (v.num_total_clips, v.num_clip_chunks, v.clip_chunk_index) == (len(spans), len(subs), i)
+                assert v.metadata is src.metadata and v.clip_stats is src.clip_stats and v.errors == {"note": "kept"} and v.errors is not src.errors
+            assert t.stage_perf["Up"].process_time == (2.0 if i == 0 else 0.0)  # carried by the first subtask only
+            assert t.fraction == pytest.approx(len(t.video.clips) / len(spans))
+            pos += len(t.video.clips)
+        assert pos == len(spans)
+    v = _video()
+    v.clips = [Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0.0, 1.0))]
+    with pytest.raises(ValueError, match="less than start"):
+        S.slice_video_clips(v, 1, 0, 0, 1)
+    with pytest.raises(ValueError, match="out of range"):
+        S.slice_video_clips(v, 0, 2, 0, 1)

@@ -96,3 +96,21 @@ def test_stage_contract_matches_clip_transcoding_stage(tmp_path):
     empty = SplitPipeTask(session_id="e", video=Video(input_video="e.mp4", clips=[clips[0]]))
     stage.process_data([empty])
     assert "ClipStreamCopyStage" in empty.video.errors  # "Please load video!" recorded, not raised (:283-287)
+
+
+def test_stream_copy_stage_rechunks_like_the_transcoding_stage():
+    """num_clips_per_chunk: ClipStreamCopyStage returns what ClipTranscodingStage returns (clip_extraction_stages.py:301) - one
+    task per ~num_clips_per_chunk * 8 s of clips, bookkeeping fields set for the downstream weight / fraction arithmetic."""
+    data = synth_h264.make_clip(320, 192, 30, 4.0, seed=2, gop=30)
+    clips = [Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(float(s), float(s + 1))) for s in range(4)]
+    video = Video(input_video="v.mp4", encoded_data=data, clips=clips)
+    video.metadata.duration, video.metadata.size = 4.0, len(data)
+    out = ClipStreamCopyStage(num_clips_per_chunk=1).process_data([SplitPipeTask(session_id="s", video=video)])  # 8 s of clips per chunk -> one chunk
+    assert len(out) == 1 and len(out[0].video.clips) == 4 and all(c.encoded_data for c in out[0].video.clips)
+    video2 = Video(input_video="v.mp4", encoded_data=data, clips=[Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0.0, 4.0)), Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(0.0, 4.0)),
+                                                                   Clip(uuid=uuid.uuid4(), source_video="v.mp4", span=(1.0, 4.0))])
+    video2.metadata.duration, video2.metadata.size = 4.0, len(data)
+    out = ClipStreamCopyStage(num_clips_per_chunk=1, snap_spans=False).process_data([SplitPipeTask(session_id="s", video=video2)])
+    assert [len(t.video.clips) for t in out] == [2, 1]  # 4 s + 4 s reaches 8: the chunk closes
+    assert [(t.video.num_total_clips, t.video.num_clip_chunks, t.video.clip_chunk_index) for t in out] == [(3, 2, 0), (3, 2, 1)]
+    assert out[0].weight == pytest.approx(4.0 / 300 * 2 / 3) and not out[0].video.encoded_data

@@ -162,6 +162,19 @@ except Exception:  # noqa: BLE001
                 return None
             return "10le" in pix or "10be" in pix
 
+        def populate_timestamps(self) -> None:
+            """data_model.py:449-460: per-frame presentation timestamps (seconds, float32, sorted) - from the moov index here,
+            from a PyAV demux of every packet in the reference (decoder_utils.py:230-278)."""
+            from .runtime import mp4_index
+            from .sampling import timestamps_from_index
+
+            data = self.encoded_data.resolve()
+            if data is None:
+                error_msg = "No video data available: encoded_data is None"
+                raise ValueError(error_msg)
+            idx = mp4_index(data)
+            self.timestamps = timestamps_from_index(idx["pts"], idx["timescale"])
+
         def populate_metadata(self) -> None:
             """data_model.py:455-494, with the moov index instead of an ffprobe subprocess."""
             from .runtime import mp4_index

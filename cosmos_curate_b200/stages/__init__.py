@@ -6,6 +6,7 @@ Same-name drop-ins (constructor arguments, task mutations and error convention o
     VideoFrameExtractionStage   cosmos_curate/pipelines/video/clipping/frame_extraction_stages.py:71-204
     ImageCLIPEmbeddingStage     cosmos_curate/pipelines/image/embedding/image_embedding_stages.py:219-283
     TransNetV2ClipExtractionStage  cosmos_curate/pipelines/video/clipping/transnetv2_extraction_stages.py:39-212
+    VideoDownloader             cosmos_curate/pipelines/video/read_write/download_stages.py:40-228 (local files only, host only)
     FixedStrideExtractorStage   cosmos_curate/pipelines/video/clipping/clip_extraction_stages.py:664-760 (host only)
     InternVideo2FrameCreationStage  cosmos_curate/pipelines/video/embedding/internvideo2_stages.py:43-184 (the tower's input tube)
 New fused stage (replaces ClipFrameExtractionStage -> AestheticFilterStage [-> clip embedding] in one GPU pass):
@@ -16,6 +17,7 @@ New fused stage (replaces ClipFrameExtractionStage -> AestheticFilterStage [-> c
 
 from .aesthetic_filter import AestheticFilterStage  # noqa: F401
 from .clip_stream_copy import ClipStreamCopyStage  # noqa: F401
+from .download import VideoDownloader  # noqa: F401
 from .fixed_stride import FixedStrideExtractorStage  # noqa: F401
 from .fused_clip import NvdecClipAestheticStage  # noqa: F401
 from .frame_extraction import ClipFrameExtractionStage, VideoFrameExtractionStage  # noqa: F401

@@ -172,3 +172,34 @@ def test_chunk_tasks_matches_the_reference_chunking():
         S.slice_video_clips(v, 1, 0, 0, 1)
     with pytest.raises(ValueError, match="out of range"):
         S.slice_video_clips(v, 0, 2, 0, 1)
+
+
+def test_host_side_chain_download_split_cut_on_the_reference_fixture(tmp_path):
+    """VideoDownloader -> FixedStrideExtractorStage -> ClipStreamCopyStage(num_clips_per_chunk) on the reference's own media
+    fixture, all host code: what reaches the GPU stages is a list of SplitPipeTasks whose clips carry standalone MP4 bytes."""
+    import shutil
+
+    from cosmos_curate_b200.interfaces import run_pipeline
+    from cosmos_curate_b200.runtime import mp4_index
+    from cosmos_curate_b200.stages import ClipStreamCopyStage, VideoDownloader
+
+    src = tmp_path / "sintel.mp4"
+    shutil.copy(GOLDEN / "sintel_clip_10s.mp4", src)
+    task = SplitPipeTask(session_id=str(src), video=Video(input_video=src))
+    missing = SplitPipeTask(session_id="gone", video=Video(input_video=tmp_path / "gone.mp4"))
+    remote = SplitPipeTask(session_id="s3", video=Video(input_video="s3://bucket/v.mp4"))
+    out = run_pipeline([task, missing, remote], [VideoDownloader(log_stats=True), FixedStrideExtractorStage(clip_len_s=4, clip_stride_s=4, min_clip_length_s=2)])
+    assert out is not None and len(out) == 3
+    v = task.video
+    assert v.metadata.num_frames == 240 and v.metadata.framerate == 24.0 and v.metadata.video_codec == "h264" and v.has_metadata()
+    assert v.timestamps.dtype == np.float32 and len(v.timestamps) == 240 and v.timestamps[1] == np.float32(1 / 24)
+    assert v.nvdec_support() and v.weight == pytest.approx(10.0 / 300) and "VideoDownloader" in task.stage_perf
+    assert [c.span for c in v.clips] == [(0.0, 4.0), (4.0, 8.0), (8.0, 10.0)]
+    assert "download" in missing.video.errors and "FixedStrideExtractorStage" in missing.errors and not missing.video.clips
+    assert "no storage client" in remote.video.errors["download"]
+    cut = ClipStreamCopyStage(num_clips_per_chunk=1).process_data([task])
+    assert [len(t.video.clips) for t in cut] == [2, 1]  # 4 s + 4 s of clips close the first chunk
+    first = cut[0].video.clips[0]
+    idx = mp4_index(first.encoded_data.resolve())
+    assert idx["width"] == 854 and idx["n_samples"] >= 96 and first.span[0] == 0.0  # the fixture is one GOP: every cut starts at its only sync sample
+    assert cut[1].video.clip_chunk_index == 1 and cut[1].fraction == pytest.approx(1 / 3)

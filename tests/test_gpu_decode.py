@@ -226,7 +226,7 @@ def test_decoder_pool_keeps_one_session_per_stream_shape(ctx):
     assert len(set(seen)) == 2 and seen[0] == seen[2] == seen[4] and seen[1] == seen[3] == seen[5]
     for s in shapes:  # five shapes through a table of MAX_SHAPES = 4
         assert dp.submit(job, s, shape=s).result() == 2
-        np.testing.assert_array_equal(pools[s].buf.cpu().numpy(), ref[s])
+        np.testing.assert_array_equal(pools[s].buf.cpu().numpy()[:, :, : s[0]], ref[s][:, :, : s[0]])  # the pitch padding is not written
     assert len(dp._decoders) == DecoderPool.MAX_SHAPES
     assert dp.submit(job, shapes[0], shape=None).result() == 2  # shape-less callers keep working (one shared session)
     dp.close()

@@ -494,3 +494,42 @@ def test_internvideo2_frame_creation_stage_matches_the_reference_formulation(ctx
     np.testing.assert_array_equal(d1.intern_video_2_frames.resolve(), c1.intern_video_2_frames.resolve())
     assert d2.errors["frame_extraction"] == "video_decode_failed" and not d2.intern_video_2_frames
     assert d3.intern_video_2_frames.resolve().shape == (0,) and not d3.errors  # the reference's empty array for too short clips
+
+
+def test_local_split_pipeline_chain_from_file_to_dedup(ctx, tmp_path):
+    """The whole slice a user of the reference's split pipeline would run here, stage classes only: VideoDownloader ->
+    FixedStrideExtractorStage -> ClipStreamCopyStage (re-chunking like ClipTranscodingStage) -> NvdecClipAestheticStage ->
+    the ClipWriterStage file layout -> the dedup reader -> semdedup_cluster.  Checks the plumbing (tasks multiply at the chunking
+    stage, every clip is scored and embedded, files round-trip); the numbers themselves are pinned by the tests above."""
+    import shutil
+
+    from cosmos_curate_b200 import dedup as D
+    from cosmos_curate_b200 import embedding_io as E
+    from cosmos_curate_b200.data_model import SplitPipeTask, Video
+    from cosmos_curate_b200.interfaces import run_pipeline
+    from cosmos_curate_b200.stages import ClipStreamCopyStage, FixedStrideExtractorStage, NvdecClipAestheticStage, VideoDownloader
+
+    src = tmp_path / "sintel.mp4"
+    shutil.copy(GOLDEN / "sintel_clip_10s.mp4", src)
+    model, _, _, _ = _model()
+    stages = [VideoDownloader(log_stats=True), FixedStrideExtractorStage(clip_len_s=4, clip_stride_s=3, min_clip_length_s=2, log_stats=True),
+              ClipStreamCopyStage(num_clips_per_chunk=1, snap_spans=False, log_stats=True),
+              NvdecClipAestheticStage(score_threshold=-9.0, reduction="mean", write_embedding=True, max_batch=32, num_decoders=2, log_stats=True, model=model)]
+    out = run_pipeline([SplitPipeTask(session_id=str(src), video=Video(input_video=src))], stages)
+    assert out is not None and len(out) == 2  # spans (0,4) (3,7) (6,10) (9,10 dropped: < 2 s): 4 + 4 s close a chunk, the third clip forms the next
+    clips = [c for t in out for c in t.video.clips]
+    assert [c.span for c in clips] == [(0.0, 4.0), (3.0, 7.0), (6.0, 10.0)]
+    assert all(c.aesthetic_score is not None and c.aesthetic_score > -1.0 and c.openai_embedding.shape == (model.tower.out_dim,) for c in clips)
+    assert all(abs(float(np.linalg.norm(c.openai_embedding)) - 1.0) < 1e-5 for c in clips)
+    assert {"VideoDownloader", "FixedStrideExtractorStage", "ClipStreamCopyStage", "NvdecClipAestheticStage"} <= set(out[0].stage_perf)
+    assert [t.video.clip_chunk_index for t in out] == [0, 1] and out[0].video.num_total_clips == 3
+    for t in out:
+        E.write_task_outputs(t, str(tmp_path / "out"), "openai")
+    files = sorted((tmp_path / "out" / "openai_embd_parquet").glob("*.parquet"))
+    assert len(files) == 2  # one per (video, chunk)
+    ids, emb = E.read_embedding_parquets([str(f) for f in files])
+    assert sorted(ids.tolist()) == sorted(str(c.uuid) for c in clips) and emb.shape == (3, model.tower.out_dim)
+    by_id = {str(c.uuid): c.openai_embedding for c in clips}
+    np.testing.assert_array_equal(emb, np.stack([by_id[i] for i in ids.tolist()]))
+    r = D.semdedup_cluster(ids, emb, np.zeros(3, np.float32), eps=0.01)
+    assert r["total"] == 3 and len(r["id"]) == 3

@@ -68,7 +68,6 @@ class InternVideo2FrameFormulator(ModelInterface):
 
     def _formulate_host(self, picked: list[np.ndarray]) -> np.ndarray:
         dev = self._device()
-        out = []
         by_shape: dict[tuple, list[int]] = {}
         for i, f in enumerate(picked):
             if f.ndim != 3 or f.shape[-1] != 3 or f.dtype != np.uint8:

@@ -186,3 +186,24 @@ def grouping_module():
     import importlib
 
     return importlib.import_module("cosmos_curate.core.utils.misc.grouping")
+
+
+def stage_compare_functions():
+    """`_compare_values` and its helpers from the reference's stage-output comparator (core/utils/misc/stage_compare.py:58-66, 173-313),
+    executed from source (the module imports ray / xenna at the top; these functions need numpy and attrs only)."""
+    import ast
+    from collections.abc import Mapping, Sequence
+    from typing import Any, cast
+
+    import attrs
+    import numpy as np
+    import numpy.typing as npt
+
+    path = REFERENCE_ROOT / "cosmos_curate" / "core" / "utils" / "misc" / "stage_compare.py"
+    tree = ast.parse(path.read_text())
+    wanted = {"FieldDiff", "_compare_arrays", "_compare_attrs", "_compare_mapping", "_compare_sequence", "_compare_values"}
+    body = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in wanted]
+    assert {n.name for n in body} == wanted
+    ns = {"np": np, "npt": npt, "attrs": attrs, "Mapping": Mapping, "Sequence": Sequence, "Any": Any, "cast": cast}
+    exec(compile(ast.Module(body=body, type_ignores=[]), str(path), "exec"), ns)  # noqa: S102 - reference code, build container only
+    return {k: ns[k] for k in wanted}

@@ -257,3 +257,27 @@ def test_all_gather_embeddings_gloo_world2():
     ragged = [g for g in got if g[2] is None]
     for _, e, _ in ragged:
         assert e.shape == (2, 3) and (e == 1).all()
+
+
+def test_stage_outputs_pass_the_reference_style_task_compare():
+    """Stage replay the way the reference judges a changed stage (stage_compare.run_stage_compare): the same input tasks through two
+    configurations of AestheticFilterStage - one model call per task vs clips of all tasks batched together - must give tasks that
+    compare equal on session_id / videos / errors at atol 0; a different threshold must not."""
+    import copy
+
+    from cosmos_curate_b200.compare import compare_tasks
+
+    def tasks():
+        rng = np.random.default_rng(3)
+        return [_task([_clip(list(rng.integers(20, 255, size=n))) for n in (3, 5, 2)]) for _ in range(3)]
+
+    golden, cand, other = tasks(), None, None
+    cand, other = copy.deepcopy(golden), copy.deepcopy(golden)
+    for t in golden:
+        run_pipeline([t], [AestheticFilterStage(score_threshold=3.0, reduction="min", model=_FakeScorer())])
+    st = AestheticFilterStage(score_threshold=3.0, reduction="min", model=_FakeScorer(), stage_batch_size=3, max_batch=4, log_stats=True)
+    run_pipeline(cand, [st])
+    assert compare_tasks(golden, cand, atol=0.0) == []
+    run_pipeline(other, [AestheticFilterStage(score_threshold=6.0, reduction="min", model=_FakeScorer())])
+    fields = {d.field.split(".")[-1].split("[")[0] for _, d in compare_tasks(golden, other, atol=0.0)}
+    assert fields and fields <= {"clips", "filtered_clips", "num_filtered_by_aesthetic", "num_passed"}

@@ -322,6 +322,14 @@ std::string mp4_parse(const uint8_t* data, size_t size, Mp4Track* out) {
     }
     return false;  // first video track only (stream_idx 0 in the reference)
   });
+  if (done && out->size.empty()) {
+    // fragmented files (ffmpeg -movflags frag_keyframe, DASH / CMAF segments) keep their samples in moof / trun boxes behind an
+    // mvex declaration; the reference's clips are plain ffmpeg MP4s (clip_extraction_stages.py:318-442) - say what this is instead
+    // of reporting a zero-frame video
+    Box mvex;
+    if (find_box(r, moov.body, moov.end, fourcc("mvex"), &mvex)) return "fragmented MP4 (mvex / moof sample tables) is not supported";
+    return "video track has no samples";
+  }
   return done ? "" : err;
 }
 

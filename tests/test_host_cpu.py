@@ -225,3 +225,35 @@ def test_internvideo2_frame_selection_and_resampling_rule():
     assert stage.process_data([task]) == [task]  # neither clip reaches the GPU
     assert clips[0].errors == {"encoded_data": "empty"}
     assert clips[1].errors == {"frames-FrameExtractionPolicy.sequence-2000": "missing"}
+
+
+def test_mp4_index_names_fragmented_files():
+    """A fragmented MP4 (ffmpeg -movflags frag_keyframe / CMAF: empty moov sample tables + mvex, samples in moof boxes) is refused
+    with a message that says so; a plain track without samples likewise - not reported as a zero-frame video."""
+    import struct
+
+    from cosmos_curate_b200._lib import CurateB200Error
+    from cosmos_curate_b200.runtime import mp4_index
+
+    def box(kind: bytes, body: bytes) -> bytes:
+        return struct.pack(">I", 8 + len(body)) + kind + body
+
+    def full(kind: bytes, body: bytes, version=0, flags=0) -> bytes:
+        return box(kind, struct.pack(">I", (version << 24) | flags) + body)
+
+    avcc = box(b"avcC", bytes([1, 66, 0, 30, 0xFF, 0xE1]) + struct.pack(">H", 4) + bytes([0x67, 66, 0, 30]) + bytes([1]) + struct.pack(">H", 2) + bytes([0x68, 0xCE]))
+    entry = struct.pack(">I", 0)[:0] + bytes(6) + struct.pack(">H", 1) + bytes(16) + struct.pack(">HH", 320, 192) + struct.pack(">II", 0x480000, 0x480000) + bytes(4) + struct.pack(">H", 1) + bytes(32) + struct.pack(">Hh", 24, -1)
+    avc1 = box(b"avc1", entry + avcc)
+    stbl = box(b"stbl", full(b"stsd", struct.pack(">I", 1) + avc1) + full(b"stsz", struct.pack(">II", 0, 0)) + full(b"stco", struct.pack(">I", 0)) +
+               full(b"stsc", struct.pack(">I", 0)) + full(b"stts", struct.pack(">I", 0)))
+    mdia = box(b"mdia", full(b"mdhd", struct.pack(">IIIIHH", 0, 0, 30000, 0, 0x55C4, 0)) + full(b"hdlr", struct.pack(">I", 0) + b"vide" + bytes(12) + b"v\0") +
+               box(b"minf", stbl))
+    trak = box(b"trak", mdia)
+    mvhd = full(b"mvhd", struct.pack(">IIII", 0, 0, 1000, 0) + bytes(80))
+    ftyp = box(b"ftyp", b"isom" + struct.pack(">I", 512) + b"isomiso5")
+    for with_mvex, text in ((True, "fragmented MP4"), (False, "no samples")):
+        moov = box(b"moov", mvhd + trak + (box(b"mvex", full(b"trex", bytes(20))) if with_mvex else b""))
+        data = np.frombuffer(ftyp + moov + box(b"moof", bytes(16)) + box(b"mdat", bytes(64)), dtype=np.uint8)
+        with pytest.raises(CurateB200Error, match=text) as e:
+            mp4_index(data)
+        assert e.value.code == -5  # CB_ERR_DEMUX: the stages record video_decode_failed

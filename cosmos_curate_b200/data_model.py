@@ -75,6 +75,18 @@ except Exception:  # noqa: BLE001
         num_filtered_by_artificial_text: int = 0
         num_passed: int = 0
         num_transcoded: int = 0
+        num_with_embeddings: int = 0
+        num_with_caption: int = 0
+        num_with_webp: int = 0
+        total_clip_duration: float = 0.0
+        max_clip_duration: float = 0.0
+        total_prompt_tokens: int = 0
+        total_output_tokens: int = 0
+
+        def combine(self, other) -> None:  # data_model.py:369-390
+            for f in attrs.fields(type(self)):
+                a, b = getattr(self, f.name), getattr(other, f.name)
+                setattr(self, f.name, max(a, b) if f.name == "max_clip_duration" else a + b)
 
     @attrs.define
     class Clip:

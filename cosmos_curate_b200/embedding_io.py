@@ -114,6 +114,19 @@ def write_grouped_embeddings_parquet(video, output_path: str, embedding_algorith
     return _write(dest, buf.getvalue())
 
 
+def extract_clip_metadata(clip) -> dict[str, Any] | None:
+    """width / height / framerate / num_frames / video_codec / num_bytes of the clip's encoded_data, None without bytes."""
+    data = clip.encoded_data.resolve() if clip.encoded_data else None
+    if data is None:
+        return None
+    from .runtime import mp4_index
+    from .sampling import video_metadata_from_index
+
+    m = video_metadata_from_index(mp4_index(data))
+    return {"width": m.width, "height": m.height, "framerate": m.fps, "num_frames": m.num_frames, "video_codec": m.video_codec,
+            "num_bytes": int(np.asarray(data).nbytes)}  # fmt: skip
+
+
 def make_clip_metadata(clip, video, output_path: str, embedding_algorithm: str = "openai", *, filtered: bool = False, embedding_model_version: str = "") -> dict[str, Any]:
     """The fields of _make_clip_metadata (:796-886) this path owns; windows / captions are other stages' business."""
     m = video.metadata
@@ -122,6 +135,13 @@ def make_clip_metadata(clip, video, output_path: str, embedding_algorithm: str =
         "width_source": m.width, "height_source": m.height, "framerate_source": m.framerate,
         "clip_location": str(get_clip_uri(clip.uuid, get_output_path_clips(output_path, filtered=filtered), "mp4")),
     }  # fmt: skip
+    clip_metadata = None
+    try:  # Clip.extract_metadata (data_model.py:283-308): the clip file's own facts - from its MP4 index here, ffprobe there
+        clip_metadata = extract_clip_metadata(clip)
+    except Exception as e:  # noqa: BLE001
+        clip.errors["extract_metadata"] = str(e)
+    if clip_metadata:
+        data.update(clip_metadata)
     if clip.aesthetic_score is not None:
         data["aesthetic_score"] = clip.aesthetic_score
     if len(clip.errors) > 0:
@@ -139,7 +159,7 @@ def make_clip_metadata(clip, video, output_path: str, embedding_algorithm: str =
 
 def write_clip_metadata(clip, video, output_path: str, embedding_algorithm: str = "openai", *, filtered: bool = False) -> pathlib.Path:
     data = make_clip_metadata(clip, video, output_path, embedding_algorithm, filtered=filtered)
-    data = {k: v for k, v in data.items() if k != "embedding"}  # the per-clip json omits the vector (:896-905); the pickle holds it
+    data = {k: v for k, v in data.items() if k not in ("embedding", "embedding_model_name", "embedding_model_version")}  # :896-905: the pickle holds the vector
     return _write(get_clip_uri(clip.uuid, get_output_path_metas(output_path, "v0"), "json"), json.dumps(data, indent=4).encode())
 
 

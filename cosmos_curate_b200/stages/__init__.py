@@ -8,6 +8,7 @@ Same-name drop-ins (constructor arguments, task mutations and error convention o
     TransNetV2ClipExtractionStage  cosmos_curate/pipelines/video/clipping/transnetv2_extraction_stages.py:39-212
     VideoDownloader             cosmos_curate/pipelines/video/read_write/download_stages.py:40-228 (local files only, host only)
     FixedStrideExtractorStage   cosmos_curate/pipelines/video/clipping/clip_extraction_stages.py:664-760 (host only)
+    ClipWriterStage             cosmos_curate/pipelines/video/read_write/metadata_writer_stage.py:66-1020 (local output directory, host only)
     InternVideo2FrameCreationStage  cosmos_curate/pipelines/video/embedding/internvideo2_stages.py:43-184 (the tower's input tube)
 New fused stage (replaces ClipFrameExtractionStage -> AestheticFilterStage [-> clip embedding] in one GPU pass):
     NvdecClipAestheticStage
@@ -16,6 +17,7 @@ New fused stage (replaces ClipFrameExtractionStage -> AestheticFilterStage [-> c
 """
 
 from .aesthetic_filter import AestheticFilterStage  # noqa: F401
+from .clip_writer import ClipWriterStage  # noqa: F401
 from .clip_stream_copy import ClipStreamCopyStage  # noqa: F401
 from .download import VideoDownloader  # noqa: F401
 from .fixed_stride import FixedStrideExtractorStage  # noqa: F401

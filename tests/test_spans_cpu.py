@@ -203,3 +203,11 @@ def test_host_side_chain_download_split_cut_on_the_reference_fixture(tmp_path):
     idx = mp4_index(first.encoded_data.resolve())
     assert idx["width"] == 854 and idx["n_samples"] >= 96 and first.span[0] == 0.0  # the fixture is one GOP: every cut starts at its only sync sample
     assert cut[1].video.clip_chunk_index == 1 and cut[1].fraction == pytest.approx(1 / 3)
+    # ... and out again: the writer stage's layout under a local directory (no GPU stage in between: no scores, no embeddings)
+    from cosmos_curate_b200.stages import ClipWriterStage
+
+    ClipWriterStage(str(tmp_path / "out"), str(tmp_path), generate_embeddings=False).process_data(cut)
+    assert sorted(p.name for p in (tmp_path / "out" / "processed_clip_chunks").iterdir()) == ["sintel.mp4_0.json", "sintel.mp4_1.json"]
+    assert (tmp_path / "out" / "processed_videos" / "sintel.mp4.json").exists() and len(list((tmp_path / "out" / "clips").glob("*.mp4"))) == 3
+    back = (tmp_path / "out" / "clips" / f"{first.uuid}.mp4").read_bytes()
+    assert mp4_index(np.frombuffer(back, dtype=np.uint8))["n_samples"] == idx["n_samples"]

@@ -448,6 +448,31 @@ def device_numa_cpus(ctx: Context) -> tuple[int | None, list[int]]:
         return None, []
 
 
+class SessionTable:
+    """One NVDEC session per stream shape for a single-threaded caller (the same rule DecoderPool applies per worker thread:
+    a session that is fed another resolution is destroyed and re-created by the driver, ~0.4 s each time)."""
+
+    MAX_SHAPES = 4
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self._decs: dict = {}
+
+    def get(self, shape) -> Decoder:
+        d = self._decs.pop(shape, None)
+        if d is None or d.h is None:
+            while len(self._decs) >= self.MAX_SHAPES:
+                self._decs.pop(next(iter(self._decs))).close()  # least recently used
+            d = Decoder(self.ctx)
+        self._decs[shape] = d
+        return d
+
+    def close(self) -> None:
+        for d in self._decs.values():
+            d.close()
+        self._decs.clear()
+
+
 class DecoderPool:
     """Persistent NVDEC sessions behind a thread pool: one `Decoder` per worker thread, created on first use and kept across
     calls (session creation costs ~10 ms and a context-lock round trip), worker threads pinned to the host CPUs of the GPU's

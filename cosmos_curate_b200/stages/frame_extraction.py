@@ -18,7 +18,7 @@ from .. import _lib
 from .._lib import CurateB200Error
 from ..data_model import LazyData, StageTimer
 from ..interfaces import CuratorStage, CuratorStageResource
-from ..runtime import Decoder, alloc_nv12_pool, decode_thumbnails, get_context, mp4_index
+from ..runtime import SessionTable, alloc_nv12_pool, decode_thumbnails, get_context, mp4_index
 from ..sampling import FrameExtractionPolicy
 
 try:
@@ -78,12 +78,12 @@ class ClipFrameExtractionStage(CuratorStage):
 
     def stage_setup(self) -> None:
         self._ctx = get_context()
-        self._decoder = Decoder(self._ctx)
+        self._sessions = SessionTable(self._ctx)  # one NVDEC session per clip resolution (a mixed stream would re-create a single one per clip)
         self._pools: dict[tuple, object] = {}
 
     def destroy(self) -> None:
-        if getattr(self, "_decoder", None):
-            self._decoder.close()
+        if getattr(self, "_sessions", None):
+            self._sessions.close()
 
     MAX_POOLS = 4  # resolutions kept resident (LRU); a 64-slot 1080p pool is 0.2 GB and the actor may own only 0.25 GPU
 
@@ -108,7 +108,7 @@ class ClipFrameExtractionStage(CuratorStage):
         plan = sampling.plan_extraction(ts, self._extraction_policies, self._target_fps)
         all_ids = np.unique(np.concatenate(list(plan.values()))).astype(np.int32)
         pool = self._surface_pool(idx["width"], idx["height"], len(all_ids))
-        self._decoder.decode(data, all_ids, pool, np.arange(len(all_ids), dtype=np.int32))
+        self._sessions.get((idx["width"], idx["height"])).decode(data, all_ids, pool, np.arange(len(all_ids), dtype=np.int32))
         slots = np.arange(len(all_ids), dtype=np.int32)
         if self._target_res[0] > 0 and self._target_res[1] > 0:  # only 3 * th * tw bytes per frame cross PCIe (150 KB instead of 6 MB)
             th, tw = self._target_res
@@ -163,18 +163,18 @@ class VideoFrameExtractionStage(CuratorStage):
 
     def stage_setup(self) -> None:
         self._ctx = get_context()
-        self._decoder = Decoder(self._ctx)
+        self._sessions = SessionTable(self._ctx)
 
     def destroy(self) -> None:
-        if getattr(self, "_decoder", None):
-            self._decoder.close()
+        if getattr(self, "_sessions", None):
+            self._sessions.close()
 
     def _frames(self, data) -> np.ndarray:
         idx = mp4_index(data)
         h, w = self.output_hw
         if h == -1 or w == -1:  # the reference's "pick a size for me" rule (nvcodec_utils.py:129-136)
             w, h = sampling.pynvc_target_size(idx["width"], idx["height"], w, h)
-        return decode_thumbnails(self._decoder, data, w, h, idx["n_samples"]).cpu().numpy()
+        return decode_thumbnails(self._sessions.get((idx["width"], idx["height"])), data, w, h, idx["n_samples"]).cpu().numpy()
 
     def process_data(self, tasks):
         self._timer.reinit(self, sum(x.get_major_size() for x in tasks))

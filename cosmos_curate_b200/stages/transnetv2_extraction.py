@@ -105,14 +105,14 @@ class NvdecShotDetectionStage(TransNetV2ClipExtractionStage):
         super().__init__(*args, num_gpus_per_worker=num_gpus_per_worker, **kwargs)
 
     def stage_setup(self) -> None:
-        from ..runtime import Decoder, get_context
+        from ..runtime import SessionTable, get_context
 
         super().stage_setup()
-        self._decoder = Decoder(get_context())
+        self._sessions = SessionTable(get_context())  # one NVDEC session per source resolution
 
     def destroy(self) -> None:
-        if getattr(self, "_decoder", None):
-            self._decoder.close()
+        if getattr(self, "_sessions", None):
+            self._sessions.close()
 
     def process_data(self, tasks):
         from .._lib import CurateB200Error
@@ -129,7 +129,8 @@ class NvdecShotDetectionStage(TransNetV2ClipExtractionStage):
                 try:
                     if not video.has_metadata():
                         video.populate_metadata()
-                    frames = decode_thumbnails(self._decoder, data, 48, 27, mp4_index(data)["n_samples"])
+                    idx = mp4_index(data)
+                    frames = decode_thumbnails(self._sessions.get((idx["width"], idx["height"])), data, 48, 27, idx["n_samples"])
                 except (CurateB200Error, KeyError) as e:
                     logger.error(f"Video frame extraction failed on {video.input_video}: {e}")
                     video.errors["frame_extraction"] = "null"

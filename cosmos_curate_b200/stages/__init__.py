@@ -10,6 +10,7 @@ Same-name drop-ins (constructor arguments, task mutations and error convention o
     FixedStrideExtractorStage   cosmos_curate/pipelines/video/clipping/clip_extraction_stages.py:664-760 (host only)
     ClipWriterStage             cosmos_curate/pipelines/video/read_write/metadata_writer_stage.py:66-1020 (local output directory, host only)
     InternVideo2FrameCreationStage  cosmos_curate/pipelines/video/embedding/internvideo2_stages.py:43-184 (the tower's input tube)
+    ClipFrameEmbeddingStage     local producer of clip.openai_embedding (the slot of embedding/openai_embedding_stage.py:47-190)
 New fused stage (replaces ClipFrameExtractionStage -> AestheticFilterStage [-> clip embedding] in one GPU pass):
     NvdecClipAestheticStage
     NvdecShotDetectionStage      (VideoFrameExtractionStage -> TransNetV2ClipExtractionStage, frames stay in HBM)
@@ -18,6 +19,7 @@ New fused stage (replaces ClipFrameExtractionStage -> AestheticFilterStage [-> c
 
 from .aesthetic_filter import AestheticFilterStage  # noqa: F401
 from .clip_writer import ClipWriterStage  # noqa: F401
+from .clip_embedding import ClipFrameEmbeddingStage  # noqa: F401
 from .clip_stream_copy import ClipStreamCopyStage  # noqa: F401
 from .download import VideoDownloader  # noqa: F401
 from .fixed_stride import FixedStrideExtractorStage  # noqa: F401

@@ -281,3 +281,41 @@ def test_stage_outputs_pass_the_reference_style_task_compare():
     run_pipeline(other, [AestheticFilterStage(score_threshold=6.0, reduction="min", model=_FakeScorer())])
     fields = {d.field.split(".")[-1].split("[")[0] for _, d in compare_tasks(golden, other, atol=0.0)}
     assert fields and fields <= {"clips", "filtered_clips", "num_filtered_by_aesthetic", "num_passed"}
+
+
+def test_clip_frame_embedding_stage_contract():
+    """ClipFrameEmbeddingStage: the local producer of clip.openai_embedding (the OpenAIEmbeddingStage slot,
+    openai_embedding_stage.py:145-190): signature lookup at target_fps, the reference's error key / message, frames dropped after
+    a successful embedding, mean -> L2 pooling, batches shared across clips and tasks, model failures recorded per clip."""
+    from cosmos_curate_b200.stages import ClipFrameEmbeddingStage
+    from cosmos_curate_b200.stages.clip_embedding import pool_clip_embedding
+
+    class _FakeEmbedder(_FakeScorer):
+        def __call__(self, frames):
+            self.calls.append(frames.shape)
+            lvl = frames.reshape(len(frames), -1).mean(axis=1).astype(np.float32)
+            e = np.stack([np.cos(lvl / 100), np.sin(lvl / 100), np.zeros_like(lvl)], axis=1)  # unit-norm rows
+            return torch.from_numpy(e)
+
+    model = _FakeEmbedder()
+    stage = ClipFrameEmbeddingStage(target_fps=2.0, model=model, max_batch=8, stage_batch_size=2, log_stats=True)
+    assert stage._frame_extraction_signature == SIG2 and stage.resources.gpus == 0.25 and stage.stage_batch_size == 2
+    a, b = _clip([10, 50, 90], sigs=(SIG2,)), _clip([200, 220], sigs=(SIG1, SIG2))
+    missing = _clip([7], sigs=(SIG1,))
+    t1, t2 = _task([a, missing]), _task([b])
+    out = run_pipeline([t1, t2], [stage])
+    assert out is not None and model.was_setup and "ClipFrameEmbeddingStage" in t1.stage_perf and "ClipFrameEmbeddingStage" in t2.stage_perf
+    assert missing.errors == {"openai_embedding": "extracted frames missing"} and missing.openai_embedding is None and missing.extracted_frames
+    lv = np.array([10, 50, 90], np.float32)
+    want = pool_clip_embedding(np.stack([np.cos(lv / 100), np.sin(lv / 100), np.zeros(3, np.float32)], axis=1))
+    assert a.openai_embedding.dtype == np.float32 and np.allclose(a.openai_embedding, want, atol=1e-7) and abs(np.linalg.norm(a.openai_embedding) - 1) < 1e-6
+    assert b.openai_embedding is not None and not a.extracted_frames and not b.extracted_frames  # dropped (openai_embedding_stage.py:165)
+    assert [c[0] for c in model.calls] == [5]  # the five frames of both tasks' clips in ONE tower batch
+
+    class _Broken(_FakeScorer):
+        def __call__(self, frames):
+            raise RuntimeError("tower down")
+
+    c = _clip([1, 2], sigs=(SIG2,))
+    ClipFrameEmbeddingStage(model=_Broken()).process_data([_task([c])])
+    assert c.errors == {"openai_embedding": "tower down"} and c.openai_embedding is None and c.extracted_frames  # recorded, not raised; frames kept for a retry

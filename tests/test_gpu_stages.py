@@ -538,7 +538,7 @@ def test_local_split_pipeline_chain_from_file_to_dedup(ctx, tmp_path):
 def test_clip_frame_embedding_stage_on_gpu_matches_the_oracle_and_the_fused_stage(ctx):
     """ClipFrameExtractionStage(2 fps) -> ClipFrameEmbeddingStage: `clip.openai_embedding` against the fp32 oracle pooled the same
     way (mean -> L2), and against NvdecClipAestheticStage(write_embedding=True) at the same rate - the fused stage of the same
-    tower must land on the same vector (same frames, same kernels; batch composition may differ)."""
+    tower must land on the same vector within the u8 resize budget (same frames and tower; the resize kernel differs by input format)."""
     from cosmos_curate_b200.interfaces import run_pipeline
     from cosmos_curate_b200.models.clip import CLIPImageEmbeddings
     from cosmos_curate_b200.runtime import VitTower, get_context
@@ -568,4 +568,4 @@ def test_clip_frame_embedding_stage_on_gpu_matches_the_oracle_and_the_fused_stag
     fused = _clip_task(data)
     run_pipeline([fused], [NvdecClipAestheticStage(score_threshold=-9.0, reduction="mean", target_fps=2.0, write_embedding=True, max_batch=32, num_decoders=2, model=model)])
     f = fused.video.clips[0].openai_embedding
-    assert np.linalg.norm(f - a.openai_embedding) / np.linalg.norm(f) < 1e-5
+    assert np.linalg.norm(f - a.openai_embedding) / np.linalg.norm(f) < 1e-3  # NV12 surfaces -> tensor-pipe resize vs RGB frames -> SIMT resize: <= 1 LSB apart on a few pixels

@@ -9,6 +9,9 @@ files ClipWriterStage writes last - so a run killed between two clip chunks of a
                                     applies to the NEW videos, like the reference's
     order_video_paths               primary camera first, the rest sorted (:193-211)
     extract_multi_cam_split_tasks   one task per UUID-named session directory (:214-281)
+    write_split_summary             `summary.json`: totals + one record per input video aggregated over its clip-chunk summaries
+                                    (pipelines/video/read_write/summary_writers.py:127-262; captions / perf stats are other
+                                    stages' business)
 
 Object stores are out of this path's scope: every path is a local directory.
 """
@@ -116,3 +119,59 @@ def extract_multi_cam_split_tasks(sessions_prefix: str, primary_camera_keyword: 
             break
     logger.info(f"Extracted {len(tasks)} session tasks from {sessions_prefix}")
     return tasks
+
+
+CLIP_STATS_KEYS = ("num_clips_filtered_by_motion", "num_clips_filtered_by_aesthetic", "num_clips_filtered_by_qwen_classifier",
+                   "num_clips_filtered_by_qwen_semantic", "num_clips_filtered_by_artificial_text", "num_clips_passed", "num_clips_transcoded",
+                   "num_clips_with_embeddings", "num_clips_with_caption", "num_clips_with_webp")  # fmt: skip
+
+
+def write_split_summary(input_path: str, input_videos_relative: list[str], num_input_videos_selected: int, output_path: str, *,
+                        embedding_algorithm: str, limit: int = 0, pipeline_run_time: float = 0.0, video_bytes: int = 0, num_remuxed_videos: int = 0,
+                        multi_cam: bool = False) -> dict:  # fmt: skip
+    """Aggregates processed_videos/<rel>.json and processed_clip_chunks/<rel>_<k>.json into <output_path>/summary.json; returns it."""
+    out = pathlib.Path(output_path)
+    pv, pc = out / "processed_videos", out / "processed_clip_chunks"
+    listed = files_relative(pv)
+    sessions = sorted({f.split("/")[0] for f in listed}) if multi_cam else listed
+    summary: dict = {"num_input_videos": len(input_videos_relative), "num_input_videos_selected": num_input_videos_selected,
+                     "num_processed_videos": len(sessions), "embedding_algorithm": embedding_algorithm, "total_video_duration": 0, "total_clip_duration": 0,
+                     "max_clip_duration": 0, "pipeline_run_time": pipeline_run_time, "total_video_bytes": video_bytes, "num_remuxed_videos": num_remuxed_videos,
+                     "total_prompt_tokens": 0, "total_output_tokens": 0}  # fmt: skip
+    for key in CLIP_STATS_KEYS:
+        summary[f"total_{key}"] = 0
+    for video in input_videos_relative:
+        rec: dict = {"source_video": str(pathlib.Path(input_path) / video)}
+        summary[video] = rec
+        meta_path = pv / f"{video}.json"
+        if not meta_path.exists():
+            if limit == 0:
+                logger.error(f"video process-record {video} not found ???")
+            rec["processed"] = False
+            continue
+        meta = json.loads(meta_path.read_text())
+        chunks = []
+        for k in range(meta.get("num_clip_chunks", 0)):
+            cp = pc / f"{video}_{k}.json"
+            if cp.exists():
+                chunks.append(json.loads(cp.read_text()))
+            else:
+                logger.error(f"clip chunk record {cp} not found ???")
+        rec.update({"video_uuid": meta.get("video_uuid", "N/A"), "num_clip_chunks": len(chunks), "num_total_clips": meta.get("num_total_clips", "N/A"),
+                    "clips": [], "filtered_clips": []})  # fmt: skip
+        for key in CLIP_STATS_KEYS:
+            rec[key] = 0
+        for ch in chunks:
+            for key in CLIP_STATS_KEYS:
+                rec[key] += ch.get(key, 0)
+                summary[f"total_{key}"] += ch.get(key, 0)
+            rec["clips"].extend(ch.get("clips", []))
+            rec["filtered_clips"].extend(ch.get("filtered_clips", []))
+            summary["total_clip_duration"] += ch.get("total_clip_duration", 0)
+            summary["max_clip_duration"] = max(summary["max_clip_duration"], ch.get("max_clip_duration", 0))
+            summary["total_prompt_tokens"] += ch.get("total_prompt_tokens", 0)
+            summary["total_output_tokens"] += ch.get("total_output_tokens", 0)
+        summary["total_video_duration"] += meta.get("duration", 0) or 0
+    out.mkdir(parents=True, exist_ok=True)
+    (out / "summary.json").write_text(json.dumps(summary, indent=4))
+    return summary

@@ -69,3 +69,25 @@ def test_multi_camera_sessions(tmp_path):
         P.order_video_paths(["front_a.mp4", "front_b.mp4"], {".mp4"}, "front")
     with pytest.raises(ValueError, match="No primary camera"):
         P.order_video_paths(["rear.mp4"], {".mp4"}, "front")
+
+
+def test_split_summary_aggregates_the_writer_stage_outputs(tmp_path):
+    """summary.json (summary_writers.py:127-262) from the files ClipWriterStage wrote: totals, per-video records, unprocessed inputs."""
+    inp, out = tmp_path / "in", tmp_path / "out"
+
+    def chunk(name, k, n, n_pass, n_filt, dur):
+        mk = lambda i: Clip(uuid=uuid.uuid5(uuid.NAMESPACE_URL, f"{name}{k}{i}"), source_video=name, span=(0.0, dur))  # noqa: E731
+        v = Video(input_video=inp / name, clips=[mk(i) for i in range(n_pass)], filtered_clips=[mk(9 + i) for i in range(n_filt)], clip_chunk_index=k, num_clip_chunks=n,
+                  num_total_clips=7)
+        v.metadata.duration = 100.0
+        v.clip_stats.num_filtered_by_aesthetic = n_filt
+        return SplitPipeTask(session_id=name, video=v)
+
+    ClipWriterStage(str(out), str(inp), generate_embeddings=False).process_data([chunk("a.mp4", 0, 2, 3, 1, 4.0), chunk("a.mp4", 1, 2, 2, 1, 6.0), chunk("b.mp4", 0, 1, 1, 0, 2.5)])
+    s = P.write_split_summary(str(inp), ["a.mp4", "b.mp4", "c.mp4"], 3, str(out), embedding_algorithm="openai", limit=5, pipeline_run_time=1.5)
+    assert json.loads((out / "summary.json").read_text()) == s
+    assert (s["num_input_videos"], s["num_processed_videos"], s["total_num_clips_passed"], s["total_num_clips_filtered_by_aesthetic"]) == (3, 2, 6, 2)
+    assert s["total_video_duration"] == 200.0 and s["max_clip_duration"] == 6.0 and s["total_clip_duration"] == pytest.approx(4 * 4.0 + 3 * 6.0 + 2.5)
+    assert s["a.mp4"]["num_clip_chunks"] == 2 and len(s["a.mp4"]["clips"]) == 5 and len(s["a.mp4"]["filtered_clips"]) == 2 and s["a.mp4"]["num_total_clips"] == 7
+    assert s["a.mp4"]["video_uuid"] == str(uuid.uuid5(uuid.NAMESPACE_URL, str(inp / "a.mp4"))) and s["c.mp4"] == {"source_video": str(inp / "c.mp4"), "processed": False}
+    assert s["embedding_algorithm"] == "openai" and s["pipeline_run_time"] == 1.5

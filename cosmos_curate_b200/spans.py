@@ -45,37 +45,34 @@ def validate_video_timestamps(video_timestamps: list[np.ndarray]) -> None:
 
 
 def videos_timestamps(videos: list[Video]) -> list[np.ndarray]:
-    for video in videos:
-        if (video.timestamps is None or len(video.timestamps) == 0) and "timestamps" not in video.errors:
-            video.errors["timestamps"] = "missing"
-    missing = [v for v in videos if v.timestamps is None or len(v.timestamps) == 0]
-    if missing:
-        msg = f"Videos missing timestamps: {[str(v.input_video) for v in missing]}"
+    without = [v for v in videos if v.timestamps is None or len(v.timestamps) == 0]
+    for v in without:
+        v.errors.setdefault("timestamps", "missing")  # an earlier stage's message wins
+    if without:
+        msg = f"Videos missing timestamps: {[str(v.input_video) for v in without]}"
         raise ValueError(msg)
     return [v.timestamps for v in videos]
 
 
 def videos_durations(videos: list[Video]) -> list[float]:
-    def duration(video: Video) -> float:
-        num_frames, framerate = video.metadata.num_frames, video.metadata.framerate
-        if num_frames is None or framerate is None or framerate <= 0:
-            return -1.0
-        return float(num_frames / framerate)
-
-    return [duration(v) for v in videos]
+    out = []
+    for v in videos:
+        n, fps = v.metadata.num_frames, v.metadata.framerate
+        out.append(float(n / fps) if n is not None and fps is not None and fps > 0 else -1.0)
+    return out
 
 
 def make_spans_fixed_stride(start_s: float, end_s: float, clip_len_s: float, clip_stride_s: float, min_clip_length_s: float) -> list[tuple[float, float]]:
     """Windows of clip_len_s every clip_stride_s from start_s while the window START is before end_s; the last ones are cut at
     end_s and kept only if still >= min_clip_length_s long.  The start accumulates by repeated addition (float semantics)."""
-    spans: list[tuple[float, float]] = []
-    start_span_s = start_s
-    while start_span_s < end_s:
-        end_span_s = min(start_span_s + clip_len_s, end_s)
-        if (end_span_s - start_span_s) >= min_clip_length_s:
-            spans.append((start_span_s, end_span_s))
-        start_span_s += clip_stride_s
-    return spans
+    out: list[tuple[float, float]] = []
+    t = start_s
+    while t < end_s:
+        stop = end_s if t + clip_len_s > end_s else t + clip_len_s  # == min(t + clip_len_s, end_s)
+        if stop - t >= min_clip_length_s:
+            out.append((t, stop))
+        t += clip_stride_s  # accumulated, never recomputed as start + k * stride: the reference's floats depend on it
+    return out
 
 
 def make_clip_uuids(session_id: str, spans: list[tuple[float, float]]) -> list[UUID]:
@@ -88,23 +85,21 @@ def populate_clips_fixed_stride(videos: list[Video], session_id: str, clip_len_s
     The window is [0, min over videos of (first timestamp + duration) - max first timestamp), the reference's backwards-compatible
     choice (:582-638)."""
     durations = videos_durations(videos)
-    if len([d for d in durations if d > 0]) < len(videos):
+    if any(d <= 0 for d in durations):
         msg = "Some videos have invalid (zero or negative) duration"
         raise ValueError(msg)
-    video_ts = videos_timestamps(videos)
-    validate_video_timestamps(video_ts)
-    starts_s = [float(ts[0]) for ts in video_ts]
-    ends_s = [t + d for t, d in zip(starts_s, durations, strict=True)]
-    start_s = max(starts_s)
-    if start_s > 0.1:  # noqa: PLR2004
-        logger.warning(f"Videos start at {start_s:.2f}s (not 0), but duration-based end_s assumes start=0. This may cause unexpected span boundaries.")
-    end_s = min(ends_s) - start_s
-    spans = make_spans_fixed_stride(0.0, end_s, clip_len_s, clip_stride_s, min_clip_length_s)
-    if limit_clips > 0:
-        spans = spans[:limit_clips]
-    for span, clip_uuid in zip(spans, make_clip_uuids(session_id, spans), strict=True):
-        for video in videos:
-            video.clips.append(Clip(uuid=clip_uuid, source_video=str(video.input_video), span=span))
+    stamps = videos_timestamps(videos)
+    validate_video_timestamps(stamps)
+    first = [float(ts[0]) for ts in stamps]
+    latest_start = max(first)
+    if latest_start > 0.1:  # noqa: PLR2004
+        logger.warning(f"cameras start at {latest_start:.2f} s, but the window below is measured from 0: span boundaries may surprise")
+    window_end = min(t0 + d for t0, d in zip(first, durations, strict=True)) - latest_start
+    spans = make_spans_fixed_stride(0.0, window_end, clip_len_s, clip_stride_s, min_clip_length_s)
+    spans = spans[:limit_clips] if limit_clips > 0 else spans
+    ids = make_clip_uuids(session_id, spans)
+    for video in videos:
+        video.clips.extend(Clip(uuid=u, source_video=str(video.input_video), span=sp) for u, sp in zip(ids, spans, strict=True))
 
 
 def check_clip_time_alignment(clips_per_video: list[list[Clip]]) -> list[int]:

@@ -32,6 +32,16 @@ def shard_by_weight(weights, world_size: int) -> list[list[int]]:
     return out
 
 
+def shard_tasks(tasks: list, world_size: int, rank: int) -> list:
+    """This rank's share of `tasks`, balanced by `PipelineTask.weight` (a SplitPipeTask's weight is the summed duration of its videos
+    normalised to 5 minutes x the fraction of clips it carries, data_model.py:509-523, 779-790).  Every rank computes the same
+    partition from the same list: no communication; input order is kept within a rank."""
+    if not 0 <= rank < world_size:
+        msg = f"rank {rank} outside world of {world_size}"
+        raise ValueError(msg)
+    return [tasks[i] for i in shard_by_weight([t.weight for t in tasks], world_size)[rank]]
+
+
 def clip_weight(width: int, height: int, n_frames: int) -> float:
     """Decode cost proxy: pixels that NVDEC has to produce."""
     return float(width) * float(height) * float(n_frames)

@@ -219,6 +219,18 @@ def test_shard_by_weight_is_balanced_and_complete():
     assert sharding.rank_slice(10, 1, 4).tolist() == [1, 5, 9]
     with pytest.raises(ValueError):
         sharding.shard_by_weight([1.0], 0)
+    # tasks sharded by their own weight (Video.weight: duration / 300 x fraction of clips carried)
+    tasks = []
+    for i, dur in enumerate([600.0, 30.0, 30.0, 300.0, 45.0, 900.0, 10.0]):
+        v = Video(input_video=f"v{i}.mp4")
+        v.metadata.size, v.metadata.duration = 1, dur
+        tasks.append(SplitPipeTask(session_id=f"s{i}", video=v))
+    shares = [sharding.shard_tasks(tasks, 3, r) for r in range(3)]
+    assert sorted(t.session_id for sh in shares for t in sh) == sorted(t.session_id for t in tasks)  # a partition
+    assert [t.session_id for t in shares[0]] == ["s5"] and max(sum(t.weight for t in sh) for sh in shares) == pytest.approx(3.0)  # the 15-minute video alone
+    assert all([t.session_id for t in sh] == sorted((t.session_id for t in sh), key=lambda s: int(s[1:])) for sh in shares)  # input order kept
+    with pytest.raises(ValueError):
+        sharding.shard_tasks(tasks, 3, 3)
 
 
 def _gloo_worker(rank: int, world: int, port: int, q):

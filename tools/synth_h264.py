@@ -171,15 +171,18 @@ def full(typ: bytes, version: int, flags: int, *payload: bytes) -> bytes:
     return box(typ, struct.pack(">I", (version << 24) | flags), *payload)
 
 
-def mux_mp4(samples: list[bytes], sync: list[bool], sps_nal: bytes, pps_nal: bytes, width: int, height: int, fps_num: int, fps_den: int = 1) -> bytes:
+def mux_mp4(samples: list[bytes], sync: list[bool], sps_nal: bytes, pps_nal: bytes, width: int, height: int, fps_num: int, fps_den: int = 1,
+            sample_entry: bytes | None = None) -> bytes:
+    """`sample_entry`: a complete visual sample entry box (e.g. hvc1 from tools/synth_hevc) instead of the avc1 entry built here."""
     timescale, delta = fps_num * 512 if fps_den == 1 else fps_num, 512 if fps_den == 1 else fps_den
     n = len(samples)
     duration = n * delta
-    avcc = box(b"avcC", bytes([1, sps_nal[1], sps_nal[2], sps_nal[3], 0xFF, 0xE1]), struct.pack(">H", len(sps_nal)), sps_nal, bytes([1]),
-               struct.pack(">H", len(pps_nal)), pps_nal)  # fmt: skip
-    avc1 = box(b"avc1", b"\x00" * 6, struct.pack(">H", 1), b"\x00" * 16, struct.pack(">HH", width, height), struct.pack(">II", 0x00480000, 0x00480000),
-               b"\x00" * 4, struct.pack(">H", 1), b"\x00" * 32, struct.pack(">Hh", 0x18, -1), avcc)  # fmt: skip
-    stsd = full(b"stsd", 0, 0, struct.pack(">I", 1), avc1)
+    if sample_entry is None:
+        avcc = box(b"avcC", bytes([1, sps_nal[1], sps_nal[2], sps_nal[3], 0xFF, 0xE1]), struct.pack(">H", len(sps_nal)), sps_nal, bytes([1]),
+                   struct.pack(">H", len(pps_nal)), pps_nal)  # fmt: skip
+        sample_entry = box(b"avc1", b"\x00" * 6, struct.pack(">H", 1), b"\x00" * 16, struct.pack(">HH", width, height), struct.pack(">II", 0x00480000, 0x00480000),
+                           b"\x00" * 4, struct.pack(">H", 1), b"\x00" * 32, struct.pack(">Hh", 0x18, -1), avcc)  # fmt: skip
+    stsd = full(b"stsd", 0, 0, struct.pack(">I", 1), sample_entry)
     stts = full(b"stts", 0, 0, struct.pack(">III", 1, n, delta))
     sync_ids = [i + 1 for i, s in enumerate(sync) if s]
     stss = full(b"stss", 0, 0, struct.pack(">I", len(sync_ids)), b"".join(struct.pack(">I", i) for i in sync_ids))

@@ -79,3 +79,21 @@ def test_compare_values_agrees_with_the_reference(golden, candidate, atol):
     for g, c in ((golden, candidate), (golden, golden)):
         want, got = [key(d) for d in ref("t", g, c, atol=atol)], [key(d) for d in C.compare_values("t", g, c, atol=atol)]
         assert repr(got) == repr(want)  # repr: NaN-carrying details compare equal as text
+
+
+@_cfg
+@given(track=st.lists(st.sampled_from([0, 0, 0, 0, 1]), min_size=1, max_size=600), entire=st.booleans(), min_len=st.one_of(st.none(), st.integers(1, 80)),
+       max_len=st.one_of(st.none(), st.integers(1, 200)), mode=st.sampled_from(["truncate", "stride"]), crop=st.one_of(st.none(), st.integers(0, 20)))
+def test_shot_logic_agrees_with_the_reference(track, entire, min_len, max_len, mode, crop):
+    """0/1 transition tracks -> scenes -> filtered scenes: transnetv2_extraction_stages._get_scenes / _get_filtered_scenes."""
+    from cosmos_curate_b200 import shots
+
+    f = ref_import.transnetv2_stage_functions()
+    pred = np.array(track, dtype=np.uint8).reshape(-1, 1)
+    want = f["_get_scenes"](pred, entire_scene_as_clip=entire)
+    got = shots.scenes_from_predictions(pred, entire_scene_as_clip=entire)
+    assert np.array_equal(got, want) and got.dtype == want.dtype
+    if len(want):
+        want_f = f["_get_filtered_scenes"](want.copy(), min_length=min_len, max_length=max_len, max_length_mode=mode, crop_length=crop)
+        got_f = shots.filter_scenes(got.copy(), min_length=min_len, max_length=max_len, max_length_mode=mode, crop_length=crop)
+        assert np.array_equal(got_f, want_f)

@@ -97,3 +97,17 @@ def test_shot_logic_agrees_with_the_reference(track, entire, min_len, max_len, m
         want_f = f["_get_filtered_scenes"](want.copy(), min_length=min_len, max_length=max_len, max_length_mode=mode, crop_length=crop)
         got_f = shots.filter_scenes(got.copy(), min_length=min_len, max_length=max_len, max_length_mode=mode, crop_length=crop)
         assert np.array_equal(got_f, want_f)
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(h=st.integers(1, 260), w=st.integers(1, 260), th=st.integers(1, 72), tw=st.integers(1, 72), n=st.integers(8, 19), seed=st.integers(0, 2**31 - 1))
+def test_video_tube_oracle_agrees_with_the_reference_formulation(h, w, th, tw, n, seed):
+    """oracle/video_tube.py vs InternVideo2MultiModality._construct_frames (cv2.resize + numpy) on arbitrary sizes, every float32 bit:
+    up- and down-scaling, 1-pixel sources and targets, the exact-2x INTER_AREA reroute, the copy for equal sizes."""
+    from oracle import video_tube as T
+
+    rng = np.random.default_rng(seed)
+    frames = [rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8) for _ in range(n)]
+    want = ref_import.internvideo2_formulator()._construct_frames(frames, fnum=8, target_size=(tw, th))
+    got = T.construct_frames(frames, fnum=8, target_size=(tw, th))
+    assert got.shape == want.shape and np.array_equal(got, want)
